@@ -1,0 +1,192 @@
+/*
+ * raindrop_b200.h -- C ABI of librd_b200.so (sm_100a), the device side of the Raindrop hot path.
+ *
+ * The reference (mims-harvard/Raindrop) is pure Python; it has no FFI of its own.  The boundary
+ * a maintainer binds is therefore the set of Python call sites listed beside each entry point
+ * (paths relative to the reference tree).  Our `raindrop_b200/models_rd.py` binds them through
+ * ctypes; INTEGRATION.md shows the same stubs applied to the reference's own files.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host; all tensors are dense,
+ *     row-major fp32 (indices int64) exactly as the reference's torch tensors are laid out;
+ *   - `stream` is a cudaStream_t passed as void*; every call is stream-ordered, allocation-free
+ *     and sync-free (CUDA-graph capturable).  Scratch memory is provided by the caller: query
+ *     the size first;
+ *   - return value 0 = ok, negative = error (rd_last_error_string() describes it); nothing
+ *     throws across the ABI.
+ */
+#ifndef RAINDROP_B200_H
+#define RAINDROP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RD_ABI_VERSION 1
+#define RD_MAX_LAYERS 8
+#define RD_D_PE 16 /* d_pe, code/models_rd.py:215 */
+
+/* Shapes of one Raindrop_v2 instance + one batch (code/models_rd.py:208-264, 278-284). */
+typedef struct rd_dims {
+  int32_t B;         /* samples in this batch (any >= 1)                                  */
+  int32_t T;         /* max_len                                                           */
+  int32_t N;         /* d_inp = sensors                                                   */
+  int32_t d_ob;      /* d_model / d_inp (4 in code/Raindrop.py:125)                       */
+  int32_t nhead;     /* temporal attention heads                                          */
+  int32_t nhid;      /* feed-forward width                                                */
+  int32_t nlayers;   /* encoder layers (<= RD_MAX_LAYERS)                                 */
+  int32_t d_static;  /* 0 = no static branch (static=False)                               */
+  int32_t n_classes;
+  int32_t training;  /* 1: dropout active (model.train()), 0: eval                        */
+  float dropout_p;   /* one p for every dropout site, as in the reference                 */
+  float ln_eps;      /* 1e-5                                                              */
+  float pe_timescales[RD_D_PE / 2]; /* max_len ** linspace(0,1,8) computed in fp64 on host,
+                                       cast to fp32 (code/models_rd.py:31,34)             */
+} rd_dims;
+
+/* Parameters that take part in the live path.  Names = state-dict keys. */
+typedef struct rd_encoder_layer_params {
+  const float* in_proj_weight;  /* [3D, D] */
+  const float* in_proj_bias;    /* [3D]    */
+  const float* out_proj_weight; /* [D, D]  */
+  const float* out_proj_bias;   /* [D]     */
+  const float* linear1_weight;  /* [nhid, D] */
+  const float* linear1_bias;    /* [nhid]  */
+  const float* linear2_weight;  /* [D, nhid] */
+  const float* linear2_bias;    /* [D]     */
+  const float* norm1_weight;    /* [D] */
+  const float* norm1_bias;
+  const float* norm2_weight;
+  const float* norm2_bias;
+} rd_encoder_layer_params;
+
+typedef struct rd_params {
+  const float* R_u;             /* [1, N*d_ob]  plain tensor, code/models_rd.py:241          */
+  const float* emb_weight;      /* [N, d_static] or NULL                                     */
+  const float* emb_bias;        /* [N] or NULL                                               */
+  const float* ob1_value_weight;/* ob_propagation.lin_value.weight        [C, C], C=T*d_ob   */
+  const float* ob1_value_bias;  /* [C] */
+  const float* ob2_value_weight;/* ob_propagation_layer2.lin_value.weight [C, C]             */
+  const float* ob2_value_bias;
+  const float* mlp0_weight;     /* mlp_static.0.weight [Df, Df], Df = D + (static ? N : 0)   */
+  const float* mlp0_bias;
+  const float* mlp2_weight;     /* mlp_static.2.weight [n_classes, Df]                       */
+  const float* mlp2_bias;
+  rd_encoder_layer_params layer[RD_MAX_LAYERS];
+} rd_params;
+
+/* Same members, writable: gradients (written, not accumulated).  R_u gets no gradient. */
+typedef struct rd_encoder_layer_grads {
+  float* in_proj_weight; float* in_proj_bias; float* out_proj_weight; float* out_proj_bias;
+  float* linear1_weight; float* linear1_bias; float* linear2_weight; float* linear2_bias;
+  float* norm1_weight; float* norm1_bias; float* norm2_weight; float* norm2_bias;
+} rd_encoder_layer_grads;
+
+typedef struct rd_grads {
+  float* emb_weight; float* emb_bias;
+  float* ob1_value_weight; float* ob1_value_bias;
+  float* ob2_value_weight; float* ob2_value_bias;
+  float* mlp0_weight; float* mlp0_bias; float* mlp2_weight; float* mlp2_bias;
+  rd_encoder_layer_grads layer[RD_MAX_LAYERS];
+} rd_grads;
+
+/* Named views into the activation workspace written by rd_raindrop_v2_fwd (for parity tests). */
+enum rd_ws_buffer {
+  RD_WS_X0 = 0,    /* lifted input   [B*N, C]  (code/models_rd.py:290-296,326-327)          */
+  RD_WS_H1 = 1,    /* layer-1 output [B*N, C]  (code/models_rd.py:329-330)                  */
+  RD_WS_ENC_IN = 2,/* cat(obs, pe)   [T, B, D] (code/models_rd.py:341,354)                  */
+  RD_WS_ENC_OUT = 3,/* r_out         [T, B, D] (code/models_rd.py:358)                      */
+  RD_WS_FEAT = 4,  /* cat(pooled, emb) [B, Df] (code/models_rd.py:379,384)                  */
+  RD_WS_RNG = 5    /* 2 x uint64 (seed, step counter) captured by this forward              */
+};
+
+int rd_abi_version(void);
+const char* rd_last_error_string(void);
+
+/* ---- graph prologue --------------------------------------------------------------------
+ * s[n] = sum_{e: tgt[e]==n} softmax_{e->n}(w)   with PyG's  exp(w-max)/(sum+1e-16).
+ * Replaces `softmax(gamma, index)` + `scatter(..., reduce='add')` of
+ * code/Ob_propagation.py:195,226-228 for the live path where the message depends on the
+ * target only (code/Ob_propagation.py:200).  edge_tgt = edge_index[1] (code/models_rd.py:310). */
+int rd_node_scale(const int64_t* edge_tgt, const float* edge_w, int32_t E, int32_t N,
+                  float* node_scale, void* stream);
+
+/* ---- one observation-propagation layer (operator level) -----------------------------------
+ * out[r, :] = relu(x[r, :] . W^T + b) * node_scale[r % scale_mod]      x, out: [rows, C]
+ * Replaces Observation_progation.forward with use_beta=False (code/Ob_propagation.py:94-132,
+ * 157-160,187-211,213-228) for `rows / N` samples at once (code/models_rd.py:322-336). */
+int rd_obprop_fwd(const float* x, const float* weight, const float* bias, const float* node_scale,
+                  int32_t scale_mod, int64_t rows, int32_t C, float* out, void* stream);
+
+/* Backward of the above.  d_out, out: [rows, C].  Writes d_x (may be NULL), d_weight, d_bias.
+ * scratch: rd_obprop_bwd_scratch_bytes(rows, C) bytes. */
+size_t rd_obprop_bwd_scratch_bytes(int64_t rows, int32_t C);
+int rd_obprop_bwd(const float* x, const float* out, const float* d_out, const float* weight,
+                  const float* node_scale, int32_t scale_mod, int64_t rows, int32_t C,
+                  float* d_x, float* d_weight, float* d_bias, void* scratch, void* stream);
+
+/* ---- whole Raindrop_v2 forward / backward ---------------------------------------------------
+ * Replaces Raindrop_v2.forward (code/models_rd.py:278-387) for the live configuration
+ * (sensor_wise_mask=False, aggreg='mean', use_beta=False) and its autograd backward
+ * (code/Raindrop.py:323).
+ *   src     [T, B, 2N]   times [T, B]   lengths [B] int64   statics [B, d_static] or NULL
+ *   node_scale [N]       from rd_node_scale on the model's graph
+ *   rng_state  2 x uint64 on the device: {seed, counter}; the forward copies it into the
+ *              workspace and increments the counter (only when training && dropout_p > 0)
+ *   workspace  rd_workspace_bytes(dims) bytes, kept by the caller until backward is done
+ *   logits  [B, n_classes]                                                                */
+size_t rd_workspace_bytes(const rd_dims* dims);
+size_t rd_backward_scratch_bytes(const rd_dims* dims);
+/* offset (bytes) and element count of a named buffer inside the workspace; -1 if unknown */
+int64_t rd_workspace_offset(const rd_dims* dims, int32_t which, int64_t* n_floats);
+
+int rd_raindrop_v2_fwd(const rd_dims* dims, const rd_params* params, const float* src,
+                       const float* statics, const float* times, const int64_t* lengths,
+                       const float* node_scale, uint64_t* rng_state, void* workspace,
+                       float* logits, void* stream);
+
+int rd_raindrop_v2_bwd(const rd_dims* dims, const rd_params* params, const float* statics,
+                       const int64_t* lengths, const float* node_scale, const void* workspace,
+                       const float* d_logits, const rd_grads* grads, void* scratch, void* stream);
+
+/* ---- pieces exposed on their own (module-level drop-ins and tests) -------------------------
+ * pe[t,b,:] = [sin(times/ts_k), cos(times/ts_k)]  -> out[(t*B+b)*ld + col0 + 0..15]
+ * Replaces PositionalEncodingTF.getPE (code/models_rd.py:28-37) without the host round trip. */
+int rd_positional_encoding(const float* times, int64_t n_tokens, const float* timescales_host,
+                           float* out, int64_t ld, int32_t col0, void* stream);
+
+/* TransformerConv.forward (code/transformer_conv.py:139-207), concat=True, root_weight=True,
+ * beta=False, no edge features.  x [n_nodes, in]; weights [H*F, in]; edge_w may be NULL (then the
+ * logits are q_i.k_j/sqrt(F)).  out [n_nodes, H*F]; alpha [E, H] (post-softmax, as returned).
+ * scratch: rd_transformer_conv_scratch_bytes(...) */
+size_t rd_transformer_conv_scratch_bytes(int32_t n_nodes, int32_t in_ch, int32_t heads, int32_t out_ch,
+                                         int32_t E);
+int rd_transformer_conv_fwd(const float* x, int32_t n_nodes, int32_t in_ch, int32_t heads,
+                            int32_t out_ch, const int64_t* edge_src, const int64_t* edge_tgt,
+                            const float* edge_w, int32_t E, const float* wq, const float* bq,
+                            const float* wk, const float* bk, const float* wv, const float* bv,
+                            const float* ws, const float* bs, float* out, float* alpha,
+                            void* scratch, void* stream);
+
+/* ---- training-step helpers (the caller-side ops of code/Raindrop.py:321-324) ----------------
+ * mean cross entropy + d(loss)/d(logits), torch.nn.CrossEntropyLoss semantics. */
+int rd_cross_entropy_fwd_bwd(const float* logits, const int64_t* y, int32_t B, int32_t n_classes,
+                             float* loss, float* d_logits, void* stream);
+/* torch.optim.Adam (no weight decay, no amsgrad) on flat buffers; `step` is a device counter
+ * incremented by the call; grad is multiplied by grad_scale first (1/world_size after a sum). */
+int rd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
+                 float lr, float beta1, float beta2, float eps, float grad_scale, int64_t* step,
+                 void* stream);
+
+/* debug: materialise the dropout keep/scale mask (0 or 1/(1-p)) of one dropout site, so tests can
+ * replay train-mode forward/backward in the oracle with identical masks.  `site` ids in DESIGN.md. */
+int rd_debug_dropout_mask(const uint64_t* rng_captured, uint32_t site, int64_t n, float p, float* out,
+                          void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RAINDROP_B200_H */

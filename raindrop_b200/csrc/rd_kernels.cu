@@ -1,0 +1,438 @@
+// Non-GEMM kernels of the Raindrop hot path: input lift, positional encoding, graph prologue,
+// LayerNorm, masked attention softmax, masked mean, loss and optimiser.  All are HBM-bound
+// streaming kernels: coalesced along the fastest tensor dimension, one warp per row for the
+// row-wise reductions (warp-shuffle, no shared memory), grid sized from the element count.
+#include <stdarg.h>
+#include <string.h>
+
+#include "rd_kernels.cuh"
+
+namespace rd {
+
+// ---- error plumbing ---------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+const char* last_error() { return g_err; }
+int check_launch(const char* what) {
+  cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    set_error("%s: %s", what, cudaGetErrorString(e));
+    cudaGetLastError();
+    return -1;
+  }
+  return 0;
+}
+
+namespace {
+
+constexpr int TPB = 256;
+inline unsigned blocks_for(int64_t n, int tpb = TPB) { return (unsigned)ceil_div(n, tpb); }
+
+__global__ void rng_capture_kernel(uint64_t* state, uint64_t* cap, int advance) {
+  cap[0] = state[0];
+  cap[1] = state[1];
+  if (advance) state[1] = state[1] + 1;
+}
+
+__global__ void lift_kernel(const float* __restrict__ src, const float* __restrict__ R_u, int B, int T, int N,
+                            int d_ob, float drop_p, const uint64_t* __restrict__ rng, float* __restrict__ X0) {
+  const long long C = (long long)T * d_ob;
+  const long long total = (long long)B * N * C;
+  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= total) return;
+  long long row = o / C;
+  int c = (int)(o - row * C);
+  int b = (int)(row / N), n = (int)(row - (long long)b * N);
+  int t = c / d_ob, k = c - t * d_ob;
+  float v = __ldg(src + ((long long)t * B + b) * (2 * N) + n) * __ldg(R_u + n * d_ob + k);
+  v = fmaxf(v, 0.f);
+  if (drop_p > 0.f) {
+    uint64_t idx = ((uint64_t)t * B + b) * (uint64_t)(N * d_ob) + (uint64_t)(n * d_ob + k);
+    v *= dropout_scale(rng, SITE_LIFT, idx, drop_p, 1.f / (1.f - drop_p));
+  }
+  X0[o] = v;
+}
+
+struct TS8 { float v[8]; };
+__global__ void posenc_kernel(const float* __restrict__ times, long long n_tokens, TS8 ts, float* __restrict__ out,
+                              long long ld, int col0) {
+  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_tokens * 16) return;
+  long long tok = o >> 4;
+  int j = (int)(o & 15);
+  float scaled = __ldg(times + tok) / ts.v[j & 7];
+  out[tok * ld + col0 + j] = (j < 8) ? sinf(scaled) : cosf(scaled);
+}
+
+// one warp per node: segment max, then sum of exp, then s = sum(exp / (sum + 1e-16))
+__global__ void node_scale_kernel(const int64_t* __restrict__ tgt, const float* __restrict__ w, int E, int N,
+                                  float* __restrict__ s) {
+  int node = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (node >= N) return;
+  float mx = -INFINITY;
+  for (int e = lane; e < E; e += 32)
+    if (tgt[e] == node) mx = fmaxf(mx, w[e]);
+  mx = warp_max(mx);
+  if (mx == -INFINITY) {  // no incoming edge: scatter-add leaves the row at exactly zero
+    if (lane == 0) s[node] = 0.f;
+    return;
+  }
+  float sum = 0.f;
+  for (int e = lane; e < E; e += 32)
+    if (tgt[e] == node) sum += expf(w[e] - mx);
+  sum = warp_sum(sum);
+  float den = sum + 1e-16f;
+  float acc = 0.f;
+  for (int e = lane; e < E; e += 32)
+    if (tgt[e] == node) acc += expf(w[e] - mx) / den;
+  acc = warp_sum(acc);
+  if (lane == 0) s[node] = acc;
+}
+
+__global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, long long rows, int D, float eps,
+                                     float* __restrict__ y, float* __restrict__ stats) {
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * D;
+  float s = 0.f;
+  for (int j = lane; j < D; j += 32) s += xr[j];
+  float mean = warp_sum(s) / (float)D;
+  float q = 0.f;
+  for (int j = lane; j < D; j += 32) { float d = xr[j] - mean; q += d * d; }
+  float var = warp_sum(q) / (float)D;
+  float rstd = 1.f / sqrtf(var + eps);
+  float* yr = y + row * D;
+  for (int j = lane; j < D; j += 32) yr[j] = (xr[j] - mean) * rstd * __ldg(gamma + j) + __ldg(beta + j);
+  if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
+}
+
+__global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                        const float* __restrict__ gamma, const float* __restrict__ dy,
+                                        long long rows, int D, float* __restrict__ dx) {
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + row * D;
+  const float* dyr = dy + row * D;
+  float mean = stats[2 * row], rstd = stats[2 * row + 1];
+  float s1 = 0.f, s2 = 0.f;
+  for (int j = lane; j < D; j += 32) {
+    float g = dyr[j] * __ldg(gamma + j);
+    float xh = (xr[j] - mean) * rstd;
+    s1 += g;
+    s2 += g * xh;
+  }
+  s1 = warp_sum(s1) / (float)D;
+  s2 = warp_sum(s2) / (float)D;
+  float* dxr = dx + row * D;
+  for (int j = lane; j < D; j += 32) {
+    float g = dyr[j] * __ldg(gamma + j);
+    float xh = (xr[j] - mean) * rstd;
+    dxr[j] = rstd * (g - s1 - xh * s2);
+  }
+}
+
+constexpr int LN_ROWS = 256;
+__global__ void layernorm_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ stats,
+                                           const float* __restrict__ dy, long long rows, int D,
+                                           float* __restrict__ partial) {
+  int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= D) return;
+  long long r0 = (long long)blockIdx.y * LN_ROWS, r1 = min(rows, r0 + LN_ROWS);
+  float dg = 0.f, db = 0.f;
+  for (long long r = r0; r < r1; ++r) {
+    float d = dy[r * D + j];
+    dg += d * (x[r * D + j] - stats[2 * r]) * stats[2 * r + 1];
+    db += d;
+  }
+  partial[(long long)blockIdx.y * D + j] = dg;                  // [chunks][D] for dgamma
+  partial[((long long)gridDim.y + blockIdx.y) * D + j] = db;    // then [chunks][D] for dbeta
+}
+
+__global__ void attn_softmax_fwd_kernel(float* __restrict__ S, const int64_t* __restrict__ lengths, int B, int H,
+                                        int T, float drop_p, const uint64_t* __restrict__ rng, uint32_t site,
+                                        float* __restrict__ Pd) {
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  long long rows = (long long)B * H * T;
+  if (row >= rows) return;
+  int b = (int)(row / ((long long)H * T));
+  long long len = lengths[b];
+  int nv = (int)(len < T ? (len < 0 ? 0 : len) : T);
+  float* sr = S + row * T;
+  float mx = -INFINITY;
+  for (int j = lane; j < nv; j += 32) mx = fmaxf(mx, sr[j]);
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int j = lane; j < nv; j += 32) sum += expf(sr[j] - mx);
+  sum = warp_sum(sum);
+  float inv = nv > 0 ? 1.f / sum : 0.f;
+  float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  for (int j = lane; j < T; j += 32) {
+    float p = j < nv ? expf(sr[j] - mx) * inv : 0.f;
+    sr[j] = p;
+    if (Pd) {
+      float m = drop_p > 0.f ? dropout_scale(rng, site, (uint64_t)row * T + j, drop_p, ik) : 1.f;
+      Pd[row * T + j] = p * m;
+    }
+  }
+}
+
+__global__ void attn_softmax_bwd_kernel(const float* __restrict__ P, float* __restrict__ dP, long long rows, int T,
+                                        float drop_p, const uint64_t* __restrict__ rng, uint32_t site) {
+  long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* pr = P + row * T;
+  float* dr = dP + row * T;
+  float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float dot = 0.f;
+  for (int j = lane; j < T; j += 32) {
+    float m = drop_p > 0.f ? dropout_scale(rng, site, (uint64_t)row * T + j, drop_p, ik) : 1.f;
+    dot += dr[j] * m * pr[j];
+  }
+  dot = warp_sum(dot);
+  for (int j = lane; j < T; j += 32) {
+    float m = drop_p > 0.f ? dropout_scale(rng, site, (uint64_t)row * T + j, drop_p, ik) : 1.f;
+    dr[j] = pr[j] * (dr[j] * m - dot);
+  }
+}
+
+__global__ void masked_mean_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengths, int T, int B,
+                                       int D, float* __restrict__ out, long long ld) {
+  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (long long)B * D) return;
+  int b = (int)(o / D), d = (int)(o - (long long)b * D);
+  long long len = lengths[b];
+  int nv = (int)(len < T ? (len < 0 ? 0 : len) : T);
+  float s = 0.f;
+  for (int t = 0; t < nv; ++t) s += x[((long long)t * B + b) * D + d];
+  out[(long long)b * ld + d] = s / (float)(len + 1);
+}
+
+__global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, long long ld,
+                                       const int64_t* __restrict__ lengths, int T, int B, int D,
+                                       float* __restrict__ dx) {
+  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (long long)T * B * D) return;
+  int d = (int)(o % D);
+  long long tb = o / D;
+  int b = (int)(tb % B), t = (int)(tb / B);
+  long long len = lengths[b];
+  dx[o] = (t < len) ? dout[(long long)b * ld + d] / (float)(len + 1) : 0.f;
+}
+
+__global__ void obprop_out_grad_kernel(const float* __restrict__ dZ, const float* __restrict__ Z,
+                                       const float* __restrict__ s, int B, int T, int N, int d_ob, int D,
+                                       float* __restrict__ dZ2) {
+  const long long C = (long long)T * d_ob;
+  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (long long)B * N * C) return;
+  long long row = o / C;
+  int c = (int)(o - row * C);
+  int b = (int)(row / N), n = (int)(row - (long long)b * N);
+  int t = c / d_ob, k = c - t * d_ob;
+  long long zi = ((long long)t * B + b) * D + n * d_ob + k;
+  dZ2[o] = (Z[zi] > 0.f) ? dZ[zi] * __ldg(s + n) : 0.f;
+}
+
+__global__ void apply_dropout_kernel(const float* __restrict__ x, long long n, float p,
+                                     const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float xv = x ? x[i] : 1.f;
+  y[i] = xv * dropout_scale(rng, site, (uint64_t)i, p, 1.f / (1.f - p));
+}
+
+__global__ void relu_scale_bwd_kernel(const float* __restrict__ d_out, const float* __restrict__ out,
+                                      const float* __restrict__ scale, int mod, long long rows, int C,
+                                      float* __restrict__ d_pre) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  long long r = i / C;
+  d_pre[i] = out[i] > 0.f ? d_out[i] * __ldg(scale + (r % mod)) : 0.f;
+}
+
+__global__ void cross_entropy_kernel(const float* __restrict__ logits, const int64_t* __restrict__ y, int B, int ncls,
+                                     float* __restrict__ loss, float* __restrict__ dlogits) {
+  __shared__ float red[TPB / 32];
+  float local = 0.f;
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
+    const float* l = logits + (long long)b * ncls;
+    float mx = -INFINITY;
+    for (int c = 0; c < ncls; ++c) mx = fmaxf(mx, l[c]);
+    float sum = 0.f;
+    for (int c = 0; c < ncls; ++c) sum += expf(l[c] - mx);
+    float lse = mx + logf(sum);
+    int yy = (int)y[b];
+    local += lse - l[yy];
+    if (dlogits) {
+      float invB = 1.f / (float)B;
+      for (int c = 0; c < ncls; ++c)
+        dlogits[(long long)b * ncls + c] = (expf(l[c] - lse) - (c == yy ? 1.f : 0.f)) * invB;
+    }
+  }
+  local = warp_sum(local);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = local;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float s = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += red[w];
+    *loss = s / (float)B;
+  }
+}
+
+__global__ void adam_tick_kernel(int64_t* step) { *step = *step + 1; }
+
+__global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float gscale,
+                            const int64_t* __restrict__ step) {
+  __shared__ float bc[2];
+  if (threadIdx.x == 0) {
+    double t = (double)(*step);
+    bc[0] = (float)(1.0 - pow((double)b1, t));
+    bc[1] = (float)sqrt(1.0 - pow((double)b2, t));
+  }
+  __syncthreads();
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float gi = g[i] * gscale;
+  float mi = b1 * m[i] + (1.f - b1) * gi;
+  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+  m[i] = mi;
+  v[i] = vi;
+  float denom = sqrtf(vi) / bc[1] + eps;
+  p[i] -= (lr / bc[0]) * (mi / denom);
+}
+
+}  // namespace
+
+// ---- wrappers ----------------------------------------------------------------------------------
+int rng_capture(uint64_t* state, uint64_t* cap, int advance, cudaStream_t st) {
+  rng_capture_kernel<<<1, 1, 0, st>>>(state, cap, advance);
+  RD_CHECK_LAUNCH("rng_capture_kernel");
+  return 0;
+}
+
+int lift(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p, const uint64_t* rng,
+         float* X0, cudaStream_t st) {
+  int64_t total = (int64_t)B * N * T * d_ob;
+  lift_kernel<<<blocks_for(total), TPB, 0, st>>>(src, R_u, B, T, N, d_ob, drop_p, rng, X0);
+  RD_CHECK_LAUNCH("lift_kernel");
+  return 0;
+}
+
+int posenc(const float* times, int64_t n_tokens, const float* ts8_host, float* out, int64_t ld, int col0,
+           cudaStream_t st) {
+  TS8 ts;
+  memcpy(ts.v, ts8_host, sizeof(ts.v));
+  posenc_kernel<<<blocks_for(n_tokens * 16), TPB, 0, st>>>(times, n_tokens, ts, out, ld, col0);
+  RD_CHECK_LAUNCH("posenc_kernel");
+  return 0;
+}
+
+int node_scale(const int64_t* edge_tgt, const float* edge_w, int E, int N, float* s, cudaStream_t st) {
+  node_scale_kernel<<<blocks_for((int64_t)N * 32), TPB, 0, st>>>(edge_tgt, edge_w, E, N, s);
+  RD_CHECK_LAUNCH("node_scale_kernel");
+  return 0;
+}
+
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int D, float eps, float* y,
+                  float* stats, cudaStream_t st) {
+  layernorm_fwd_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, gamma, beta, rows, D, eps, y, stats);
+  RD_CHECK_LAUNCH("layernorm_fwd_kernel");
+  return 0;
+}
+
+int64_t ln_bwd_scratch_floats(int64_t rows, int D) { return ceil_div(rows, LN_ROWS) * 2 * D; }
+
+int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows, int D,
+                  float* dx, float* dgamma, float* dbeta, float* scratch, cudaStream_t st) {
+  layernorm_bwd_dx_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, stats, gamma, dy, rows, D, dx);
+  RD_CHECK_LAUNCH("layernorm_bwd_dx_kernel");
+  int chunks = (int)ceil_div(rows, LN_ROWS);
+  if (chunks > 65535) { set_error("layernorm_bwd: too many row chunks"); return -2; }
+  dim3 grid((unsigned)ceil_div(D, 128), (unsigned)chunks);
+  layernorm_bwd_param_kernel<<<grid, 128, 0, st>>>(x, stats, dy, rows, D, scratch);
+  RD_CHECK_LAUNCH("layernorm_bwd_param_kernel");
+  RD_TRY(reduce_partials(scratch, chunks, D, dgamma, st));
+  RD_TRY(reduce_partials(scratch + (int64_t)chunks * D, chunks, D, dbeta, st));
+  return 0;
+}
+
+int attn_softmax_fwd(float* S, const int64_t* lengths, int B, int H, int T, float drop_p, const uint64_t* rng,
+                     uint32_t site, float* Pd, cudaStream_t st) {
+  int64_t rows = (int64_t)B * H * T;
+  attn_softmax_fwd_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(S, lengths, B, H, T, drop_p, rng, site, Pd);
+  RD_CHECK_LAUNCH("attn_softmax_fwd_kernel");
+  return 0;
+}
+
+int attn_softmax_bwd(const float* P, float* dP, int B, int H, int T, float drop_p, const uint64_t* rng,
+                     uint32_t site, cudaStream_t st) {
+  int64_t rows = (int64_t)B * H * T;
+  attn_softmax_bwd_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(P, dP, rows, T, drop_p, rng, site);
+  RD_CHECK_LAUNCH("attn_softmax_bwd_kernel");
+  return 0;
+}
+
+int masked_mean_fwd(const float* x, const int64_t* lengths, int T, int B, int D, float* out, int64_t ld,
+                    cudaStream_t st) {
+  masked_mean_fwd_kernel<<<blocks_for((int64_t)B * D), TPB, 0, st>>>(x, lengths, T, B, D, out, ld);
+  RD_CHECK_LAUNCH("masked_mean_fwd_kernel");
+  return 0;
+}
+
+int masked_mean_bwd(const float* dout, int64_t ld, const int64_t* lengths, int T, int B, int D, float* dx,
+                    cudaStream_t st) {
+  masked_mean_bwd_kernel<<<blocks_for((int64_t)T * B * D), TPB, 0, st>>>(dout, ld, lengths, T, B, D, dx);
+  RD_CHECK_LAUNCH("masked_mean_bwd_kernel");
+  return 0;
+}
+
+int obprop_out_grad(const float* dZ, const float* Z, const float* s, int B, int T, int N, int d_ob, int D,
+                    float* dZ2, cudaStream_t st) {
+  int64_t total = (int64_t)B * N * T * d_ob;
+  obprop_out_grad_kernel<<<blocks_for(total), TPB, 0, st>>>(dZ, Z, s, B, T, N, d_ob, D, dZ2);
+  RD_CHECK_LAUNCH("obprop_out_grad_kernel");
+  return 0;
+}
+
+int apply_dropout(const float* x, int64_t n, float p, const uint64_t* rng, uint32_t site, float* y,
+                  cudaStream_t st) {
+  apply_dropout_kernel<<<blocks_for(n), TPB, 0, st>>>(x, n, p, rng, site, y);
+  RD_CHECK_LAUNCH("apply_dropout_kernel");
+  return 0;
+}
+
+int relu_scale_bwd(const float* d_out, const float* out, const float* scale, int mod, int64_t rows, int C,
+                   float* d_pre, cudaStream_t st) {
+  relu_scale_bwd_kernel<<<blocks_for(rows * C), TPB, 0, st>>>(d_out, out, scale, mod, rows, C, d_pre);
+  RD_CHECK_LAUNCH("relu_scale_bwd_kernel");
+  return 0;
+}
+
+int cross_entropy(const float* logits, const int64_t* y, int B, int ncls, float* loss, float* dlogits,
+                  cudaStream_t st) {
+  cross_entropy_kernel<<<1, TPB, 0, st>>>(logits, y, B, ncls, loss, dlogits);
+  RD_CHECK_LAUNCH("cross_entropy_kernel");
+  return 0;
+}
+
+int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+         float gscale, int64_t* step, cudaStream_t st) {
+  adam_tick_kernel<<<1, 1, 0, st>>>(step);
+  adam_kernel<<<blocks_for(n), TPB, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, gscale, step);
+  RD_CHECK_LAUNCH("adam_kernel");
+  return 0;
+}
+
+}  // namespace rd

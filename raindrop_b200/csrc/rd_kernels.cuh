@@ -1,0 +1,57 @@
+// Launch wrappers for the non-GEMM kernels of the hot path (rd_kernels.cu).
+#pragma once
+#include "rd_common.cuh"
+
+namespace rd {
+
+int rng_capture(uint64_t* rng_state, uint64_t* captured, int advance, cudaStream_t st);
+
+// X0[(b*N+n), t*d_ob+k] = dropout(relu(src[t,b,n] * R_u[n*d_ob+k]))    code/models_rd.py:285-296,323-327
+int lift(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p,
+         const uint64_t* rng, float* X0, cudaStream_t st);
+
+int posenc(const float* times, int64_t n_tokens, const float* ts8_host, float* out, int64_t ld, int col0,
+           cudaStream_t st);
+
+int node_scale(const int64_t* edge_tgt, const float* edge_w, int E, int N, float* s, cudaStream_t st);
+
+// y = LN(x) * gamma + beta over the last dim (width D); stats[row] = {mean, rstd}
+int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int D, float eps,
+                  float* y, float* stats, cudaStream_t st);
+// dx from dy; dgamma/dbeta via partials. scratch >= ln_bwd_scratch_floats(rows, D)
+int64_t ln_bwd_scratch_floats(int64_t rows, int D);
+int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows,
+                  int D, float* dx, float* dgamma, float* dbeta, float* scratch, cudaStream_t st);
+
+// in-place masked softmax over rows of S [B,H,T,T]; key j masked when j >= lengths[b].
+// If Pd != nullptr also writes the dropped probabilities (training).
+int attn_softmax_fwd(float* S, const int64_t* lengths, int B, int H, int T, float drop_p,
+                     const uint64_t* rng, uint32_t site, float* Pd, cudaStream_t st);
+// dS = P * (dP - sum_j dP_j P_j), dP = dPd * mask/(1-p); in place on dP
+int attn_softmax_bwd(const float* P, float* dP, int B, int H, int T, float drop_p, const uint64_t* rng,
+                     uint32_t site, cudaStream_t st);
+
+// pooled[b, d] = sum_{t < len_b} x[t,b,d] / (len_b + 1) -> out[b*ld + d]     code/models_rd.py:366-379
+int masked_mean_fwd(const float* x, const int64_t* lengths, int T, int B, int D, float* out, int64_t ld,
+                    cudaStream_t st);
+int masked_mean_bwd(const float* dout, int64_t ld, const int64_t* lengths, int T, int B, int D, float* dx,
+                    cudaStream_t st);
+
+// dZ2[(b*N+n), t*d_ob+k] = dZ[t,b,n*d_ob+k] * s[n] * (Z[t,b,n*d_ob+k] > 0)
+int obprop_out_grad(const float* dZ, const float* Z, const float* s, int B, int T, int N, int d_ob, int D,
+                    float* dZ2, cudaStream_t st);
+
+// y[i] = x[i] * mask(site, i)   (re-generates the forward's dropout mask)
+int apply_dropout(const float* x, int64_t n, float p, const uint64_t* rng, uint32_t site, float* y,
+                  cudaStream_t st);
+
+// d_pre = d_out * scale[r % mod] * (out > 0)
+int relu_scale_bwd(const float* d_out, const float* out, const float* scale, int mod, int64_t rows, int C,
+                   float* d_pre, cudaStream_t st);
+
+int cross_entropy(const float* logits, const int64_t* y, int B, int ncls, float* loss, float* dlogits,
+                  cudaStream_t st);
+int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
+         float gscale, int64_t* step, cudaStream_t st);
+
+}  // namespace rd

@@ -1,0 +1,518 @@
+// Host-side orchestration of the Raindrop_v2 hot path and the C ABI (include/raindrop_b200.h).
+//
+// Data layout in HBM (all fp32, row-major, 256-byte aligned sub-buffers of one caller-provided
+// workspace so that nothing is allocated between forward and backward):
+//   X0, H1          [B*N, C]   sensor-major rows, C = T*d_ob  (observation propagation operands)
+//   Z[l]            [T, B, D]  encoder layer inputs/outputs, seq-first exactly like the reference
+//   qkv, ctx, r1, x1, f, r2    per encoder layer, token-major [T*B, .]
+//   P (and Pd)      [B, H, T, T] attention probabilities (and their dropped copy when training)
+#include <math.h>
+#include <string.h>
+
+#include "rd_kernels.cuh"
+#include "rd_obprop_tc.cuh"
+
+namespace rd {
+namespace {
+
+struct Shape {
+  int B, T, N, dob, H, nhid, L, ds, ncls;
+  int C, Dm, D, Df, hd;
+  int64_t M1, M2;
+  float p;  // effective dropout probability (0 in eval)
+};
+
+int make_shape(const rd_dims* d, Shape* s) {
+  if (!d) { set_error("dims is NULL"); return -2; }
+  s->B = d->B; s->T = d->T; s->N = d->N; s->dob = d->d_ob; s->H = d->nhead; s->nhid = d->nhid;
+  s->L = d->nlayers; s->ds = d->d_static; s->ncls = d->n_classes;
+  if (s->B < 1 || s->T < 1 || s->N < 1 || s->dob < 1 || s->H < 1 || s->nhid < 1 || s->L < 1 ||
+      s->L > RD_MAX_LAYERS || s->ncls < 1 || s->ds < 0) {
+    set_error("invalid dims (B=%d T=%d N=%d d_ob=%d nhead=%d nhid=%d nlayers=%d d_static=%d n_classes=%d)",
+              s->B, s->T, s->N, s->dob, s->H, s->nhid, s->L, s->ds, s->ncls);
+    return -2;
+  }
+  s->C = s->T * s->dob; s->Dm = s->N * s->dob; s->D = s->Dm + RD_D_PE;
+  if (s->D % s->H != 0) { set_error("d_model+16 = %d not divisible by nhead = %d", s->D, s->H); return -2; }
+  s->hd = s->D / s->H;
+  s->Df = s->D + (s->ds > 0 ? s->N : 0);
+  s->M1 = (int64_t)s->B * s->N; s->M2 = (int64_t)s->T * s->B;
+  s->p = (d->training && d->dropout_p > 0.f) ? d->dropout_p : 0.f;
+  if (s->p >= 1.f) { set_error("dropout_p must be < 1"); return -2; }
+  return 0;
+}
+
+struct Arena {
+  int64_t off = 0;  // floats
+  int64_t take(int64_t n) { int64_t o = off; off += round_up(n > 0 ? n : 1, 64); return o; }
+};
+
+struct WsLayout {
+  int64_t rng, X0, H1, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
+  struct { int64_t qkv, P, Pd, ctx, r1, st1, x1, f, r2, st2; } l[RD_MAX_LAYERS];
+};
+
+WsLayout ws_layout(const Shape& s) {
+  WsLayout w;
+  Arena a;
+  w.rng = a.take(4);
+  w.X0 = a.take(s.M1 * s.C);
+  w.H1 = a.take(s.M1 * s.C);
+  for (int i = 0; i <= s.L; ++i) w.Z[i] = a.take(s.M2 * s.D);
+  int64_t pp = (int64_t)s.B * s.H * s.T * s.T;
+  for (int i = 0; i < s.L; ++i) {
+    w.l[i].qkv = a.take(s.M2 * 3 * s.D);
+    w.l[i].P = a.take(pp);
+    w.l[i].Pd = a.take(pp);
+    w.l[i].ctx = a.take(s.M2 * s.D);
+    w.l[i].r1 = a.take(s.M2 * s.D);
+    w.l[i].st1 = a.take(s.M2 * 2);
+    w.l[i].x1 = a.take(s.M2 * s.D);
+    w.l[i].f = a.take(s.M2 * s.nhid);
+    w.l[i].r2 = a.take(s.M2 * s.D);
+    w.l[i].st2 = a.take(s.M2 * 2);
+  }
+  w.feat = a.take((int64_t)s.B * s.Df);
+  w.hpre = a.take((int64_t)s.B * s.Df);
+  w.total = a.off;
+  return w;
+}
+
+struct BwLayout {
+  int64_t dfeat, dhpre, gA, gB, gC, gF, gD, dqkv, dP, gO2, gO1, partial, aux, total;
+  int64_t partial_floats, aux_floats;
+};
+
+int64_t tn_partial_floats(int Nout, int Kin, int64_t rows) {
+  int ns;
+  return gemm_splitk_plan(Nout, Kin, (int)rows, &ns);
+}
+
+BwLayout bw_layout(const Shape& s) {
+  BwLayout b;
+  Arena a;
+  b.dfeat = a.take((int64_t)s.B * s.Df);
+  b.dhpre = a.take((int64_t)s.B * s.Df);
+  b.gA = a.take(s.M2 * s.D);
+  b.gB = a.take(s.M2 * s.D);
+  b.gC = a.take(s.M2 * s.D);
+  b.gF = a.take(s.M2 * s.nhid);
+  b.gD = a.take(s.M2 * s.D);
+  b.dqkv = a.take(s.M2 * 3 * s.D);
+  b.dP = a.take((int64_t)s.B * s.H * s.T * s.T);
+  b.gO2 = a.take(s.M1 * s.C);
+  b.gO1 = a.take(s.M1 * s.C);
+  int64_t pf = 0;
+  auto upd = [&](int no, int ki, int64_t rows) { int64_t v = tn_partial_floats(no, ki, rows); if (v > pf) pf = v; };
+  upd(s.C, s.C, s.M1);
+  upd(3 * s.D, s.D, s.M2); upd(s.D, s.D, s.M2); upd(s.nhid, s.D, s.M2); upd(s.D, s.nhid, s.M2);
+  upd(s.Df, s.Df, s.B); upd(s.ncls, s.Df, s.B);
+  if (s.ds > 0) upd(s.N, s.ds, s.B);
+  b.partial_floats = pf;
+  b.partial = a.take(pf);
+  int64_t af = 0;
+  auto upa = [&](int64_t v) { if (v > af) af = v; };
+  upa(colsum_scratch_floats(s.M1, s.C));
+  upa(colsum_scratch_floats(s.M2, 3 * s.D));
+  upa(colsum_scratch_floats(s.M2, s.nhid));
+  upa(colsum_scratch_floats(s.B, s.Df));
+  upa(ln_bwd_scratch_floats(s.M2, s.D));
+  b.aux_floats = af;
+  b.aux = a.take(af);
+  b.total = a.off;
+  return b;
+}
+
+// Y[M,N] = epi(X[M,K] . W[N,K]^T)
+GemmP nt(const float* X, int64_t ldx, const float* W, int64_t ldw, float* Y, int64_t ldy, int64_t M, int N, int K) {
+  GemmP g;
+  g.A = X; g.ta = 0; g.sAi = ldx; g.sAk = 1;
+  g.B = W; g.tb = 1; g.sBj = ldw; g.sBk = 1;
+  g.C = Y; g.sCi = ldy; g.sCj = 1;
+  g.M = (int)M; g.N = N; g.K = K;
+  return g;
+}
+// dX[M,Kin] = epi(dY[M,Nout] . W[Nout,Kin])
+GemmP nn(const float* dY, int64_t ldy, const float* W, int64_t ldw, float* dX, int64_t ldx, int64_t M, int Kin, int Nout) {
+  GemmP g;
+  g.A = dY; g.ta = 0; g.sAi = ldy; g.sAk = 1;
+  g.B = W; g.tb = 0; g.sBk = ldw; g.sBj = 1;
+  g.C = dX; g.sCi = ldx; g.sCj = 1;
+  g.M = (int)M; g.N = Kin; g.K = Nout;
+  return g;
+}
+// dW[Nout,Kin] = sum_r dY[r,Nout]^T X[r,Kin]   (split over rows, deterministic two-stage reduce)
+int tn(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int Nout, int Kin, int64_t rows,
+       float* partial, cudaStream_t st) {
+  GemmP g;
+  g.A = dY; g.ta = 1; g.sAk = ldy; g.sAi = 1;
+  g.B = X; g.tb = 0; g.sBk = ldx; g.sBj = 1;
+  g.C = dW; g.sCi = Kin; g.sCj = 1;
+  g.M = Nout; g.N = Kin; g.K = (int)rows;
+  int ns;
+  gemm_splitk_plan(Nout, Kin, (int)rows, &ns);
+  g.nsplit = ns; g.partial = partial;
+  return gemm(g, st);
+}
+
+}  // namespace
+
+// ---- observation propagation layer (operator level) ---------------------------------------------
+// Forward goes to the tcgen05 kernel when the shape fits its tiling, otherwise to the generic
+// CUDA-core GEMM (same epilogue).
+static int obprop_forward(const float* x, const float* W, const float* b, const float* s, int mod, int64_t rows,
+                          int C, float* out, int perm, int pB, int pN, int pdob, int pD, cudaStream_t st) {
+  if (obprop_tc_supported(C)) return obprop_tc_fwd(x, W, b, s, mod, rows, C, out, perm, pB, pN, pdob, pD, st);
+  GemmP g = nt(x, C, W, C, out, C, rows, C, C);
+  g.bias = b; g.relu = 1; g.rowscale = s; g.rowscale_mod = mod;
+  g.perm = perm; g.pB = pB; g.pN = pN; g.pdob = pdob; g.pD = pD;
+  return gemm(g, st);
+}
+
+static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* src, const float* statics,
+                        const float* times, const int64_t* lengths, const float* nscale, uint64_t* rng_state,
+                        float* ws, float* logits, cudaStream_t st) {
+  Shape s;
+  RD_TRY(make_shape(dims, &s));
+  if (s.ds > 0 && (!statics || !P->emb_weight || !P->emb_bias)) { set_error("static branch needs statics/emb"); return -2; }
+  WsLayout w = ws_layout(s);
+  uint64_t* rng = reinterpret_cast<uint64_t*>(ws + w.rng);
+  if (s.p > 0.f) {
+    if (!rng_state) { set_error("training with dropout needs rng_state"); return -2; }
+    RD_TRY(rng_capture(rng_state, rng, 1, st));
+  }
+  float* X0 = ws + w.X0; float* H1 = ws + w.H1;
+  RD_TRY(lift(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, X0, st));
+  RD_TRY(obprop_forward(X0, P->ob1_value_weight, P->ob1_value_bias, nscale, s.N, s.M1, s.C, H1, 0, 0, 0, 0, 0, st));
+  float* Z0 = ws + w.Z[0];
+  RD_TRY(obprop_forward(H1, P->ob2_value_weight, P->ob2_value_bias, nscale, s.N, s.M1, s.C, Z0, 1, s.B, s.N, s.dob, s.D, st));
+  RD_TRY(posenc(times, s.M2, dims->pe_timescales, Z0, s.D, s.Dm, st));
+
+  const float scale = 1.f / sqrtf((float)s.hd);
+  const int64_t row3 = (int64_t)s.B * 3 * s.D;
+  const int64_t TT = (int64_t)s.T * s.T;
+  for (int l = 0; l < s.L; ++l) {
+    const rd_encoder_layer_params& E = P->layer[l];
+    float* x = ws + w.Z[l];
+    float* qkv = ws + w.l[l].qkv;
+    float* Pm = ws + w.l[l].P;
+    float* Pd = s.p > 0.f ? ws + w.l[l].Pd : nullptr;
+    {
+      GemmP g = nt(x, s.D, E.in_proj_weight, s.D, qkv, 3 * s.D, s.M2, 3 * s.D, s.D);
+      g.bias = E.in_proj_bias;
+      RD_TRY(gemm(g, st));
+    }
+    {  // S[b,h] = scale * Q K^T
+      GemmP g;
+      g.A = qkv; g.ta = 0; g.sAi = row3; g.sAk = 1; g.sAzo = 3 * s.D; g.sAzi = s.hd;
+      g.B = qkv + s.D; g.tb = 1; g.sBj = row3; g.sBk = 1; g.sBzo = 3 * s.D; g.sBzi = s.hd;
+      g.C = Pm; g.sCi = s.T; g.sCj = 1; g.sCzo = s.H * TT; g.sCzi = TT;
+      g.M = s.T; g.N = s.T; g.K = s.hd; g.nz = s.B * s.H; g.nz_inner = s.H; g.alpha = scale;
+      RD_TRY(gemm(g, st));
+    }
+    RD_TRY(attn_softmax_fwd(Pm, lengths, s.B, s.H, s.T, s.p, rng, SITE_ATTN + l, Pd, st));
+    float* ctx = ws + w.l[l].ctx;
+    {  // ctx[b,h] = P V
+      GemmP g;
+      g.A = Pd ? Pd : Pm; g.ta = 0; g.sAi = s.T; g.sAk = 1; g.sAzo = s.H * TT; g.sAzi = TT;
+      g.B = qkv + 2 * s.D; g.tb = 0; g.sBk = row3; g.sBj = 1; g.sBzo = 3 * s.D; g.sBzi = s.hd;
+      g.C = ctx; g.sCi = (int64_t)s.B * s.D; g.sCj = 1; g.sCzo = s.D; g.sCzi = s.hd;
+      g.M = s.T; g.N = s.hd; g.K = s.T; g.nz = s.B * s.H; g.nz_inner = s.H;
+      RD_TRY(gemm(g, st));
+    }
+    float* r1 = ws + w.l[l].r1; float* x1 = ws + w.l[l].x1;
+    {
+      GemmP g = nt(ctx, s.D, E.out_proj_weight, s.D, r1, s.D, s.M2, s.D, s.D);
+      g.bias = E.out_proj_bias; g.drop_p = s.p; g.rng = rng; g.drop_site = SITE_RESID1 + l;
+      g.resid = x; g.resid_ld = s.D;
+      RD_TRY(gemm(g, st));
+    }
+    RD_TRY(layernorm_fwd(r1, E.norm1_weight, E.norm1_bias, s.M2, s.D, dims->ln_eps, x1, ws + w.l[l].st1, st));
+    float* f = ws + w.l[l].f; float* r2 = ws + w.l[l].r2;
+    {
+      GemmP g = nt(x1, s.D, E.linear1_weight, s.D, f, s.nhid, s.M2, s.nhid, s.D);
+      g.bias = E.linear1_bias; g.relu = 1; g.drop_p = s.p; g.rng = rng; g.drop_site = SITE_FFN + l;
+      RD_TRY(gemm(g, st));
+    }
+    {
+      GemmP g = nt(f, s.nhid, E.linear2_weight, s.nhid, r2, s.D, s.M2, s.D, s.nhid);
+      g.bias = E.linear2_bias; g.drop_p = s.p; g.rng = rng; g.drop_site = SITE_RESID2 + l;
+      g.resid = x1; g.resid_ld = s.D;
+      RD_TRY(gemm(g, st));
+    }
+    RD_TRY(layernorm_fwd(r2, E.norm2_weight, E.norm2_bias, s.M2, s.D, dims->ln_eps, ws + w.Z[l + 1], ws + w.l[l].st2, st));
+  }
+  float* feat = ws + w.feat; float* hpre = ws + w.hpre;
+  RD_TRY(masked_mean_fwd(ws + w.Z[s.L], lengths, s.T, s.B, s.D, feat, s.Df, st));
+  if (s.ds > 0) {
+    GemmP g = nt(statics, s.ds, P->emb_weight, s.ds, feat + s.D, s.Df, s.B, s.N, s.ds);
+    g.bias = P->emb_bias;
+    RD_TRY(gemm(g, st));
+  }
+  {
+    GemmP g = nt(feat, s.Df, P->mlp0_weight, s.Df, hpre, s.Df, s.B, s.Df, s.Df);
+    g.bias = P->mlp0_bias; g.relu = 1;
+    RD_TRY(gemm(g, st));
+  }
+  {
+    GemmP g = nt(hpre, s.Df, P->mlp2_weight, s.Df, logits, s.ncls, s.B, s.ncls, s.Df);
+    g.bias = P->mlp2_bias;
+    RD_TRY(gemm(g, st));
+  }
+  return 0;
+}
+
+static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* statics, const int64_t* lengths,
+                        const float* nscale, const float* ws, const float* dlogits, const rd_grads* G, float* sc,
+                        cudaStream_t st) {
+  Shape s;
+  RD_TRY(make_shape(dims, &s));
+  WsLayout w = ws_layout(s);
+  BwLayout b = bw_layout(s);
+  const uint64_t* rng = reinterpret_cast<const uint64_t*>(ws + w.rng);
+  float* partial = sc + b.partial; float* aux = sc + b.aux;
+  const float ik = s.p > 0.f ? 1.f / (1.f - s.p) : 1.f;
+
+  // ---- head: logits = mlp2(relu(mlp0(feat)))                      code/models_rd.py:383-385
+  const float* feat = ws + w.feat; const float* hpre = ws + w.hpre;
+  float* dfeat = sc + b.dfeat; float* dhpre = sc + b.dhpre;
+  RD_TRY(tn(dlogits, s.ncls, hpre, s.Df, G->mlp2_weight, s.ncls, s.Df, s.B, partial, st));
+  RD_TRY(colsum(dlogits, s.B, s.ncls, s.ncls, G->mlp2_bias, aux, st));
+  {
+    GemmP g = nn(dlogits, s.ncls, P->mlp2_weight, s.Df, dhpre, s.Df, s.B, s.Df, s.ncls);
+    g.gate = hpre; g.gate_ld = s.Df;
+    RD_TRY(gemm(g, st));
+  }
+  RD_TRY(tn(dhpre, s.Df, feat, s.Df, G->mlp0_weight, s.Df, s.Df, s.B, partial, st));
+  RD_TRY(colsum(dhpre, s.B, s.Df, s.Df, G->mlp0_bias, aux, st));
+  RD_TRY(gemm(nn(dhpre, s.Df, P->mlp0_weight, s.Df, dfeat, s.Df, s.B, s.Df, s.Df), st));
+  if (s.ds > 0) {
+    RD_TRY(tn(dfeat + s.D, s.Df, statics, s.ds, G->emb_weight, s.N, s.ds, s.B, partial, st));
+    RD_TRY(colsum(dfeat + s.D, s.B, s.N, s.Df, G->emb_bias, aux, st));
+  }
+  float* gA = sc + b.gA; float* gB = sc + b.gB; float* gC = sc + b.gC; float* gF = sc + b.gF; float* gD = sc + b.gD;
+  float* dqkv = sc + b.dqkv; float* dP = sc + b.dP;
+  RD_TRY(masked_mean_bwd(dfeat, s.Df, lengths, s.T, s.B, s.D, gA, st));
+
+  const float scale = 1.f / sqrtf((float)s.hd);
+  const int64_t row3 = (int64_t)s.B * 3 * s.D;
+  const int64_t TT = (int64_t)s.T * s.T;
+  for (int l = s.L - 1; l >= 0; --l) {
+    const rd_encoder_layer_params& E = P->layer[l];
+    const rd_encoder_layer_grads& GE = G->layer[l];
+    const float* x = ws + w.Z[l];
+    const float* qkv = ws + w.l[l].qkv; const float* Pm = ws + w.l[l].P;
+    const float* Pd = s.p > 0.f ? ws + w.l[l].Pd : Pm;
+    const float* ctx = ws + w.l[l].ctx; const float* r1 = ws + w.l[l].r1; const float* x1 = ws + w.l[l].x1;
+    const float* f = ws + w.l[l].f; const float* r2 = ws + w.l[l].r2;
+    // norm2 + feed-forward block
+    RD_TRY(layernorm_bwd(r2, ws + w.l[l].st2, E.norm2_weight, gA, s.M2, s.D, gB, GE.norm2_weight, GE.norm2_bias, aux, st));
+    const float* dg = gB;
+    if (s.p > 0.f) { RD_TRY(apply_dropout(gB, s.M2 * s.D, s.p, rng, SITE_RESID2 + l, gC, st)); dg = gC; }
+    RD_TRY(tn(dg, s.D, f, s.nhid, GE.linear2_weight, s.D, s.nhid, s.M2, partial, st));
+    RD_TRY(colsum(dg, s.M2, s.D, s.D, GE.linear2_bias, aux, st));
+    {
+      GemmP g = nn(dg, s.D, E.linear2_weight, s.nhid, gF, s.nhid, s.M2, s.nhid, s.D);
+      g.gate = f; g.gate_ld = s.nhid; g.gate_scale = ik;  // relu' and the FFN dropout mask in one
+      RD_TRY(gemm(g, st));
+    }
+    RD_TRY(tn(gF, s.nhid, x1, s.D, GE.linear1_weight, s.nhid, s.D, s.M2, partial, st));
+    RD_TRY(colsum(gF, s.M2, s.nhid, s.nhid, GE.linear1_bias, aux, st));
+    {
+      GemmP g = nn(gF, s.nhid, E.linear1_weight, s.D, gA, s.D, s.M2, s.D, s.nhid);
+      g.resid = gB; g.resid_ld = s.D;
+      RD_TRY(gemm(g, st));
+    }
+    // norm1 + self-attention block
+    RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, gB, GE.norm1_weight, GE.norm1_bias, aux, st));
+    const float* dy = gB;
+    if (s.p > 0.f) { RD_TRY(apply_dropout(gB, s.M2 * s.D, s.p, rng, SITE_RESID1 + l, gC, st)); dy = gC; }
+    RD_TRY(tn(dy, s.D, ctx, s.D, GE.out_proj_weight, s.D, s.D, s.M2, partial, st));
+    RD_TRY(colsum(dy, s.M2, s.D, s.D, GE.out_proj_bias, aux, st));
+    RD_TRY(gemm(nn(dy, s.D, E.out_proj_weight, s.D, gD, s.D, s.M2, s.D, s.D), st));
+    {  // dPd[b,h] = dctx V^T
+      GemmP g;
+      g.A = gD; g.ta = 0; g.sAi = (int64_t)s.B * s.D; g.sAk = 1; g.sAzo = s.D; g.sAzi = s.hd;
+      g.B = qkv + 2 * s.D; g.tb = 1; g.sBj = row3; g.sBk = 1; g.sBzo = 3 * s.D; g.sBzi = s.hd;
+      g.C = dP; g.sCi = s.T; g.sCj = 1; g.sCzo = s.H * TT; g.sCzi = TT;
+      g.M = s.T; g.N = s.T; g.K = s.hd; g.nz = s.B * s.H; g.nz_inner = s.H;
+      RD_TRY(gemm(g, st));
+    }
+    {  // dV[b,h] = Pd^T dctx
+      GemmP g;
+      g.A = Pd; g.ta = 1; g.sAk = s.T; g.sAi = 1; g.sAzo = s.H * TT; g.sAzi = TT;
+      g.B = gD; g.tb = 0; g.sBk = (int64_t)s.B * s.D; g.sBj = 1; g.sBzo = s.D; g.sBzi = s.hd;
+      g.C = dqkv + 2 * s.D; g.sCi = row3; g.sCj = 1; g.sCzo = 3 * s.D; g.sCzi = s.hd;
+      g.M = s.T; g.N = s.hd; g.K = s.T; g.nz = s.B * s.H; g.nz_inner = s.H;
+      RD_TRY(gemm(g, st));
+    }
+    RD_TRY(attn_softmax_bwd(Pm, dP, s.B, s.H, s.T, s.p, rng, SITE_ATTN + l, st));
+    {  // dQ[b,h] = scale * dS K
+      GemmP g;
+      g.A = dP; g.ta = 0; g.sAi = s.T; g.sAk = 1; g.sAzo = s.H * TT; g.sAzi = TT;
+      g.B = qkv + s.D; g.tb = 0; g.sBk = row3; g.sBj = 1; g.sBzo = 3 * s.D; g.sBzi = s.hd;
+      g.C = dqkv; g.sCi = row3; g.sCj = 1; g.sCzo = 3 * s.D; g.sCzi = s.hd;
+      g.M = s.T; g.N = s.hd; g.K = s.T; g.nz = s.B * s.H; g.nz_inner = s.H; g.alpha = scale;
+      RD_TRY(gemm(g, st));
+    }
+    {  // dK[b,h] = scale * dS^T Q
+      GemmP g;
+      g.A = dP; g.ta = 1; g.sAk = s.T; g.sAi = 1; g.sAzo = s.H * TT; g.sAzi = TT;
+      g.B = qkv; g.tb = 0; g.sBk = row3; g.sBj = 1; g.sBzo = 3 * s.D; g.sBzi = s.hd;
+      g.C = dqkv + s.D; g.sCi = row3; g.sCj = 1; g.sCzo = 3 * s.D; g.sCzi = s.hd;
+      g.M = s.T; g.N = s.hd; g.K = s.T; g.nz = s.B * s.H; g.nz_inner = s.H; g.alpha = scale;
+      RD_TRY(gemm(g, st));
+    }
+    RD_TRY(tn(dqkv, 3 * s.D, x, s.D, GE.in_proj_weight, 3 * s.D, s.D, s.M2, partial, st));
+    RD_TRY(colsum(dqkv, s.M2, 3 * s.D, 3 * s.D, GE.in_proj_bias, aux, st));
+    {
+      GemmP g = nn(dqkv, 3 * s.D, E.in_proj_weight, s.D, gA, s.D, s.M2, s.D, 3 * s.D);
+      g.resid = gB; g.resid_ld = s.D;
+      RD_TRY(gemm(g, st));
+    }
+  }
+  // ---- observation propagation: gA = d(loss)/d(Z0) [T,B,D]          code/models_rd.py:322-343
+  float* gO2 = sc + b.gO2; float* gO1 = sc + b.gO1;
+  const float* X0 = ws + w.X0; const float* H1 = ws + w.H1;
+  RD_TRY(obprop_out_grad(gA, ws + w.Z[0], nscale, s.B, s.T, s.N, s.dob, s.D, gO2, st));
+  RD_TRY(tn(gO2, s.C, H1, s.C, G->ob2_value_weight, s.C, s.C, s.M1, partial, st));
+  RD_TRY(colsum(gO2, s.M1, s.C, s.C, G->ob2_value_bias, aux, st));
+  {
+    GemmP g = nn(gO2, s.C, P->ob2_value_weight, s.C, gO1, s.C, s.M1, s.C, s.C);
+    g.rowscale = nscale; g.rowscale_mod = s.N; g.gate = H1; g.gate_ld = s.C;
+    RD_TRY(gemm(g, st));
+  }
+  RD_TRY(tn(gO1, s.C, X0, s.C, G->ob1_value_weight, s.C, s.C, s.M1, partial, st));
+  RD_TRY(colsum(gO1, s.M1, s.C, s.C, G->ob1_value_bias, aux, st));
+  return 0;
+}
+
+}  // namespace rd
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace rd;
+
+extern "C" {
+
+int rd_abi_version(void) { return RD_ABI_VERSION; }
+const char* rd_last_error_string(void) { return last_error(); }
+
+int rd_node_scale(const int64_t* edge_tgt, const float* edge_w, int32_t E, int32_t N, float* out, void* stream) {
+  if (!edge_tgt || !edge_w || !out || E < 0 || N < 1) { set_error("rd_node_scale: bad arguments"); return -2; }
+  return node_scale(edge_tgt, edge_w, E, N, out, (cudaStream_t)stream);
+}
+
+int rd_obprop_fwd(const float* x, const float* weight, const float* bias, const float* nscale, int32_t mod,
+                  int64_t rows, int32_t C, float* out, void* stream) {
+  if (!x || !weight || !bias || !nscale || !out || rows < 0 || C < 1 || mod < 1) {
+    set_error("rd_obprop_fwd: bad arguments");
+    return -2;
+  }
+  if (rows == 0) return 0;
+  return obprop_forward(x, weight, bias, nscale, mod, rows, C, out, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+}
+
+size_t rd_obprop_bwd_scratch_bytes(int64_t rows, int32_t C) {
+  int64_t a = round_up(rows * C, 64) + round_up(tn_partial_floats(C, C, rows), 64) + round_up(colsum_scratch_floats(rows, C), 64);
+  return (size_t)a * sizeof(float);
+}
+
+int rd_obprop_bwd(const float* x, const float* out, const float* d_out, const float* weight, const float* nscale,
+                  int32_t mod, int64_t rows, int32_t C, float* d_x, float* d_weight, float* d_bias, void* scratch,
+                  void* stream) {
+  if (!x || !out || !d_out || !weight || !nscale || !d_weight || !d_bias || !scratch || rows < 1 || C < 1) {
+    set_error("rd_obprop_bwd: bad arguments");
+    return -2;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  float* dpre = (float*)scratch;
+  float* partial = dpre + round_up(rows * C, 64);
+  float* aux = partial + round_up(tn_partial_floats(C, C, rows), 64);
+  RD_TRY(relu_scale_bwd(d_out, out, nscale, mod, rows, C, dpre, st));
+  RD_TRY(tn(dpre, C, x, C, d_weight, C, C, rows, partial, st));
+  RD_TRY(colsum(dpre, rows, C, C, d_bias, aux, st));
+  if (d_x) RD_TRY(gemm(nn(dpre, C, weight, C, d_x, C, rows, C, C), st));
+  return 0;
+}
+
+size_t rd_workspace_bytes(const rd_dims* dims) {
+  Shape s;
+  if (make_shape(dims, &s) != 0) return 0;
+  return (size_t)ws_layout(s).total * sizeof(float);
+}
+
+size_t rd_backward_scratch_bytes(const rd_dims* dims) {
+  Shape s;
+  if (make_shape(dims, &s) != 0) return 0;
+  return (size_t)bw_layout(s).total * sizeof(float);
+}
+
+int64_t rd_workspace_offset(const rd_dims* dims, int32_t which, int64_t* n_floats) {
+  Shape s;
+  if (make_shape(dims, &s) != 0) return -1;
+  WsLayout w = ws_layout(s);
+  int64_t off = -1, n = 0;
+  switch (which) {
+    case RD_WS_X0: off = w.X0; n = s.M1 * s.C; break;
+    case RD_WS_H1: off = w.H1; n = s.M1 * s.C; break;
+    case RD_WS_ENC_IN: off = w.Z[0]; n = s.M2 * s.D; break;
+    case RD_WS_ENC_OUT: off = w.Z[s.L]; n = s.M2 * s.D; break;
+    case RD_WS_FEAT: off = w.feat; n = (int64_t)s.B * s.Df; break;
+    case RD_WS_RNG: off = w.rng; n = 4; break;
+    default: set_error("rd_workspace_offset: unknown buffer %d", which); return -1;
+  }
+  if (n_floats) *n_floats = n;
+  return off * (int64_t)sizeof(float);
+}
+
+int rd_raindrop_v2_fwd(const rd_dims* dims, const rd_params* params, const float* src, const float* statics,
+                       const float* times, const int64_t* lengths, const float* node_scale, uint64_t* rng_state,
+                       void* workspace, float* logits, void* stream) {
+  if (!dims || !params || !src || !times || !lengths || !node_scale || !workspace || !logits) {
+    set_error("rd_raindrop_v2_fwd: NULL argument");
+    return -2;
+  }
+  return raindrop_fwd(dims, params, src, statics, times, lengths, node_scale, rng_state, (float*)workspace, logits,
+                      (cudaStream_t)stream);
+}
+
+int rd_raindrop_v2_bwd(const rd_dims* dims, const rd_params* params, const float* statics, const int64_t* lengths,
+                       const float* node_scale, const void* workspace, const float* d_logits, const rd_grads* grads,
+                       void* scratch, void* stream) {
+  if (!dims || !params || !lengths || !node_scale || !workspace || !d_logits || !grads || !scratch) {
+    set_error("rd_raindrop_v2_bwd: NULL argument");
+    return -2;
+  }
+  return raindrop_bwd(dims, params, statics, lengths, node_scale, (const float*)workspace, d_logits, grads,
+                      (float*)scratch, (cudaStream_t)stream);
+}
+
+int rd_positional_encoding(const float* times, int64_t n_tokens, const float* timescales_host, float* out,
+                           int64_t ld, int32_t col0, void* stream) {
+  if (!times || !timescales_host || !out || n_tokens < 0) { set_error("rd_positional_encoding: bad arguments"); return -2; }
+  if (n_tokens == 0) return 0;
+  return posenc(times, n_tokens, timescales_host, out, ld, col0, (cudaStream_t)stream);
+}
+
+int rd_cross_entropy_fwd_bwd(const float* logits, const int64_t* y, int32_t B, int32_t ncls, float* loss,
+                             float* d_logits, void* stream) {
+  if (!logits || !y || !loss || B < 1 || ncls < 1) { set_error("rd_cross_entropy_fwd_bwd: bad arguments"); return -2; }
+  return cross_entropy(logits, y, B, ncls, loss, d_logits, (cudaStream_t)stream);
+}
+
+int rd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
+                 float beta2, float eps, float grad_scale, int64_t* step, void* stream) {
+  if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n < 0) { set_error("rd_adam_step: bad arguments"); return -2; }
+  if (n == 0) return 0;
+  return adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, grad_scale, step, (cudaStream_t)stream);
+}
+
+int rd_debug_dropout_mask(const uint64_t* rng_captured, uint32_t site, int64_t n, float p, float* out, void* stream) {
+  if (!rng_captured || !out || n < 0 || p < 0.f || p >= 1.f) { set_error("rd_debug_dropout_mask: bad arguments"); return -2; }
+  if (n == 0) return 0;
+  return apply_dropout(nullptr, n, p, rng_captured, site, out, (cudaStream_t)stream);
+}
+
+}  // extern "C"

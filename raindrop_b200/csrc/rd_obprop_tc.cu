@@ -1,0 +1,387 @@
+// Observation-propagation layer forward on the 5th-gen tensor cores (sm_100a).
+//
+//   out[r, :] = relu(x[r, :] . W^T + b) * s[r % N]            x: [B*N, C] fp32, W: [C, C] fp32
+//
+// which is what `Observation_progation` computes on the live path (code/Ob_propagation.py:187-228:
+// the message relu(lin_value(x_i)) depends on the target only, so segment-softmax + scatter-add
+// collapse to the per-node factor s, see rd_node_scale).  Roofline: 8*C bytes and 2*C^2 flops per
+// row -> C/4 flop/B (60 at P19): HBM-bound, so the design goal is to stream x exactly once:
+//
+//   * persistent CTAs (one per SM), static round-robin over 128-row tiles x n-tiles;
+//   * warp 0: TMA producer  - x tile [128 x 32] and W tile [BN x 32] fp32 per k-block into a
+//             4-stage 128B-swizzled shared-memory ring (W comes from L2, x from HBM);
+//   * warp 1: one elected thread issues tcgen05.mma kind::tf32 (M=128, N=BN<=256, K=8), fp32
+//             accumulators in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i
+//             overlaps the MMAs of tile i+1;
+//   * warps 2-5: epilogue - tcgen05.ld 32 columns at a time, + bias, relu, * s, stage through
+//             shared memory and write with TMA bulk stores (coalesced 128 B lines; for the second
+//             layer a 4-D tensor map scatters straight into the [T, B, D] encoder input,
+//             code/models_rd.py:338-341, no separate permute pass).
+// fp32 bits are fed to the tensor core unchanged (TF32 reads the top 19 bits); SURVEY.md section 7
+// measured the effect on the logits at 1e-5 normwise.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "rd_obprop_tc.cuh"
+
+namespace rd {
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 32;                 // tf32 per k-block: 128 bytes = one swizzle row
+constexpr int MAX_STAGES = 4;
+constexpr int NTHREADS = 192;
+constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
+constexpr int STG_BYTES = 4096;              // 32 rows x 32 floats per epilogue warp buffer
+constexpr int SMEM_LIMIT = 232448;           // 227 KB
+
+struct TcParams {
+  int M, C, BN, n_tiles, m_tiles, k_blocks, nstages;
+  const float* bias;
+  const float* scale;
+  int scale_mod;
+  int perm, pB, pN;
+};
+
+// ---- PTX wrappers -------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// K-major operand tile, rows of 128 bytes, 128B swizzle, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                 const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.BN * 128u;
+  const uint32_t stg_base = base + (uint32_t)p.nstages * stage_bytes;        // 8 x 4 KB staging
+  const uint32_t bias_base = stg_base + 8 * STG_BYTES;                        // 2 x 256 floats
+  const uint32_t bar_base = bias_base + 2 * 256 * 4;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ===== TMA producer ==========================================================================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int m_t = tile / p.n_tiles, n_t = tile - m_t * p.n_tiles;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), stage_bytes);
+          const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+          tma_load_2d(&tmA, full_bar(stage), sa, kb * BK, m_t * BM);
+          tma_load_2d(&tmW, full_bar(stage), sa + A_STAGE_BYTES, kb * BK, n_t * p.BN);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer (one thread) ==============================================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+          const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + A_STAGE_BYTES);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk)  // advance 32 bytes (8 tf32) inside the swizzle row
+            umma_tf32(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+          umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
+          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else {
+    // ===== epilogue warps 2..5: TMEM -> registers -> smem -> TMA store ===========================
+    const int q = warp & 3;               // TMEM lane quarter this warp may access
+    const int et = threadIdx.x - 64;      // 0..127
+    const uint32_t my_stg = stg_base + (uint32_t)(warp - 2) * 2u * STG_BYTES;
+    int acc = 0; uint32_t acc_phase = 0; int buf = 0;
+    const int n_chunks = (p.BN + 31) / 32;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_t = tile / p.n_tiles, n_t = tile - m_t * p.n_tiles;
+      const int col0 = n_t * p.BN;
+      for (int c = et; c < 256; c += 128) bias_s[acc * 256 + c] = (c < p.BN && col0 + c < p.C) ? __ldg(p.bias + col0 + c) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int row0 = m_t * BM + q * 32;
+      const int row = row0 + lane;
+      const float sc = row < p.M ? __ldg(p.scale + (row % p.scale_mod)) : 0.f;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + ch * 32), v);
+        if (lane == 0) bulk_wait_read<1>();   // the store that used this staging buffer has drained
+        __syncwarp();
+        const uint32_t stg = my_stg + (uint32_t)buf * STG_BYTES;
+        const float* bs = bias_s + acc * 256 + ch * 32;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float4 o;
+          o.x = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bs[4 * j4 + 0], 0.f) * sc;
+          o.y = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bs[4 * j4 + 1], 0.f) * sc;
+          o.z = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bs[4 * j4 + 2], 0.f) * sc;
+          o.w = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bs[4 * j4 + 3], 0.f) * sc;
+          // plain: [32 rows][128 B] with the 128B swizzle the tensor map expects
+          // perm : [8 t][32 n][4 k] dense (box {4, 32, 1, 8})
+          const uint32_t off = p.perm ? (uint32_t)((j4 * 32 + lane) * 16)
+                                      : (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) << 4));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          const int c0 = col0 + ch * 32;
+          if (!p.perm) {
+            tma_store_2d(&tmOut, stg, c0, row0);
+          } else {
+            const int b0 = row0 / p.pN;
+            int nstart = row0 - b0 * p.pN;
+            for (int bb = b0; nstart > -32 && bb < p.pB; ++bb, nstart -= p.pN)
+              tma_store_4d(&tmOut, stg, 0, nstart, bb, c0 >> 2);
+          }
+          bulk_commit();
+        }
+        buf ^= 1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// ---- host side -----------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+int encode(CUtensorMap* m, const void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
+           const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return -3; }
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<void*>(addr), dims, strides_bytes,
+                  box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed: CUresult %d", what, (int)r); return -3; }
+  return 0;
+}
+
+int num_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+void plan_n(int C, int* BN, int* n_tiles) {
+  if (C <= 256) { *n_tiles = 1; *BN = (int)round_up(C, 16); return; }
+  int best_bn = 256, best_nt = (int)ceil_div(C, 256), best_pad = best_nt * 256;
+  for (int bn = 256; bn >= 128; bn -= 32) {   // multi-tile: BN % 32 == 0 so no epilogue chunk straddles tiles
+    int nt = (int)ceil_div(C, bn);
+    if (nt * bn < best_pad) { best_pad = nt * bn; best_bn = bn; best_nt = nt; }
+  }
+  *BN = best_bn; *n_tiles = best_nt;
+}
+
+}  // namespace
+
+bool obprop_tc_supported(int C) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("RD_OBPROP_TC"); env = (e && e[0] == '0') ? 0 : 1; }
+  return env == 1 && C % 4 == 0 && C >= 16;
+}
+
+int obprop_tc_fwd(const float* x, const float* W, const float* b, const float* scale, int mod, int64_t rows, int C,
+                  float* out, int perm, int pB, int pN, int pdob, int pD, cudaStream_t st) {
+  if (perm && pdob != 4) { set_error("obprop_tc_fwd: permuted store needs d_ob == 4"); return -2; }
+  if (rows > 0x7fffffffLL) { set_error("obprop_tc_fwd: too many rows"); return -2; }
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out)) & 15) {
+    set_error("obprop_tc_fwd: pointers must be 16-byte aligned");
+    return -2;
+  }
+  TcParams p;
+  p.M = (int)rows; p.C = C;
+  plan_n(C, &p.BN, &p.n_tiles);
+  p.m_tiles = (int)ceil_div(rows, BM);
+  p.k_blocks = (int)ceil_div(C, BK);
+  const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
+  const int fixed = 1024 + 8 * STG_BYTES + 2 * 256 * 4 + 256;
+  p.nstages = (SMEM_LIMIT - fixed) / stage_bytes;
+  if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
+  if (p.nstages < 2) { set_error("obprop_tc_fwd: not enough shared memory"); return -2; }
+  const int smem_bytes = fixed + p.nstages * stage_bytes;
+  p.bias = b; p.scale = scale; p.scale_mod = mod;
+  p.perm = perm; p.pB = pB; p.pN = pN;
+
+  CUtensorMap tmA, tmW, tmOut;
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)C * 4};
+    cuuint32_t box[2] = {BK, BM};
+    RD_TRY(encode(&tmA, x, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "x"));
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)C};
+    cuuint64_t str[1] = {(cuuint64_t)C * 4};
+    cuuint32_t box[2] = {BK, (cuuint32_t)p.BN};
+    RD_TRY(encode(&tmW, W, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "W"));
+  }
+  if (!perm) {
+    cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+    cuuint64_t str[1] = {(cuuint64_t)C * 4};
+    cuuint32_t box[2] = {32, 32};
+    RD_TRY(encode(&tmOut, out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "out"));
+  } else {
+    const int T = C / 4;
+    cuuint64_t dims[4] = {4, (cuuint64_t)pN, (cuuint64_t)pB, (cuuint64_t)T};
+    cuuint64_t str[3] = {16, (cuuint64_t)pD * 4, (cuuint64_t)pB * pD * 4};
+    cuuint32_t box[4] = {4, 32, 1, 8};
+    RD_TRY(encode(&tmOut, out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "out[T,B,D]"));
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(obprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  int total = p.m_tiles * p.n_tiles;
+  int grid = total < num_sms() ? total : num_sms();
+  obprop_tc_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmA, tmW, tmOut, p);
+  RD_CHECK_LAUNCH("obprop_tc_kernel");
+  return 0;
+}
+
+}  // namespace rd

@@ -1,0 +1,116 @@
+// TransformerConv forward (code/transformer_conv.py:139-207): node-level Q/K/V/skip projections
+// through the generic GEMM (the reference projects per EDGE, E/N times redundant), then an
+// edge-softmax grouped by target and a deterministic gather-aggregate (ascending edge order, no
+// atomics).  Graphs on this path are tiny (N <= 128 sensors), so one warp scans the whole edge
+// list per (target, head).
+#include <math.h>
+
+#include "rd_kernels.cuh"
+
+namespace rd {
+namespace {
+
+__global__ void tconv_logits_kernel(const float* __restrict__ q, const float* __restrict__ k,
+                                    const int64_t* __restrict__ src, const int64_t* __restrict__ tgt,
+                                    const float* __restrict__ edge_w, int E, int H, int F, float* __restrict__ logit) {
+  int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (w >= E * H) return;
+  int e = w / H, h = w - e * H;
+  if (edge_w) {  // supplied weights replace the dot product (code/transformer_conv.py:199-200)
+    if (lane == 0) logit[w] = edge_w[e];
+    return;
+  }
+  const float* qi = q + ((long long)tgt[e] * H + h) * F;
+  const float* kj = k + ((long long)src[e] * H + h) * F;
+  float s = 0.f;
+  for (int f = lane; f < F; f += 32) s += qi[f] * kj[f];
+  s = warp_sum(s);
+  if (lane == 0) logit[w] = s / sqrtf((float)F);
+}
+
+__global__ void tconv_softmax_kernel(const float* __restrict__ logit, const int64_t* __restrict__ tgt, int E, int H,
+                                     int n_nodes, float* __restrict__ alpha) {
+  int w = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (w >= n_nodes * H) return;
+  int node = w / H, h = w - node * H;
+  float mx = -INFINITY;
+  for (int e = lane; e < E; e += 32)
+    if (tgt[e] == node) mx = fmaxf(mx, logit[e * H + h]);
+  mx = warp_max(mx);
+  if (mx == -INFINITY) return;
+  float sum = 0.f;
+  for (int e = lane; e < E; e += 32)
+    if (tgt[e] == node) sum += expf(logit[e * H + h] - mx);
+  sum = warp_sum(sum) + 1e-16f;
+  for (int e = lane; e < E; e += 32)
+    if (tgt[e] == node) alpha[e * H + h] = expf(logit[e * H + h] - mx) / sum;
+}
+
+__global__ void tconv_aggregate_kernel(const float* __restrict__ v, const float* __restrict__ alpha,
+                                       const int64_t* __restrict__ src, const int64_t* __restrict__ tgt, int E, int H,
+                                       int F, float* __restrict__ out /* holds the skip term on entry */) {
+  int node = blockIdx.x;
+  for (int c = threadIdx.x; c < H * F; c += blockDim.x) {
+    int h = c / F;
+    float acc = 0.f;
+    for (int e = 0; e < E; ++e)
+      if (tgt[e] == node) acc += alpha[e * H + h] * v[(long long)src[e] * H * F + c];
+    out[(long long)node * H * F + c] += acc;
+  }
+}
+
+GemmP proj(const float* x, int in_ch, const float* W, const float* b, float* y, int n, int HF) {
+  GemmP g;
+  g.A = x; g.ta = 0; g.sAi = in_ch; g.sAk = 1;
+  g.B = W; g.tb = 1; g.sBj = in_ch; g.sBk = 1;
+  g.C = y; g.sCi = HF; g.sCj = 1;
+  g.M = n; g.N = HF; g.K = in_ch; g.bias = b;
+  return g;
+}
+
+}  // namespace
+}  // namespace rd
+
+using namespace rd;
+
+extern "C" size_t rd_transformer_conv_scratch_bytes(int32_t n_nodes, int32_t in_ch, int32_t heads, int32_t out_ch,
+                                                    int32_t E) {
+  (void)in_ch;
+  int64_t hf = (int64_t)heads * out_ch;
+  return (size_t)(3 * round_up(n_nodes * hf, 64) + round_up((int64_t)E * heads, 64)) * sizeof(float);
+}
+
+extern "C" int rd_transformer_conv_fwd(const float* x, int32_t n_nodes, int32_t in_ch, int32_t heads, int32_t out_ch,
+                                       const int64_t* edge_src, const int64_t* edge_tgt, const float* edge_w, int32_t E,
+                                       const float* wq, const float* bq, const float* wk, const float* bk,
+                                       const float* wv, const float* bv, const float* ws, const float* bs, float* out,
+                                       float* alpha, void* scratch, void* stream) {
+  if (!x || !edge_src || !edge_tgt || !wq || !wk || !wv || !ws || !out || !alpha || !scratch || n_nodes < 1 ||
+      in_ch < 1 || heads < 1 || out_ch < 1 || E < 0) {
+    set_error("rd_transformer_conv_fwd: bad arguments");
+    return -2;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  const int HF = heads * out_ch;
+  float* q = (float*)scratch;
+  float* k = q + round_up((int64_t)n_nodes * HF, 64);
+  float* v = k + round_up((int64_t)n_nodes * HF, 64);
+  float* logit = v + round_up((int64_t)n_nodes * HF, 64);
+  RD_TRY(gemm(proj(x, in_ch, wq, bq, q, n_nodes, HF), st));
+  RD_TRY(gemm(proj(x, in_ch, wk, bk, k, n_nodes, HF), st));
+  RD_TRY(gemm(proj(x, in_ch, wv, bv, v, n_nodes, HF), st));
+  RD_TRY(gemm(proj(x, in_ch, ws, bs, out, n_nodes, HF), st));   // root/skip term, code/transformer_conv.py:168-175
+  if (E == 0) return 0;
+  tconv_logits_kernel<<<(unsigned)ceil_div((int64_t)E * heads * 32, 256), 256, 0, st>>>(q, k, edge_src, edge_tgt, edge_w,
+                                                                                      E, heads, out_ch, logit);
+  RD_CHECK_LAUNCH("tconv_logits_kernel");
+  cudaMemsetAsync(alpha, 0, sizeof(float) * (size_t)E * heads, st);
+  tconv_softmax_kernel<<<(unsigned)ceil_div((int64_t)n_nodes * heads * 32, 256), 256, 0, st>>>(logit, edge_tgt, E, heads,
+                                                                                             n_nodes, alpha);
+  RD_CHECK_LAUNCH("tconv_softmax_kernel");
+  tconv_aggregate_kernel<<<n_nodes, 128, 0, st>>>(v, alpha, edge_src, edge_tgt, E, heads, out_ch, out);
+  RD_CHECK_LAUNCH("tconv_aggregate_kernel");
+  return 0;
+}

@@ -1,0 +1,240 @@
+"""torch.autograd bindings over the C ABI (librd_b200.so).  PyTorch is plumbing here: it owns the
+device memory, the stream and the autograd graph; every number is produced by our CUDA kernels."""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as L
+
+# parameters that take part in the live path, in the order they are passed to the autograd
+# Function (state-dict keys of the reference model)
+_LAYER_KEYS = ["self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.out_proj.weight",
+               "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight",
+               "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"]
+_HEAD_FIELDS = [("emb.weight", "emb_weight"), ("emb.bias", "emb_bias"),
+                ("ob_propagation.lin_value.weight", "ob1_value_weight"),
+                ("ob_propagation.lin_value.bias", "ob1_value_bias"),
+                ("ob_propagation_layer2.lin_value.weight", "ob2_value_weight"),
+                ("ob_propagation_layer2.lin_value.bias", "ob2_value_bias"),
+                ("mlp_static.0.weight", "mlp0_weight"), ("mlp_static.0.bias", "mlp0_bias"),
+                ("mlp_static.2.weight", "mlp2_weight"), ("mlp_static.2.bias", "mlp2_bias")]
+
+
+def used_param_fields(nlayers, static):
+    """[(state-dict key, struct field path)] in Function-argument order."""
+    out = []
+    for key, field in _HEAD_FIELDS:
+        if not static and key.startswith("emb."):
+            continue
+        out.append((key, (field,)))
+    for l in range(nlayers):
+        for k, f in zip(_LAYER_KEYS, L._LAYER_FIELDS):
+            out.append(("transformer_encoder.layers.%d.%s" % (l, k), ("layer", l, f)))
+    return out
+
+
+def _set_field(struct, path, value):
+    if len(path) == 1:
+        setattr(struct, path[0], value)
+    else:
+        setattr(getattr(struct, path[0])[path[1]], path[2], value)
+
+
+def pe_timescales(max_len, d_pe=16):
+    """max_len ** linspace(0, 1, d_pe/2) in fp64, cast to fp32 (code/models_rd.py:31,34)."""
+    return (float(max_len) ** np.linspace(0, 1, d_pe // 2)).astype(np.float32)
+
+
+class Plan:
+    """Everything about one model instance that the kernels need besides the tensors."""
+
+    def __init__(self, d_inp, d_ob, nhead, nhid, nlayers, d_static, n_classes, max_len, dropout, static):
+        self.N, self.d_ob, self.nhead, self.nhid, self.nlayers = d_inp, d_ob, nhead, nhid, nlayers
+        self.d_static = d_static if static else 0
+        self.n_classes, self.T, self.dropout = n_classes, max_len, float(dropout)
+        self.static = static
+        self.fields = used_param_fields(nlayers, static)
+        self.timescales = pe_timescales(max_len)
+        self.node_scale = None      # [N] device tensor (rd_node_scale)
+        self.R_u = None             # [1, N*d_ob] device tensor
+        self.rng_state = None       # int64[2] device tensor {seed, counter}
+        self.owner = None           # weakref to the module (receives the flat gradient bucket)
+
+    def dims(self, B, training):
+        d = L.RdDims()
+        d.B, d.T, d.N, d.d_ob = B, self.T, self.N, self.d_ob
+        d.nhead, d.nhid, d.nlayers = self.nhead, self.nhid, self.nlayers
+        d.d_static, d.n_classes = self.d_static, self.n_classes
+        d.training = 1 if training else 0
+        d.dropout_p = self.dropout
+        d.ln_eps = 1e-5
+        for i, v in enumerate(self.timescales):
+            d.pe_timescales[i] = float(v)
+        return d
+
+
+def _as_f32(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t.contiguous()
+
+
+class RaindropV2Function(torch.autograd.Function):
+    """logits = Raindrop_v2.forward(...) (code/models_rd.py:278-387) as ONE autograd node:
+    rd_raindrop_v2_fwd in forward, rd_raindrop_v2_bwd in backward."""
+
+    @staticmethod
+    def forward(ctx, plan, training, src, static, times, lengths, *params):
+        lib = L.load()
+        if not src.is_cuda:
+            raise L.RaindropB200Error("raindrop_b200 runs on CUDA tensors only (no CPU fallback)")
+        T, B = src.shape[0], src.shape[1]
+        if T != plan.T or src.shape[2] != 2 * plan.N:
+            raise ValueError("src must be [max_len=%d, B, 2*d_inp=%d], got %s" % (plan.T, 2 * plan.N, tuple(src.shape)))
+        dims = plan.dims(B, training)
+        P = L.RdParams()
+        P.R_u = plan.R_u.data_ptr()
+        keep = []
+        for (key, path), t in zip(plan.fields, params):
+            if t.dtype != torch.float32 or not t.is_contiguous():
+                t = _as_f32(t)
+            keep.append(t)
+            _set_field(P, path, t.data_ptr())
+        ws_bytes = lib.rd_workspace_bytes(C.byref(dims))
+        if ws_bytes == 0:
+            L.check(-2, "rd_workspace_bytes")
+        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=src.device)
+        logits = torch.empty(B, plan.n_classes, dtype=torch.float32, device=src.device)
+        rng = plan.rng_state
+        rc = lib.rd_raindrop_v2_fwd(C.byref(dims), C.byref(P), src.data_ptr(), L.ptr(static), times.data_ptr(),
+                                    lengths.data_ptr(), plan.node_scale.data_ptr(), L.ptr(rng), ws.data_ptr(),
+                                    logits.data_ptr(), L.stream_ptr())
+        L.check(rc, "rd_raindrop_v2_fwd")
+        ctx.plan, ctx.dims, ctx.P, ctx.ws = plan, dims, P, ws
+        ctx.keep = (keep, static, lengths, plan.node_scale, plan.R_u)
+        ctx.shapes = [tuple(t.shape) for t in params]
+        ctx.mark_non_differentiable()
+        plan.last_workspace = ws
+        plan.last_dims = dims
+        return logits
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        lib = L.load()
+        plan, dims = ctx.plan, ctx.dims
+        keep, static, lengths, node_scale, _ = ctx.keep
+        d_logits = _as_f32(d_logits)
+        dev = d_logits.device
+        offs, total = [], 0
+        for shp in ctx.shapes:
+            n = int(np.prod(shp))
+            offs.append(total)
+            total += (n + 3) // 4 * 4
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        G = L.RdGrads()
+        base = flat.data_ptr()
+        for (key, path), off in zip(plan.fields, offs):
+            _set_field(G, path, base + 4 * off)
+        sc_bytes = lib.rd_backward_scratch_bytes(C.byref(dims))
+        scratch = torch.empty(sc_bytes // 4, dtype=torch.float32, device=dev)
+        rc = lib.rd_raindrop_v2_bwd(C.byref(dims), C.byref(ctx.P), L.ptr(static), lengths.data_ptr(),
+                                    node_scale.data_ptr(), ctx.ws.data_ptr(), d_logits.data_ptr(), C.byref(G),
+                                    scratch.data_ptr(), L.stream_ptr())
+        L.check(rc, "rd_raindrop_v2_bwd")
+        grads = []
+        for shp, off in zip(ctx.shapes, offs):
+            n = int(np.prod(shp))
+            grads.append(flat[off:off + n].view(shp))
+        owner = plan.owner() if plan.owner is not None else None
+        if owner is not None:
+            owner._flat_grad = flat          # the DDP bucket: one all-reduce covers every gradient
+        ctx.ws = None
+        return (None, None, None, None, None, None) + tuple(grads)
+
+
+class ObPropLayerFunction(torch.autograd.Function):
+    """One observation-propagation layer on `rows` node rows at once (rd_obprop_fwd / _bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, node_scale, mod):
+        lib = L.load()
+        x, weight, bias = _as_f32(x), _as_f32(weight), _as_f32(bias)
+        rows, Cc = x.shape
+        out = torch.empty_like(x)
+        rc = lib.rd_obprop_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), node_scale.data_ptr(), int(mod),
+                               rows, Cc, out.data_ptr(), L.stream_ptr())
+        L.check(rc, "rd_obprop_fwd")
+        ctx.save_for_backward(x, weight, out, node_scale)
+        ctx.mod = int(mod)
+        return out
+
+    @staticmethod
+    def backward(ctx, d_out):
+        lib = L.load()
+        x, weight, out, node_scale = ctx.saved_tensors
+        d_out = _as_f32(d_out)
+        rows, Cc = x.shape
+        d_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        d_w = torch.empty_like(weight)
+        d_b = torch.empty(Cc, dtype=torch.float32, device=x.device)
+        sc = torch.empty(lib.rd_obprop_bwd_scratch_bytes(rows, Cc) // 4, dtype=torch.float32, device=x.device)
+        rc = lib.rd_obprop_bwd(x.data_ptr(), out.data_ptr(), d_out.data_ptr(), weight.data_ptr(),
+                               node_scale.data_ptr(), ctx.mod, rows, Cc, L.ptr(d_x), d_w.data_ptr(), d_b.data_ptr(),
+                               sc.data_ptr(), L.stream_ptr())
+        L.check(rc, "rd_obprop_bwd")
+        return d_x, d_w, d_b, None, None
+
+
+def node_scale(edge_index, edge_weights, n_nodes):
+    """s[n] = sum over incoming edges of the segment softmax (rd_node_scale)."""
+    lib = L.load()
+    tgt = edge_index[1].contiguous().long()
+    w = _as_f32(edge_weights)
+    s = torch.empty(n_nodes, dtype=torch.float32, device=w.device)
+    L.check(lib.rd_node_scale(tgt.data_ptr(), w.data_ptr(), tgt.numel(), n_nodes, s.data_ptr(), L.stream_ptr()),
+            "rd_node_scale")
+    return s
+
+
+def positional_encoding(times, max_len, d_pe=16):
+    """[T, B] -> [T, B, 16] on the device (rd_positional_encoding)."""
+    assert d_pe == 16
+    lib = L.load()
+    t = _as_f32(times)
+    out = torch.empty(t.shape + (d_pe,), dtype=torch.float32, device=t.device)
+    ts = (C.c_float * 8)(*[float(v) for v in pe_timescales(max_len, d_pe)])
+    L.check(lib.rd_positional_encoding(t.data_ptr(), t.numel(), ts, out.data_ptr(), d_pe, 0, L.stream_ptr()),
+            "rd_positional_encoding")
+    return out
+
+
+def transformer_conv(x, edge_index, edge_weights, heads, out_channels, wq, bq, wk, bk, wv, bv, ws, bs):
+    """TransformerConv forward (inference; code/transformer_conv.py:139-207).  Returns (out, alpha)."""
+    lib = L.load()
+    x = _as_f32(x)
+    n, in_ch = x.shape
+    src_i = edge_index[0].contiguous().long()
+    tgt_i = edge_index[1].contiguous().long()
+    E = src_i.numel()
+    ew = None if edge_weights is None else _as_f32(edge_weights)
+    out = torch.empty(n, heads * out_channels, dtype=torch.float32, device=x.device)
+    alpha = torch.empty(E, heads, dtype=torch.float32, device=x.device)
+    sc = torch.empty(max(1, lib.rd_transformer_conv_scratch_bytes(n, in_ch, heads, out_channels, E) // 4),
+                     dtype=torch.float32, device=x.device)
+    ps = [_as_f32(t) for t in (wq, bq, wk, bk, wv, bv, ws, bs)]
+    rc = lib.rd_transformer_conv_fwd(x.data_ptr(), n, in_ch, heads, out_channels, src_i.data_ptr(), tgt_i.data_ptr(),
+                                     L.ptr(ew), E, *[p.data_ptr() for p in ps], out.data_ptr(), alpha.data_ptr(),
+                                     sc.data_ptr(), L.stream_ptr())
+    L.check(rc, "rd_transformer_conv_fwd")
+    return out, alpha
+
+
+def workspace_view(plan, which):
+    """Named activation buffer of the most recent forward (parity tests)."""
+    lib = L.load()
+    n = C.c_int64(0)
+    off = lib.rd_workspace_offset(C.byref(plan.last_dims), which, C.byref(n))
+    if off < 0:
+        L.check(-2, "rd_workspace_offset")
+    return plan.last_workspace[off // 4: off // 4 + n.value]

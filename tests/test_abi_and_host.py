@@ -1,0 +1,128 @@
+"""CPU: the C-ABI library loads and exports every symbol the header declares (no compute calls
+without a GPU), and the host-side logic of the drop-in (constructor, state dict, plan, sharding)."""
+import os
+import re
+
+import pytest
+import torch
+
+from helpers import build_dropin
+from raindrop_b200 import functional as RF
+from raindrop_b200 import lib as L
+from raindrop_b200.synth import make_batch, model_config, used_param_keys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ensure_built():
+    if not os.path.isfile(L.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+
+
+def test_library_exports_every_declared_symbol():
+    _ensure_built()
+    header = open(os.path.join(ROOT, "include", "raindrop_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rd_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    lib = L.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.rd_abi_version() == 1
+
+
+def test_struct_layout_matches_header_sizes():
+    import ctypes as C
+    assert C.sizeof(L.RdDims) == 4 * 10 + 4 * 2 + 4 * 8
+    assert C.sizeof(L.RdParams) == 8 * 11 + 8 * 12 * L.RD_MAX_LAYERS
+    assert C.sizeof(L.RdGrads) == 8 * 10 + 8 * 12 * L.RD_MAX_LAYERS
+
+
+def test_workspace_queries_are_pure_host_code():
+    _ensure_built()
+    import ctypes as C
+    lib = L.load()
+    plan = RF.Plan(34, 4, 2, 272, 2, 6, 2, 60, 0.2, True)
+    d = plan.dims(128, True)
+    ws, sc = lib.rd_workspace_bytes(C.byref(d)), lib.rd_backward_scratch_bytes(C.byref(d))
+    assert ws > 0 and sc > 0 and ws % 256 == 0
+    n = C.c_int64(0)
+    off = lib.rd_workspace_offset(C.byref(d), L.WS_ENC_IN, C.byref(n))
+    assert off > 0 and n.value == 60 * 128 * 152
+    d.nhead = 7          # 152 % 7 != 0 -> rejected with a message, not a crash
+    assert lib.rd_workspace_bytes(C.byref(d)) == 0
+    assert b"divisible" in lib.rd_last_error_string()
+
+
+@pytest.mark.parametrize("name", ["P19", "PAM", "TINY"])
+def test_dropin_state_dict_contract(name):
+    """Same keys/shapes as the reference (via the oracle, which is key-identical to it), R_u absent."""
+    from oracle.raindrop_oracle import build_oracle_model
+    cfg = model_config(name)
+    model = build_dropin(cfg, 3, device="cpu")
+    sd, ref = model.state_dict(), build_oracle_model(cfg).state_dict()
+    assert list(sd.keys()) == list(ref.keys())
+    assert all(sd[k].shape == ref[k].shape for k in sd)
+    assert "R_u" not in sd and not isinstance(model.R_u, torch.nn.Parameter)
+    assert [k for k, _ in model._plan.fields] == [k for k in _order(used_param_keys(cfg), model)]
+    assert len(sd) == (64 if cfg["static"] else 62)
+
+
+def _order(keys, model):
+    field_keys = [k for k, _ in model._plan.fields]
+    assert sorted(field_keys) == sorted(keys)
+    return field_keys
+
+
+def test_seeded_construction_matches_reference_init():
+    """torch.manual_seed(1) + construct draws the same initial weights as the reference does
+    (same module creation order), so a seeded run of code/Raindrop.py starts from the same point."""
+    from oracle.raindrop_oracle import build_oracle_model
+    from raindrop_b200.models_rd import Raindrop_v2
+    cfg = model_config("TINY")
+    torch.manual_seed(1)
+    m = Raindrop_v2(cfg["d_inp"], cfg["d_model"], cfg["nhead"], cfg["nhid"], cfg["nlayers"], cfg["dropout"],
+                    cfg["max_len"], cfg["d_static"], cfg["MAX"], 0.5, "mean", cfg["n_classes"],
+                    torch.ones(cfg["d_inp"], cfg["d_inp"]))
+    o = build_oracle_model(cfg, seed=1)
+    for (k1, a), (k2, b) in zip(m.state_dict().items(), o.state_dict().items()):
+        assert k1 == k2 and torch.equal(a, b), k1
+    assert torch.equal(m.R_u, o.R_u)
+
+
+def test_forward_fails_loudly_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CPU-only check")
+    cfg = model_config("TINY")
+    model = build_dropin(cfg, 3, device="cpu")
+    batch = make_batch(cfg, 2, seed=0)
+    with pytest.raises(L.RaindropB200Error):
+        model.forward(batch["src"], batch["static"], batch["times"], batch["lengths"])
+
+
+def test_unbuilt_configurations_raise():
+    from raindrop_b200.models_rd import Observation_progation, Raindrop_v2
+    with pytest.raises(NotImplementedError):
+        Raindrop_v2(5, 20, 2, 40, 2, 0.2, 12, 3, 100, 0.5, "mean", 2, torch.ones(5, 5), sensor_wise_mask=True)
+    with pytest.raises(NotImplementedError):
+        Observation_progation(20, 20, n_nodes=5, ob_dim=4, heads=2)
+
+
+def test_synthetic_batch_conventions():
+    cfg = model_config("P19")
+    b = make_batch(cfg, 16, seed=3)
+    T, N = cfg["max_len"], cfg["d_inp"]
+    assert b["src"].shape == (T, 16, 2 * N) and b["times"].shape == (T, 16)
+    assert torch.equal(b["lengths"], (b["times"] > 0).sum(0))
+    m = b["src"][:, :, N:]
+    assert set(m.unique().tolist()) <= {0.0, 1.0}
+    assert torch.all(b["src"][:, :, :N][m == 0] == 0)                     # unobserved values are zero
+    pad = torch.arange(T)[:, None] >= b["lengths"][None, :]
+    assert torch.all(b["src"][pad] == 0)                                   # padding rows are all zero
+    t0 = make_batch(cfg, 4, seed=3, first_time_zero=True)
+    assert torch.all(t0["times"][0] == 0) and torch.all(t0["lengths"] == (t0["times"] > 0).sum(0))
+    z = make_batch(cfg, 4, seed=3, zero_sensors=10)
+    assert int((z["src"][:, 0, :N].abs().sum(0) == 0).sum()) >= 10
+    again = make_batch(cfg, 16, seed=3)
+    assert all(torch.equal(b[k], again[k]) for k in ("src", "times", "lengths", "y", "static"))

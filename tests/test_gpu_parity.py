@@ -1,0 +1,322 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the reference's outputs
+(tests/golden, generated from the reference's own files) and against the CPU oracle on seeded inputs.
+
+Tolerance (BASELINE.json north_star: "forward output within 1e-3 rel-tol of the reference"), defined
+normwise as max|delta| / max|ref|.  The observation-propagation GEMMs run in
+TF32 (expected ~1e-4), everything else in fp32 (expected ~1e-6).
+"""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import (build_dropin, case_setup, check_against_golden, load_golden, normwise, sparse_structure,
+                     to_dev)
+from raindrop_b200.synth import make_batch, model_config, synth_weights, used_param_keys
+
+pytestmark = pytest.mark.gpu
+
+FWD_TOL = 1e-3     # north_star tolerance on forward tensors
+GRAD_TOL = 5e-3    # gradients: same TF32 operands, one more contraction deep
+
+GOLDEN_CASES = ["tiny_dense", "tiny_t0", "tiny_sparse", "tiny8_nostatic", "p19_b4", "p19_b5_leave10", "p12_b2", "pam_b2"]
+
+
+def _run_dropin(cfg, batch, weight_seed, train=False):
+    from raindrop_b200 import functional as RF
+    from raindrop_b200 import lib as L
+    model = build_dropin(cfg, weight_seed)
+    model.train(train)
+    d = to_dev(batch)
+    logits, distance, third = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+    assert third is None and distance.dim() == 0
+    loss = F.cross_entropy(logits, d["y"])
+    loss.backward()
+    T, B = d["src"].shape[0], d["src"].shape[1]
+    D = cfg["d_inp"] * cfg["d_ob"] + 16
+    enc_in = RF.workspace_view(model._plan, L.WS_ENC_IN).view(T, B, D)
+    enc_out = RF.workspace_view(model._plan, L.WS_ENC_OUT).view(T, B, D)
+    return model, logits, distance, loss, enc_in, enc_out
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_golden_fixture(golden_dir, name):
+    """CUDA forward + backward vs the outputs of the reference's own unmodified files."""
+    z, meta = load_golden(golden_dir, name)
+    cfg, batch = case_setup(meta)
+    model, logits, distance, loss, enc_in, enc_out = _run_dropin(cfg, batch, meta["weight_seed"])
+    errs = {}
+    assert normwise(logits, z["logits"]) < FWD_TOL
+    assert abs(loss.item() - float(z["loss"])) < 1e-3 * max(1.0, abs(float(z["loss"])))
+    assert float(distance) == float(z["distance"]) == 0.0
+    full = meta["full_tensors"]
+    D4 = cfg["d_inp"] * cfg["d_ob"]
+    check_against_golden(z, full, "obs", enc_in[:, :, :D4], FWD_TOL, errs)
+    check_against_golden(z, full, "pe", enc_in[:, :, D4:], 1e-5, errs)
+    # the encoder output at padded positions is never used by the reference (masked mean) -> compare valid rows
+    lengths = batch["lengths"]
+    T = enc_out.shape[0]
+    valid = (torch.arange(T)[:, None] < lengths[None, :]).to(enc_out.device)[:, :, None]
+    if full:
+        ref = torch.from_numpy(z["enc"]).to(enc_out.device)
+        e = normwise(enc_out * valid, ref * valid)
+        assert e < FWD_TOL, e
+    params = dict(model.named_parameters())
+    for k in used_param_keys(cfg):
+        assert params[k].grad is not None, k
+        check_against_golden(z, full, "grad." + k, params[k].grad, GRAD_TOL, errs)
+    unused = [k for k, p in params.items() if k not in set(used_param_keys(cfg))]
+    assert all(params[k].grad is None for k in unused)     # same 34 tensors get gradient as in the reference
+    print(name, "worst:", max(errs.items(), key=lambda kv: kv[1]))
+
+
+@pytest.mark.parametrize("cfg_name,B,opts", [
+    ("P19", 1, {}), ("P19", 37, {}), ("P19", 100, {"first_time_zero": True}), ("P19", 128, {"zero_sensors": 10}),
+    ("P12", 5, {}), ("PAM", 3, {}), ("TINY", 7, {"full_length": True}), ("TINY8", 9, {}),
+])
+def test_against_oracle(cfg_name, B, opts):
+    """Seeded inputs, sizes the dense oracle finishes in seconds (arbitrary B incl. remainder batches)."""
+    from oracle.raindrop_oracle import build_oracle_model
+    cfg = model_config(cfg_name, dropout=0.2)
+    batch = make_batch(cfg, B, seed=100 + B, **opts)
+    oracle = build_oracle_model(cfg).eval()
+    synth_weights(oracle, cfg, seed=21)
+    stages = {}
+    ref_logits, _, _ = oracle.forward_dense(batch["src"], batch["static"], batch["times"], batch["lengths"], stages=stages)
+    ref_loss = F.cross_entropy(ref_logits, batch["y"])
+    ref_loss.backward()
+    model, logits, _, loss, enc_in, enc_out = _run_dropin(cfg, batch, 21)
+    D4 = cfg["d_inp"] * cfg["d_ob"]
+    assert normwise(enc_in[:, :, :D4], stages["obs"]) < FWD_TOL
+    assert normwise(enc_in[:, :, D4:], stages["pe"]) < 1e-5
+    assert normwise(logits, ref_logits) < FWD_TOL
+    gp, go = dict(model.named_parameters()), dict(oracle.named_parameters())
+    for k in used_param_keys(cfg):
+        e = normwise(gp[k].grad, go[k].grad)
+        assert e < GRAD_TOL, (k, e)
+
+
+def test_edge_cases():
+    """lengths = 1, a sensor never observed, a sensor always observed, isolated graph node."""
+    from oracle.raindrop_oracle import build_oracle_model
+    cfg = model_config("TINY", dropout=0.2)
+    cfg["global_structure"] = sparse_structure(cfg["d_inp"], 9)
+    batch = make_batch(cfg, 6, seed=5)
+    batch["lengths"][0] = 1
+    batch["times"][1:, 0] = 0
+    batch["src"][1:, 0, :] = 0
+    N = cfg["d_inp"]
+    batch["src"][:, :, 2] = 0; batch["src"][:, :, N + 2] = 0          # never observed
+    batch["src"][:, :, N + 3] = (batch["times"] > 0).float()           # always observed
+    oracle = build_oracle_model(cfg).eval()
+    synth_weights(oracle, cfg, seed=3)
+    ref, _, _ = oracle.forward(batch["src"], batch["static"], batch["times"], batch["lengths"])
+    model, logits, _, _, _, _ = _run_dropin(cfg, batch, 3)
+    assert normwise(logits, ref.detach()) < FWD_TOL
+
+
+def test_full_size_properties():
+    """BASELINE configs[1] at full size (B = 128): size-independent properties."""
+    cfg = model_config("P19", dropout=0.2)
+    batch = make_batch(cfg, 128, seed=77)
+    model = build_dropin(cfg, 4).eval()
+    d = to_dev(batch)
+    with torch.no_grad():
+        a, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+        b, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+        assert torch.equal(a, b)                                           # deterministic / idempotent
+        h1, _, _ = model.forward(d["src"][:, :64], d["static"][:64], d["times"][:, :64], d["lengths"][:64])
+        h2, _, _ = model.forward(d["src"][:, 64:], d["static"][64:], d["times"][:, 64:], d["lengths"][64:])
+        assert normwise(torch.cat([h1, h2]), a) < 1e-5                      # samples are independent
+        perm = torch.randperm(128, device="cuda")
+        p, _, _ = model.forward(d["src"][:, perm], d["static"][perm], d["times"][:, perm], d["lengths"][perm])
+        assert normwise(p, a[perm]) < 1e-5                                  # permutation equivariance
+    assert torch.isfinite(a).all()
+
+
+def test_whole_validation_set_batch():
+    """evaluate_standard pushes the whole validation set through in one batch (code/utils_rd.py:310-320)."""
+    cfg = model_config("P19", dropout=0.2)
+    model = build_dropin(cfg, 4).eval()
+    batch = make_batch(cfg, 3880, seed=9)
+    d = to_dev(batch)
+    with torch.no_grad():
+        big, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+        part, _, _ = model.forward(d["src"][:, 1000:1100], d["static"][1000:1100], d["times"][:, 1000:1100],
+                                   d["lengths"][1000:1100])
+    assert big.shape == (3880, 2) and torch.isfinite(big).all()
+    assert normwise(part, big[1000:1100]) < 1e-5
+
+
+# ---- operator level -----------------------------------------------------------------------------
+def test_node_scale_and_obprop_operator(golden_dir):
+    from raindrop_b200 import functional as RF
+    from raindrop_b200.models_rd import Observation_progation
+    z = np.load(golden_dir + "/operators.npz")
+    x = torch.from_numpy(z["obprop.x"]).cuda()
+    ei = torch.from_numpy(z["obprop.edge_index"]).cuda()
+    ew = torch.from_numpy(z["obprop.edge_w"]).cuda()
+    N, Cc = x.shape
+    layer = Observation_progation(in_channels=Cc, out_channels=Cc, heads=1, n_nodes=N, ob_dim=4)
+    layer.load_state_dict({k[len("obprop.sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("obprop.sd.")})
+    layer = layer.cuda()
+    out, (ei2, alpha) = layer(x, p_t=None, edge_index=ei, edge_weights=ew, use_beta=False, edge_attr=None,
+                              return_attention_weights=True)
+    assert normwise(out, z["obprop.beta0.out"]) < FWD_TOL
+    assert torch.equal(ei2.cpu(), torch.from_numpy(z["obprop.beta0.edge_index"]))
+    assert np.array_equal(alpha.cpu().numpy(), z["obprop.beta0.alpha"])     # pre-softmax weights, bit exact
+    # rows with no incoming edge are exactly zero, like scatter-add leaves them
+    s = RF.node_scale(ei, ew, N).cpu()
+    has_in = torch.zeros(N, dtype=torch.bool)
+    has_in[ei[1].cpu()] = True
+    assert torch.all((s == 0) == ~has_in)
+    # operator backward vs autograd of the closed form
+    xr = x.clone().requires_grad_(True)
+    o = RF.ObPropLayerFunction.apply(xr, layer.lin_value.weight, layer.lin_value.bias, s.cuda(), N)
+    w = torch.randn_like(o)
+    (o * w).sum().backward()
+    xc = x.detach().cpu().double().requires_grad_(True)
+    W = layer.lin_value.weight.detach().cpu().double().requires_grad_(True)
+    bb = layer.lin_value.bias.detach().cpu().double().requires_grad_(True)
+    oc = F.relu(xc @ W.T + bb) * s.double()[:, None]
+    (oc * w.cpu().double()).sum().backward()
+    assert normwise(xr.grad, xc.grad) < GRAD_TOL
+    assert normwise(layer.lin_value.weight.grad, W.grad) < GRAD_TOL
+    assert normwise(layer.lin_value.bias.grad, bb.grad) < GRAD_TOL
+
+
+@pytest.mark.parametrize("rows,Cc", [(34 * 3, 240), (500, 860), (129, 16), (257, 1024), (40, 2400), (1000, 64)])
+def test_obprop_layer_shapes(rows, Cc):
+    """Tensor-core layer kernel on the channel widths of every BASELINE config, ragged row counts."""
+    from raindrop_b200 import functional as RF
+    g = torch.Generator().manual_seed(rows + Cc)
+    x = torch.randn(rows, Cc, generator=g)
+    W = torch.randn(Cc, Cc, generator=g) / Cc ** 0.5
+    b = torch.randn(Cc, generator=g) * 0.1
+    s = torch.rand(17, generator=g)
+    ref = F.relu(x.double() @ W.double().T + b.double()) * s.double()[torch.arange(rows) % 17][:, None]
+    out = RF.ObPropLayerFunction.apply(x.cuda(), W.cuda(), b.cuda(), s.cuda(), 17)
+    assert normwise(out, ref) < FWD_TOL
+
+
+def test_positional_encoding():
+    from oracle.raindrop_oracle import positional_encoding
+    from raindrop_b200.models_rd import PositionalEncodingTF
+    for max_len in (60, 215, 600):
+        t = torch.rand(max_len, 7) * 50
+        pe = PositionalEncodingTF(16, max_len, 100)(t)
+        assert pe.is_cuda and normwise(pe, positional_encoding(t, max_len)) < 1e-5
+
+
+def test_transformer_conv(golden_dir):
+    from raindrop_b200.models_rd import TransformerConv
+    z = np.load(golden_dir + "/operators.npz")
+    x = torch.from_numpy(z["tconv.x"]).cuda()
+    ei = torch.from_numpy(z["obprop.edge_index"]).cuda()
+    ew = torch.from_numpy(z["obprop.edge_w"]).cuda()
+    for tag, heads, w in (("tconv.w.", 1, ew), ("tconv.qk.", 2, None)):
+        conv = TransformerConv(in_channels=7, out_channels=5, heads=heads)
+        conv.load_state_dict({k[len(tag + "sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + "sd.")})
+        conv = conv.cuda()
+        out, (_, alpha) = conv(x, edge_index=ei, edge_weights=w, edge_attr=None, return_attention_weights=True)
+        assert normwise(out, z[tag + "out"]) < 1e-5
+        assert normwise(alpha, z[tag + "alpha"]) < 1e-5
+
+
+def test_cross_entropy_and_adam():
+    import ctypes as C
+    from raindrop_b200 import lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(37, 8, generator=g).cuda()
+    y = torch.randint(0, 8, (37,), generator=g).cuda()
+    loss = torch.zeros(1, device="cuda"); dl = torch.zeros_like(logits)
+    L.check(lib.rd_cross_entropy_fwd_bwd(logits.data_ptr(), y.data_ptr(), 37, 8, loss.data_ptr(), dl.data_ptr(),
+                                         L.stream_ptr()), "ce")
+    lt = logits.clone().requires_grad_(True)
+    ref = F.cross_entropy(lt, y); ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-6 and normwise(dl, lt.grad) < 1e-5
+    p = torch.randn(1000, generator=g).cuda(); p_ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.Adam([p_ref], lr=1e-2)
+    m = torch.zeros_like(p); v = torch.zeros_like(p); step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for it in range(5):
+        grad = torch.randn(1000, generator=g).cuda()
+        p_ref.grad = grad.clone(); opt.step()
+        L.check(lib.rd_adam_step(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), 1000, 1e-2, 0.9, 0.999, 1e-8,
+                                 1.0, step.data_ptr(), L.stream_ptr()), "adam")
+    assert step.item() == 5 and normwise(p, p_ref.detach()) < 1e-5
+
+
+# ---- training mode --------------------------------------------------------------------------------
+def test_train_mode_dropout_statistics_and_replay():
+    """Dropout cannot match the reference's RNG stream; check keep-rate, determinism under the same
+    (seed, counter) and that backward uses exactly the forward's masks (finite-difference free check:
+    with p -> masks replayed via rd_debug_dropout_mask the lifted input matches)."""
+    import ctypes as C
+    from raindrop_b200 import functional as RF
+    from raindrop_b200 import lib as L
+    cfg = model_config("P19", dropout=0.2)
+    batch = make_batch(cfg, 16, seed=1)
+    model = build_dropin(cfg, 2).train()
+    d = to_dev(batch)
+    out1, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+    x0_train = RF.workspace_view(model._plan, L.WS_X0).clone()
+    rng = RF.workspace_view(model._plan, L.WS_RNG).clone()
+    out2, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+    assert not torch.equal(out1, out2)                       # counter advanced -> new masks
+    model.eval()
+    with torch.no_grad():
+        model.forward(d["src"], d["static"], d["times"], d["lengths"])
+    x0_eval = RF.workspace_view(model._plan, L.WS_X0).clone()
+    nz = x0_eval != 0
+    kept = (x0_train[nz] != 0).float().mean().item()
+    assert abs(kept - 0.8) < 0.01, kept
+    assert torch.allclose(x0_train[nz][x0_train[nz] != 0], (x0_eval[nz] / 0.8)[x0_train[nz] != 0], rtol=1e-6)
+    # replay the lift mask through the debug entry point: index space is [T, B, 4N]
+    T, B, D4 = 60, 16, cfg["d_inp"] * 4
+    mask = torch.empty(T * B * D4, device="cuda")
+    lib = L.load()
+    L.check(lib.rd_debug_dropout_mask(rng.data_ptr(), L.SITE_LIFT, mask.numel(), C.c_float(0.2), mask.data_ptr(),
+                                      L.stream_ptr()), "mask")
+    mask = mask.view(T, B, cfg["d_inp"], 4).permute(1, 2, 0, 3).reshape(B * cfg["d_inp"], T * 4)
+    assert torch.allclose(x0_train.view_as(mask), x0_eval.view_as(mask) * mask, rtol=1e-6)
+
+
+def test_train_step_matches_autograd_loop():
+    """TrainStep (C ABI + CUDA graph) == the reference-style loop (autograd + torch.optim.Adam), dropout 0."""
+    from raindrop_b200.train import TrainStep
+    cfg = model_config("P19", dropout=0.0)
+    B = 32
+    m1 = build_dropin(cfg, 6).train()
+    m2 = build_dropin(cfg, 6).train()
+    opt = torch.optim.Adam(m1.parameters(), lr=1e-3)
+    ts = TrainStep(m2, B, lr=1e-3, use_graph=True)
+    with torch.no_grad():   # one-time kernel attribute setup must not happen inside the capture
+        d0 = to_dev(make_batch(cfg, B, seed=49))
+        m1.forward(d0["src"], d0["static"], d0["times"], d0["lengths"])
+    ts.capture(warmup=0)
+    for it in range(4):
+        batch = make_batch(cfg, B, seed=50 + it)
+        d = to_dev(batch)
+        logits, _, _ = m1.forward(d["src"], d["static"], d["times"], d["lengths"])
+        loss = F.cross_entropy(logits, d["y"])
+        opt.zero_grad(); loss.backward(); opt.step()
+        ts.load_batch(d)
+        l2 = ts.step()
+        assert abs(l2.item() - loss.item()) < 2e-4 * max(1.0, abs(loss.item())), (it, l2.item(), loss.item())
+    p1, p2 = dict(m1.named_parameters()), dict(m2.named_parameters())
+    for k in used_param_keys(cfg):
+        assert normwise(p2[k], p1[k]) < 2e-3, k
+
+
+def test_dropin_checkpoint_roundtrip():
+    """state_dict from the oracle (== reference keys/shapes) loads into the drop-in and back."""
+    from oracle.raindrop_oracle import build_oracle_model
+    cfg = model_config("P19", dropout=0.2)
+    oracle = build_oracle_model(cfg)
+    model = build_dropin(cfg, 1)
+    model.load_state_dict(oracle.state_dict())
+    back = model.state_dict()
+    assert list(back.keys()) == list(oracle.state_dict().keys())
+    for k, v in oracle.state_dict().items():
+        assert torch.equal(back[k].cpu(), v)
