@@ -105,6 +105,9 @@ enum rd_ws_buffer {
 
 int rd_abi_version(void);
 const char* rd_last_error_string(void);
+/* number of kernels this library has launched so far in this process (host-side counter; a
+ * CUDA-graph replay re-runs captured launches without passing through here) */
+uint64_t rd_launch_count(void);
 
 /* ---- graph prologue --------------------------------------------------------------------
  * s[n] = sum_{e: tgt[e]==n} softmax_{e->n}(w)   with PyG's  exp(w-max)/(sum+1e-16).

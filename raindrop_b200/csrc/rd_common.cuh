@@ -11,6 +11,7 @@ namespace rd {
 // ---- error reporting across the C ABI (never throw) ---------------------------------------
 void set_error(const char* fmt, ...);
 const char* last_error();
+unsigned long long launch_count();  // kernels launched by this library so far (host counter)
 int check_launch(const char* what);  // cudaPeekAtLastError -> 0 / -1
 
 #define RD_CHECK_LAUNCH(what)                    \

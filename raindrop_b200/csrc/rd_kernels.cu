@@ -18,7 +18,10 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 const char* last_error() { return g_err; }
+static unsigned long long g_launches = 0;
+unsigned long long launch_count() { return g_launches; }
 int check_launch(const char* what) {
+  ++g_launches;
   cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
@@ -430,6 +433,7 @@ int cross_entropy(const float* logits, const int64_t* y, int B, int ncls, float*
 int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
          float gscale, int64_t* step, cudaStream_t st) {
   adam_tick_kernel<<<1, 1, 0, st>>>(step);
+  RD_CHECK_LAUNCH("adam_tick_kernel");
   adam_kernel<<<blocks_for(n), TPB, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, gscale, step);
   RD_CHECK_LAUNCH("adam_kernel");
   return 0;

@@ -398,6 +398,7 @@ extern "C" {
 
 int rd_abi_version(void) { return RD_ABI_VERSION; }
 const char* rd_last_error_string(void) { return last_error(); }
+uint64_t rd_launch_count(void) { return launch_count(); }
 
 int rd_node_scale(const int64_t* edge_tgt, const float* edge_w, int32_t E, int32_t N, float* out, void* stream) {
   if (!edge_tgt || !edge_w || !out || E < 0 || N < 1) { set_error("rd_node_scale: bad arguments"); return -2; }

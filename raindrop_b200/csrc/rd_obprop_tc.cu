@@ -14,9 +14,11 @@
 //             accumulators in TMEM, double buffered (2 x 256 columns) so the epilogue of tile i
 //             overlaps the MMAs of tile i+1;
 //   * warps 2-5: epilogue - tcgen05.ld 32 columns at a time, + bias, relu, * s, stage through
-//             shared memory and write with TMA bulk stores (coalesced 128 B lines; for the second
-//             layer a 4-D tensor map scatters straight into the [T, B, D] encoder input,
-//             code/models_rd.py:338-341, no separate permute pass).
+//             shared memory and write with TMA bulk stores (coalesced 128 B lines).  For the second
+//             layer the result goes straight into the [T, B, D] encoder input
+//             (code/models_rd.py:338-341): there a lane's 4 values of one timestamp are 16 contiguous
+//             bytes and consecutive lanes are consecutive sensors, so plain st.global.v4 is already
+//             a coalesced 512-byte warp store - no staging, no separate permute pass.
 // fp32 bits are fed to the tensor core unchanged (TF32 reads the top 19 bits); SURVEY.md section 7
 // measured the effect on the logits at 1e-5 normwise.
 #include <cuda.h>
@@ -40,7 +42,8 @@ struct TcParams {
   const float* bias;
   const float* scale;
   int scale_mod;
-  int perm, pB, pN;
+  int perm, pB, pN, pD;
+  float* out;
 };
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
@@ -74,10 +77,6 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_store_4d(const CUtensorMap* map, uint32_t src, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
-               ::"l"(map), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
@@ -213,13 +212,39 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const float sc = row < p.M ? __ldg(p.scale + (row % p.scale_mod)) : 0.f;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
+      // perm: this lane's row is sensor n of sample b; its 4 values of one timestamp are 16
+      // contiguous bytes of out[t, b, n*4 .. n*4+3] and consecutive lanes are consecutive sensors,
+      // so one st.global.v4 per timestamp is a fully coalesced 512-byte warp store (no staging).
+      float* perm_row = nullptr;
+      if (p.perm && row < p.M) {
+        const int b = row / p.pN, n = row - b * p.pN;
+        perm_row = p.out + (size_t)b * p.pD + (size_t)n * 4;
+      }
       for (int ch = 0; ch < n_chunks; ++ch) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + ch * 32), v);
+        const float* bs = bias_s + acc * 256 + ch * 32;
+        const int c0 = col0 + ch * 32;
+        if (p.perm) {
+          if (perm_row) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+              const int t = (c0 >> 2) + j4;
+              if (4 * t < p.C && ch * 32 + 4 * j4 < p.BN) {
+                float4 o;
+                o.x = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bs[4 * j4 + 0], 0.f) * sc;
+                o.y = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bs[4 * j4 + 1], 0.f) * sc;
+                o.z = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bs[4 * j4 + 2], 0.f) * sc;
+                o.w = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bs[4 * j4 + 3], 0.f) * sc;
+                *reinterpret_cast<float4*>(perm_row + (size_t)t * p.pB * p.pD) = o;
+              }
+            }
+          }
+          continue;
+        }
         if (lane == 0) bulk_wait_read<1>();   // the store that used this staging buffer has drained
         __syncwarp();
         const uint32_t stg = my_stg + (uint32_t)buf * STG_BYTES;
-        const float* bs = bias_s + acc * 256 + ch * 32;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           float4 o;
@@ -227,24 +252,14 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           o.y = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bs[4 * j4 + 1], 0.f) * sc;
           o.z = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bs[4 * j4 + 2], 0.f) * sc;
           o.w = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bs[4 * j4 + 3], 0.f) * sc;
-          // plain: [32 rows][128 B] with the 128B swizzle the tensor map expects
-          // perm : [8 t][32 n][4 k] dense (box {4, 32, 1, 8})
-          const uint32_t off = p.perm ? (uint32_t)((j4 * 32 + lane) * 16)
-                                      : (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) << 4));
+          // [32 rows][128 B] with the 128B swizzle the tensor map expects
+          const uint32_t off = (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) << 4));
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
         }
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
-          const int c0 = col0 + ch * 32;
-          if (!p.perm) {
-            tma_store_2d(&tmOut, stg, c0, row0);
-          } else {
-            const int b0 = row0 / p.pN;
-            int nstart = row0 - b0 * p.pN;
-            for (int bb = b0; nstart > -32 && bb < p.pB; ++bb, nstart -= p.pN)
-              tma_store_4d(&tmOut, stg, 0, nstart, bb, c0 >> 2);
-          }
+          tma_store_2d(&tmOut, stg, c0, row0);
           bulk_commit();
         }
         buf ^= 1;
@@ -344,7 +359,7 @@ int obprop_tc_fwd(const float* x, const float* W, const float* b, const float* s
   if (p.nstages < 2) { set_error("obprop_tc_fwd: not enough shared memory"); return -2; }
   const int smem_bytes = fixed + p.nstages * stage_bytes;
   p.bias = b; p.scale = scale; p.scale_mod = mod;
-  p.perm = perm; p.pB = pB; p.pN = pN;
+  p.perm = perm; p.pB = pB; p.pN = pN; p.pD = pD; p.out = out;
 
   CUtensorMap tmA, tmW, tmOut;
   {
@@ -365,11 +380,7 @@ int obprop_tc_fwd(const float* x, const float* W, const float* b, const float* s
     cuuint32_t box[2] = {32, 32};
     RD_TRY(encode(&tmOut, out, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "out"));
   } else {
-    const int T = C / 4;
-    cuuint64_t dims[4] = {4, (cuuint64_t)pN, (cuuint64_t)pB, (cuuint64_t)T};
-    cuuint64_t str[3] = {16, (cuuint64_t)pD * 4, (cuuint64_t)pB * pD * 4};
-    cuuint32_t box[4] = {4, 32, 1, 8};
-    RD_TRY(encode(&tmOut, out, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE, "out[T,B,D]"));
+    tmOut = tmA;   // permuted output is written with plain vector stores; the map is not used
   }
   static bool attr_set = false;
   if (!attr_set) {

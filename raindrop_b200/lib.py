@@ -60,6 +60,7 @@ class RdGrads(C.Structure):
 SIGNATURES = {
     "rd_abi_version": (C.c_int, []),
     "rd_last_error_string": (C.c_char_p, []),
+    "rd_launch_count": (C.c_uint64, []),
     "rd_node_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
     "rd_obprop_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
                                 C.c_int32, C.c_void_p, C.c_void_p]),
