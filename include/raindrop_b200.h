@@ -120,9 +120,13 @@ int rd_node_scale(const int64_t* edge_tgt, const float* edge_w, int32_t E, int32
 /* ---- one observation-propagation layer (operator level) -----------------------------------
  * out[r, :] = relu(x[r, :] . W^T + b) * node_scale[r % scale_mod]      x, out: [rows, C]
  * Replaces Observation_progation.forward with use_beta=False (code/Ob_propagation.py:94-132,
- * 157-160,187-211,213-228) for `rows / N` samples at once (code/models_rd.py:322-336). */
+ * 157-160,187-211,213-228) for `rows / N` samples at once (code/models_rd.py:322-336).
+ * The tensor cores take TF32 operands: x and weight are first rounded (RN) into `scratch`
+ * (rd_obprop_fwd_scratch_bytes(rows, C) bytes); accumulation is fp32.  scratch == NULL promises that
+ * x and weight are already TF32-representable (low 13 mantissa bits zero): no rounding pass. */
+size_t rd_obprop_fwd_scratch_bytes(int64_t rows, int32_t C);
 int rd_obprop_fwd(const float* x, const float* weight, const float* bias, const float* node_scale,
-                  int32_t scale_mod, int64_t rows, int32_t C, float* out, void* stream);
+                  int32_t scale_mod, int64_t rows, int32_t C, float* out, void* scratch, void* stream);
 
 /* Backward of the above.  d_out, out: [rows, C].  Writes d_x (may be NULL), d_weight, d_bias.
  * scratch: rd_obprop_bwd_scratch_bytes(rows, C) bytes. */

@@ -87,6 +87,7 @@ struct GemmP {
   long long sAzo = 0, sAzi = 0, sBzo = 0, sBzi = 0, sCzo = 0, sCzi = 0;
   // split-K (only for nz == 1): partial sums go to `partial` [nsplit][M][N], then reduced
   int nsplit = 1; float* partial = nullptr;
+  float* asum = nullptr;   // optional extra output: asum[i] = sum_k A(i,k)  (bias gradient of a TN weight-grad GEMM)
   // epilogue, applied in this order
   float alpha = 1.f;
   const float* bias = nullptr;                         // + bias[j]
@@ -102,6 +103,8 @@ struct GemmP {
 int gemm(const GemmP& p, cudaStream_t st);
 // out[n] (+)= sum_s partial[s*n_elems + n]
 int reduce_partials(const float* partial, int nsplit, int64_t n_elems, float* out, cudaStream_t st);
+// same over a [nsplit][n1 + n2] buffer with two destinations
+int reduce_partials2(const float* partial, int nsplit, int64_t n1, float* out1, int64_t n2, float* out2, cudaStream_t st);
 // out[j] = sum_i x[i*ld + j], i < rows, j < cols; scratch >= colsum_scratch_floats(rows, cols)
 int64_t colsum_scratch_floats(int64_t rows, int cols);
 int colsum(const float* x, int64_t rows, int cols, int64_t ld, float* out, float* scratch, cudaStream_t st);

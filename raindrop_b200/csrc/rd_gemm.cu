@@ -86,6 +86,9 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(GemmP p) {
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
+  // optional: asum[i] = sum_k A(i,k) (the bias gradient rides along with the weight-gradient GEMM)
+  const bool do_asum = p.asum != nullptr && blockIdx.y == 0;
+  float asum_acc[4] = {0.f, 0.f, 0.f, 0.f};
 
   int buf = 0;
   if (kbeg < kend) {
@@ -105,6 +108,10 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(GemmP p) {
       for (int r = 0; r < 4; ++r)
 #pragma unroll
         for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
+      if (do_asum) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) asum_acc[r] += av[r];
+      }
     }
     if (more) {
       store_tiles(buf ^ 1);
@@ -114,7 +121,8 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(GemmP p) {
   }
 
   if (p.nsplit > 1) {
-    float* __restrict__ P = p.partial + (long long)split * p.M * p.N;
+    const long long per_split = (long long)p.M * p.N + (p.asum ? p.M : 0);
+    float* __restrict__ P = p.partial + (long long)split * per_split;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       int i = i0 + ty * 4 + r;
@@ -124,8 +132,14 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(GemmP p) {
         int j = j0 + tx * 4 + c;
         if (j < p.N) P[(long long)i * p.N + j] = acc[r][c] * p.alpha;
       }
+      if (do_asum && tx == 0) P[(long long)p.M * p.N + i] = asum_acc[r];
     }
     return;
+  }
+  if (do_asum && tx == 0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+      if (i0 + ty * 4 + r < p.M) p.asum[i0 + ty * 4 + r] = asum_acc[r];
   }
   float* __restrict__ C = p.C + zo * p.sCzo + zi * p.sCzi;
 #pragma unroll
@@ -140,16 +154,16 @@ __global__ void __launch_bounds__(NT) gemm_f32_kernel(GemmP p) {
   }
 }
 
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nsplit, long long n,
-                                       float* __restrict__ out) {
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nsplit, long long n, long long n1,
+                                       float* __restrict__ out, float* __restrict__ out2) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float s = 0.f;
   for (int k = 0; k < nsplit; ++k) s += partial[(long long)k * n + i];  // fixed order: deterministic
-  out[i] = s;
+  if (i < n1) out[i] = s; else out2[i - n1] = s;
 }
 
-constexpr int CS_ROWS = 256;  // rows per colsum chunk
+constexpr int CS_ROWS = 32;  // rows per colsum chunk
 
 __global__ void colsum_partial_kernel(const float* __restrict__ x, long long rows, int cols,
                                       long long ld, float* __restrict__ partial) {
@@ -177,7 +191,7 @@ int64_t gemm_splitk_plan(int M, int N, int K, int* nsplit) {
     --ns;
   }
   *nsplit = ns;
-  return ns > 1 ? (int64_t)ns * M * N : 0;
+  return ns > 1 ? (int64_t)ns * ((int64_t)M * N + M) : 0;   // room for the fused A-column-sums too
 }
 
 int gemm(const GemmP& p, cudaStream_t st) {
@@ -199,15 +213,22 @@ int gemm(const GemmP& p, cudaStream_t st) {
     else gemm_f32_kernel<false, false><<<grid, NT, 0, st>>>(p);
   }
   RD_CHECK_LAUNCH("gemm_f32_kernel");
-  if (p.nsplit > 1) return reduce_partials(p.partial, p.nsplit, (int64_t)p.M * p.N, p.C, st);
+  if (p.nsplit > 1)
+    return reduce_partials2(p.partial, p.nsplit, (int64_t)p.M * p.N, p.C, p.asum ? p.M : 0, p.asum, st);
+  return 0;
+}
+
+int reduce_partials2(const float* partial, int nsplit, int64_t n1, float* out1, int64_t n2, float* out2,
+                     cudaStream_t st) {
+  int64_t n = n1 + n2;
+  if (n <= 0) return 0;
+  reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, nsplit, n, n1, out1, out2);
+  RD_CHECK_LAUNCH("reduce_partials_kernel");
   return 0;
 }
 
 int reduce_partials(const float* partial, int nsplit, int64_t n, float* out, cudaStream_t st) {
-  if (n <= 0) return 0;
-  reduce_partials_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, nsplit, n, out);
-  RD_CHECK_LAUNCH("reduce_partials_kernel");
-  return 0;
+  return reduce_partials2(partial, nsplit, n, out, 0, nullptr, st);
 }
 
 int64_t colsum_scratch_floats(int64_t rows, int cols) { return ceil_div(rows, CS_ROWS) * cols; }

@@ -36,6 +36,27 @@ namespace {
 constexpr int TPB = 256;
 inline unsigned blocks_for(int64_t n, int tpb = TPB) { return (unsigned)ceil_div(n, tpb); }
 
+__device__ __forceinline__ float to_tf32(float v) {   // round-to-nearest TF32 (10-bit mantissa)
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+// y[j*rows + i] = RN_tf32(x[i*cols + j]): transposed, rounded copy of a weight matrix
+__global__ void transpose_round_kernel(const float* __restrict__ x, int rows, int cols, float* __restrict__ y) {
+  __shared__ float tile[32][33];
+  int bx = blockIdx.x * 32, by = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int i = by + r, j = bx + threadIdx.x;
+    tile[r][threadIdx.x] = (i < rows && j < cols) ? x[(long long)i * cols + j] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    int j = bx + r, i = by + threadIdx.x;
+    if (i < rows && j < cols) y[(long long)j * rows + i] = to_tf32(tile[threadIdx.x][r]);
+  }
+}
+
 __global__ void rng_capture_kernel(uint64_t* state, uint64_t* cap, int advance) {
   cap[0] = state[0];
   cap[1] = state[1];
@@ -43,7 +64,7 @@ __global__ void rng_capture_kernel(uint64_t* state, uint64_t* cap, int advance) 
 }
 
 __global__ void lift_kernel(const float* __restrict__ src, const float* __restrict__ R_u, int B, int T, int N,
-                            int d_ob, float drop_p, const uint64_t* __restrict__ rng, float* __restrict__ X0) {
+                            int d_ob, float drop_p, const uint64_t* __restrict__ rng, int round, float* __restrict__ X0) {
   const long long C = (long long)T * d_ob;
   const long long total = (long long)B * N * C;
   long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -58,7 +79,7 @@ __global__ void lift_kernel(const float* __restrict__ src, const float* __restri
     uint64_t idx = ((uint64_t)t * B + b) * (uint64_t)(N * d_ob) + (uint64_t)(n * d_ob + k);
     v *= dropout_scale(rng, SITE_LIFT, idx, drop_p, 1.f / (1.f - drop_p));
   }
-  X0[o] = v;
+  X0[o] = round ? to_tf32(v) : v;
 }
 
 struct TS8 { float v[8]; };
@@ -143,7 +164,7 @@ __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float
   }
 }
 
-constexpr int LN_ROWS = 256;
+constexpr int LN_ROWS = 32;
 __global__ void layernorm_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ stats,
                                            const float* __restrict__ dy, long long rows, int D,
                                            float* __restrict__ partial) {
@@ -235,7 +256,7 @@ __global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, long long
 
 __global__ void obprop_out_grad_kernel(const float* __restrict__ dZ, const float* __restrict__ Z,
                                        const float* __restrict__ s, int B, int T, int N, int d_ob, int D,
-                                       float* __restrict__ dZ2) {
+                                       int round, float* __restrict__ dZ2) {
   const long long C = (long long)T * d_ob;
   long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= (long long)B * N * C) return;
@@ -244,7 +265,8 @@ __global__ void obprop_out_grad_kernel(const float* __restrict__ dZ, const float
   int b = (int)(row / N), n = (int)(row - (long long)b * N);
   int t = c / d_ob, k = c - t * d_ob;
   long long zi = ((long long)t * B + b) * D + n * d_ob + k;
-  dZ2[o] = (Z[zi] > 0.f) ? dZ[zi] * __ldg(s + n) : 0.f;
+  float v = (Z[zi] > 0.f) ? dZ[zi] * __ldg(s + n) : 0.f;
+  dZ2[o] = round ? to_tf32(v) : v;
 }
 
 __global__ void apply_dropout_kernel(const float* __restrict__ x, long long n, float p,
@@ -325,10 +347,17 @@ int rng_capture(uint64_t* state, uint64_t* cap, int advance, cudaStream_t st) {
   return 0;
 }
 
+int transpose_round(const float* x, int rows, int cols, float* y, cudaStream_t st) {
+  dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
+  transpose_round_kernel<<<grid, dim3(32, 8), 0, st>>>(x, rows, cols, y);
+  RD_CHECK_LAUNCH("transpose_round_kernel");
+  return 0;
+}
+
 int lift(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p, const uint64_t* rng,
-         float* X0, cudaStream_t st) {
+         int round, float* X0, cudaStream_t st) {
   int64_t total = (int64_t)B * N * T * d_ob;
-  lift_kernel<<<blocks_for(total), TPB, 0, st>>>(src, R_u, B, T, N, d_ob, drop_p, rng, X0);
+  lift_kernel<<<blocks_for(total), TPB, 0, st>>>(src, R_u, B, T, N, d_ob, drop_p, rng, round, X0);
   RD_CHECK_LAUNCH("lift_kernel");
   return 0;
 }
@@ -402,9 +431,9 @@ int masked_mean_bwd(const float* dout, int64_t ld, const int64_t* lengths, int T
 }
 
 int obprop_out_grad(const float* dZ, const float* Z, const float* s, int B, int T, int N, int d_ob, int D,
-                    float* dZ2, cudaStream_t st) {
+                    int round, float* dZ2, cudaStream_t st) {
   int64_t total = (int64_t)B * N * T * d_ob;
-  obprop_out_grad_kernel<<<blocks_for(total), TPB, 0, st>>>(dZ, Z, s, B, T, N, d_ob, D, dZ2);
+  obprop_out_grad_kernel<<<blocks_for(total), TPB, 0, st>>>(dZ, Z, s, B, T, N, d_ob, D, round, dZ2);
   RD_CHECK_LAUNCH("obprop_out_grad_kernel");
   return 0;
 }

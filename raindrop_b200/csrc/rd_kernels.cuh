@@ -7,8 +7,12 @@ namespace rd {
 int rng_capture(uint64_t* rng_state, uint64_t* captured, int advance, cudaStream_t st);
 
 // X0[(b*N+n), t*d_ob+k] = dropout(relu(src[t,b,n] * R_u[n*d_ob+k]))    code/models_rd.py:285-296,323-327
+// round != 0: values are rounded (RN) to TF32 so the tensor-core layer reads them exactly
 int lift(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p,
-         const uint64_t* rng, float* X0, cudaStream_t st);
+         const uint64_t* rng, int round, float* X0, cudaStream_t st);
+
+// y [cols, rows] = RN_tf32(x [rows, cols])^T
+int transpose_round(const float* x, int rows, int cols, float* y, cudaStream_t st);
 
 int posenc(const float* times, int64_t n_tokens, const float* ts8_host, float* out, int64_t ld, int col0,
            cudaStream_t st);
@@ -39,7 +43,7 @@ int masked_mean_bwd(const float* dout, int64_t ld, const int64_t* lengths, int T
 
 // dZ2[(b*N+n), t*d_ob+k] = dZ[t,b,n*d_ob+k] * s[n] * (Z[t,b,n*d_ob+k] > 0)
 int obprop_out_grad(const float* dZ, const float* Z, const float* s, int B, int T, int N, int d_ob, int D,
-                    float* dZ2, cudaStream_t st);
+                    int round, float* dZ2, cudaStream_t st);
 
 // y[i] = x[i] * mask(site, i)   (re-generates the forward's dropout mask)
 int apply_dropout(const float* x, int64_t n, float p, const uint64_t* rng, uint32_t site, float* y,

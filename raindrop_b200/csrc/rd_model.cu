@@ -48,7 +48,7 @@ struct Arena {
 };
 
 struct WsLayout {
-  int64_t rng, X0, H1, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
+  int64_t rng, X0, H1, W1r, W2r, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
   struct { int64_t qkv, P, Pd, ctx, r1, st1, x1, f, r2, st2; } l[RD_MAX_LAYERS];
 };
 
@@ -58,6 +58,8 @@ WsLayout ws_layout(const Shape& s) {
   w.rng = a.take(4);
   w.X0 = a.take(s.M1 * s.C);
   w.H1 = a.take(s.M1 * s.C);
+  w.W1r = a.take((int64_t)s.C * s.C);   // TF32-rounded copies of the two lin_value weights
+  w.W2r = a.take((int64_t)s.C * s.C);
   for (int i = 0; i <= s.L; ++i) w.Z[i] = a.take(s.M2 * s.D);
   int64_t pp = (int64_t)s.B * s.H * s.T * s.T;
   for (int i = 0; i < s.L; ++i) {
@@ -79,7 +81,7 @@ WsLayout ws_layout(const Shape& s) {
 }
 
 struct BwLayout {
-  int64_t dfeat, dhpre, gA, gB, gC, gF, gD, dqkv, dP, gO2, gO1, partial, aux, total;
+  int64_t dfeat, dhpre, gA, gB, gC, gF, gD, dqkv, dP, gO2, gO1, W2t, partial, aux, total;
   int64_t partial_floats, aux_floats;
 };
 
@@ -102,6 +104,7 @@ BwLayout bw_layout(const Shape& s) {
   b.dP = a.take((int64_t)s.B * s.H * s.T * s.T);
   b.gO2 = a.take(s.M1 * s.C);
   b.gO1 = a.take(s.M1 * s.C);
+  b.W2t = a.take((int64_t)s.C * s.C);
   int64_t pf = 0;
   auto upd = [&](int no, int ki, int64_t rows) { int64_t v = tn_partial_floats(no, ki, rows); if (v > pf) pf = v; };
   upd(s.C, s.C, s.M1);
@@ -142,7 +145,7 @@ GemmP nn(const float* dY, int64_t ldy, const float* W, int64_t ldw, float* dX, i
   return g;
 }
 // dW[Nout,Kin] = sum_r dY[r,Nout]^T X[r,Kin]   (split over rows, deterministic two-stage reduce)
-int tn(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int Nout, int Kin, int64_t rows,
+int tn(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db, int Nout, int Kin, int64_t rows,
        float* partial, cudaStream_t st) {
   GemmP g;
   g.A = dY; g.ta = 1; g.sAk = ldy; g.sAi = 1;
@@ -152,6 +155,7 @@ int tn(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int
   int ns;
   gemm_splitk_plan(Nout, Kin, (int)rows, &ns);
   g.nsplit = ns; g.partial = partial;
+  g.asum = db;   // db[n] = sum_r dY[r, n] comes out of the same pass
   return gemm(g, st);
 }
 
@@ -160,12 +164,12 @@ int tn(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, int
 // ---- observation propagation layer (operator level) ---------------------------------------------
 // Forward goes to the tcgen05 kernel when the shape fits its tiling, otherwise to the generic
 // CUDA-core GEMM (same epilogue).
-static int obprop_forward(const float* x, const float* W, const float* b, const float* s, int mod, int64_t rows,
-                          int C, float* out, int perm, int pB, int pN, int pdob, int pD, cudaStream_t st) {
-  if (obprop_tc_supported(C)) return obprop_tc_fwd(x, W, b, s, mod, rows, C, out, perm, pB, pN, pdob, pD, st);
-  GemmP g = nt(x, C, W, C, out, C, rows, C, C);
-  g.bias = b; g.relu = 1; g.rowscale = s; g.rowscale_mod = mod;
-  g.perm = perm; g.pB = pB; g.pN = pN; g.pdob = pdob; g.pD = pD;
+static int obprop_forward(const ObpropTcArgs& a, cudaStream_t st) {
+  if (obprop_tc_supported(a.C) && (!a.perm || a.pdob == 4)) return obprop_tc_fwd(a, st);
+  GemmP g = nt(a.x, a.C, a.W, a.C, a.out, a.C, a.rows, a.C, a.C);
+  g.bias = a.bias; g.relu = a.relu; g.rowscale = a.scale; g.rowscale_mod = a.scale_mod;
+  g.gate = a.gate; g.gate_ld = a.C;
+  g.perm = a.perm; g.pB = a.pB; g.pN = a.pN; g.pdob = a.pdob; g.pD = a.pD;
   return gemm(g, st);
 }
 
@@ -182,10 +186,26 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
     RD_TRY(rng_capture(rng_state, rng, 1, st));
   }
   float* X0 = ws + w.X0; float* H1 = ws + w.H1;
-  RD_TRY(lift(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, X0, st));
-  RD_TRY(obprop_forward(X0, P->ob1_value_weight, P->ob1_value_bias, nscale, s.N, s.M1, s.C, H1, 0, 0, 0, 0, 0, st));
+  // Tensor-core operands are kept exactly TF32-representable by their producers (lift, layer-1
+  // epilogue, rounded weight copies) so the MMA's operand truncation is exact.
+  const int tc = obprop_tc_supported(s.C) ? 1 : 0;
+  const float* W1 = P->ob1_value_weight; const float* W2 = P->ob2_value_weight;
+  if (tc) {
+    RD_TRY(round_tf32(W1, (int64_t)s.C * s.C, ws + w.W1r, st));
+    RD_TRY(round_tf32(W2, (int64_t)s.C * s.C, ws + w.W2r, st));
+    W1 = ws + w.W1r; W2 = ws + w.W2r;
+  }
+  RD_TRY(lift(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, tc, X0, st));
   float* Z0 = ws + w.Z[0];
-  RD_TRY(obprop_forward(H1, P->ob2_value_weight, P->ob2_value_bias, nscale, s.N, s.M1, s.C, Z0, 1, s.B, s.N, s.dob, s.D, st));
+  {
+    ObpropTcArgs a;
+    a.x = X0; a.W = W1; a.bias = P->ob1_value_bias; a.scale = nscale; a.scale_mod = s.N;
+    a.rows = s.M1; a.C = s.C; a.out = H1; a.round_out = tc;
+    RD_TRY(obprop_forward(a, st));
+    a.x = H1; a.W = W2; a.bias = P->ob2_value_bias; a.out = Z0; a.round_out = 0;
+    a.perm = 1; a.pB = s.B; a.pN = s.N; a.pdob = s.dob; a.pD = s.D;
+    RD_TRY(obprop_forward(a, st));
+  }
   RD_TRY(posenc(times, s.M2, dims->pe_timescales, Z0, s.D, s.Dm, st));
 
   const float scale = 1.f / sqrtf((float)s.hd);
@@ -276,19 +296,16 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
   // ---- head: logits = mlp2(relu(mlp0(feat)))                      code/models_rd.py:383-385
   const float* feat = ws + w.feat; const float* hpre = ws + w.hpre;
   float* dfeat = sc + b.dfeat; float* dhpre = sc + b.dhpre;
-  RD_TRY(tn(dlogits, s.ncls, hpre, s.Df, G->mlp2_weight, s.ncls, s.Df, s.B, partial, st));
-  RD_TRY(colsum(dlogits, s.B, s.ncls, s.ncls, G->mlp2_bias, aux, st));
+  RD_TRY(tn(dlogits, s.ncls, hpre, s.Df, G->mlp2_weight, G->mlp2_bias, s.ncls, s.Df, s.B, partial, st));
   {
     GemmP g = nn(dlogits, s.ncls, P->mlp2_weight, s.Df, dhpre, s.Df, s.B, s.Df, s.ncls);
     g.gate = hpre; g.gate_ld = s.Df;
     RD_TRY(gemm(g, st));
   }
-  RD_TRY(tn(dhpre, s.Df, feat, s.Df, G->mlp0_weight, s.Df, s.Df, s.B, partial, st));
-  RD_TRY(colsum(dhpre, s.B, s.Df, s.Df, G->mlp0_bias, aux, st));
+  RD_TRY(tn(dhpre, s.Df, feat, s.Df, G->mlp0_weight, G->mlp0_bias, s.Df, s.Df, s.B, partial, st));
   RD_TRY(gemm(nn(dhpre, s.Df, P->mlp0_weight, s.Df, dfeat, s.Df, s.B, s.Df, s.Df), st));
   if (s.ds > 0) {
-    RD_TRY(tn(dfeat + s.D, s.Df, statics, s.ds, G->emb_weight, s.N, s.ds, s.B, partial, st));
-    RD_TRY(colsum(dfeat + s.D, s.B, s.N, s.Df, G->emb_bias, aux, st));
+    RD_TRY(tn(dfeat + s.D, s.Df, statics, s.ds, G->emb_weight, G->emb_bias, s.N, s.ds, s.B, partial, st));
   }
   float* gA = sc + b.gA; float* gB = sc + b.gB; float* gC = sc + b.gC; float* gF = sc + b.gF; float* gD = sc + b.gD;
   float* dqkv = sc + b.dqkv; float* dP = sc + b.dP;
@@ -309,15 +326,13 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     RD_TRY(layernorm_bwd(r2, ws + w.l[l].st2, E.norm2_weight, gA, s.M2, s.D, gB, GE.norm2_weight, GE.norm2_bias, aux, st));
     const float* dg = gB;
     if (s.p > 0.f) { RD_TRY(apply_dropout(gB, s.M2 * s.D, s.p, rng, SITE_RESID2 + l, gC, st)); dg = gC; }
-    RD_TRY(tn(dg, s.D, f, s.nhid, GE.linear2_weight, s.D, s.nhid, s.M2, partial, st));
-    RD_TRY(colsum(dg, s.M2, s.D, s.D, GE.linear2_bias, aux, st));
+    RD_TRY(tn(dg, s.D, f, s.nhid, GE.linear2_weight, GE.linear2_bias, s.D, s.nhid, s.M2, partial, st));
     {
       GemmP g = nn(dg, s.D, E.linear2_weight, s.nhid, gF, s.nhid, s.M2, s.nhid, s.D);
       g.gate = f; g.gate_ld = s.nhid; g.gate_scale = ik;  // relu' and the FFN dropout mask in one
       RD_TRY(gemm(g, st));
     }
-    RD_TRY(tn(gF, s.nhid, x1, s.D, GE.linear1_weight, s.nhid, s.D, s.M2, partial, st));
-    RD_TRY(colsum(gF, s.M2, s.nhid, s.nhid, GE.linear1_bias, aux, st));
+    RD_TRY(tn(gF, s.nhid, x1, s.D, GE.linear1_weight, GE.linear1_bias, s.nhid, s.D, s.M2, partial, st));
     {
       GemmP g = nn(gF, s.nhid, E.linear1_weight, s.D, gA, s.D, s.M2, s.D, s.nhid);
       g.resid = gB; g.resid_ld = s.D;
@@ -327,8 +342,7 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, gB, GE.norm1_weight, GE.norm1_bias, aux, st));
     const float* dy = gB;
     if (s.p > 0.f) { RD_TRY(apply_dropout(gB, s.M2 * s.D, s.p, rng, SITE_RESID1 + l, gC, st)); dy = gC; }
-    RD_TRY(tn(dy, s.D, ctx, s.D, GE.out_proj_weight, s.D, s.D, s.M2, partial, st));
-    RD_TRY(colsum(dy, s.M2, s.D, s.D, GE.out_proj_bias, aux, st));
+    RD_TRY(tn(dy, s.D, ctx, s.D, GE.out_proj_weight, GE.out_proj_bias, s.D, s.D, s.M2, partial, st));
     RD_TRY(gemm(nn(dy, s.D, E.out_proj_weight, s.D, gD, s.D, s.M2, s.D, s.D), st));
     {  // dPd[b,h] = dctx V^T
       GemmP g;
@@ -363,8 +377,7 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
       g.M = s.T; g.N = s.hd; g.K = s.T; g.nz = s.B * s.H; g.nz_inner = s.H; g.alpha = scale;
       RD_TRY(gemm(g, st));
     }
-    RD_TRY(tn(dqkv, 3 * s.D, x, s.D, GE.in_proj_weight, 3 * s.D, s.D, s.M2, partial, st));
-    RD_TRY(colsum(dqkv, s.M2, 3 * s.D, 3 * s.D, GE.in_proj_bias, aux, st));
+    RD_TRY(tn(dqkv, 3 * s.D, x, s.D, GE.in_proj_weight, GE.in_proj_bias, 3 * s.D, s.D, s.M2, partial, st));
     {
       GemmP g = nn(dqkv, 3 * s.D, E.in_proj_weight, s.D, gA, s.D, s.M2, s.D, 3 * s.D);
       g.resid = gB; g.resid_ld = s.D;
@@ -374,16 +387,23 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
   // ---- observation propagation: gA = d(loss)/d(Z0) [T,B,D]          code/models_rd.py:322-343
   float* gO2 = sc + b.gO2; float* gO1 = sc + b.gO1;
   const float* X0 = ws + w.X0; const float* H1 = ws + w.H1;
-  RD_TRY(obprop_out_grad(gA, ws + w.Z[0], nscale, s.B, s.T, s.N, s.dob, s.D, gO2, st));
-  RD_TRY(tn(gO2, s.C, H1, s.C, G->ob2_value_weight, s.C, s.C, s.M1, partial, st));
-  RD_TRY(colsum(gO2, s.M1, s.C, s.C, G->ob2_value_bias, aux, st));
-  {
+  const int tc = obprop_tc_supported(s.C) ? 1 : 0;
+  RD_TRY(obprop_out_grad(gA, ws + w.Z[0], nscale, s.B, s.T, s.N, s.dob, s.D, tc, gO2, st));
+  RD_TRY(tn(gO2, s.C, H1, s.C, G->ob2_value_weight, G->ob2_value_bias, s.C, s.C, s.M1, partial, st));
+  if (tc) {
+    // dZ1 = (dZ2 . W2) * s * [H1 > 0] on the tensor cores: "NT" form against a transposed, TF32-rounded W2
+    float* W2t = sc + b.W2t;
+    RD_TRY(transpose_round(P->ob2_value_weight, s.C, s.C, W2t, st));
+    ObpropTcArgs a;
+    a.x = gO2; a.W = W2t; a.bias = nullptr; a.relu = 0; a.scale = nscale; a.scale_mod = s.N; a.gate = H1;
+    a.rows = s.M1; a.C = s.C; a.out = gO1;
+    RD_TRY(obprop_tc_fwd(a, st));
+  } else {
     GemmP g = nn(gO2, s.C, P->ob2_value_weight, s.C, gO1, s.C, s.M1, s.C, s.C);
     g.rowscale = nscale; g.rowscale_mod = s.N; g.gate = H1; g.gate_ld = s.C;
     RD_TRY(gemm(g, st));
   }
-  RD_TRY(tn(gO1, s.C, X0, s.C, G->ob1_value_weight, s.C, s.C, s.M1, partial, st));
-  RD_TRY(colsum(gO1, s.M1, s.C, s.C, G->ob1_value_bias, aux, st));
+  RD_TRY(tn(gO1, s.C, X0, s.C, G->ob1_value_weight, G->ob1_value_bias, s.C, s.C, s.M1, partial, st));
   return 0;
 }
 
@@ -405,14 +425,28 @@ int rd_node_scale(const int64_t* edge_tgt, const float* edge_w, int32_t E, int32
   return node_scale(edge_tgt, edge_w, E, N, out, (cudaStream_t)stream);
 }
 
+size_t rd_obprop_fwd_scratch_bytes(int64_t rows, int32_t C) {
+  return (size_t)(round_up(rows * C, 64) + round_up((int64_t)C * C, 64)) * sizeof(float);
+}
+
 int rd_obprop_fwd(const float* x, const float* weight, const float* bias, const float* nscale, int32_t mod,
-                  int64_t rows, int32_t C, float* out, void* stream) {
+                  int64_t rows, int32_t C, float* out, void* scratch, void* stream) {
   if (!x || !weight || !bias || !nscale || !out || rows < 0 || C < 1 || mod < 1) {
     set_error("rd_obprop_fwd: bad arguments");
     return -2;
   }
   if (rows == 0) return 0;
-  return obprop_forward(x, weight, bias, nscale, mod, rows, C, out, 0, 0, 0, 0, 0, (cudaStream_t)stream);
+  cudaStream_t st = (cudaStream_t)stream;
+  ObpropTcArgs a;
+  a.x = x; a.W = weight; a.bias = bias; a.scale = nscale; a.scale_mod = mod; a.rows = rows; a.C = C; a.out = out;
+  if (obprop_tc_supported(C) && scratch) {   // arbitrary caller data: round both operands to TF32 first
+    float* xr = (float*)scratch;
+    float* wr = xr + round_up(rows * C, 64);
+    RD_TRY(round_tf32(x, rows * C, xr, st));
+    RD_TRY(round_tf32(weight, (int64_t)C * C, wr, st));
+    a.x = xr; a.W = wr;
+  }
+  return obprop_forward(a, st);
 }
 
 size_t rd_obprop_bwd_scratch_bytes(int64_t rows, int32_t C) {
@@ -432,8 +466,8 @@ int rd_obprop_bwd(const float* x, const float* out, const float* d_out, const fl
   float* partial = dpre + round_up(rows * C, 64);
   float* aux = partial + round_up(tn_partial_floats(C, C, rows), 64);
   RD_TRY(relu_scale_bwd(d_out, out, nscale, mod, rows, C, dpre, st));
-  RD_TRY(tn(dpre, C, x, C, d_weight, C, C, rows, partial, st));
-  RD_TRY(colsum(dpre, rows, C, C, d_bias, aux, st));
+  (void)aux;
+  RD_TRY(tn(dpre, C, x, C, d_weight, d_bias, C, C, rows, partial, st));
   if (d_x) RD_TRY(gemm(nn(dpre, C, weight, C, d_x, C, rows, C, C), st));
   return 0;
 }

@@ -41,10 +41,24 @@ struct TcParams {
   int M, C, BN, n_tiles, m_tiles, k_blocks, nstages;
   const float* bias;
   const float* scale;
+  const float* gate;
   int scale_mod;
+  int relu, round_out;
   int perm, pB, pN, pD;
   float* out;
 };
+
+__device__ __forceinline__ float rn_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+__device__ __forceinline__ float epi1(float acc, float bias, float sc, int relu, int rnd) {
+  float v = acc + bias;
+  if (relu) v = fmaxf(v, 0.f);
+  v *= sc;
+  return rnd ? rn_tf32(v) : v;
+}
 
 // ---- PTX wrappers -------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -205,7 +219,7 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_t = tile / p.n_tiles, n_t = tile - m_t * p.n_tiles;
       const int col0 = n_t * p.BN;
-      for (int c = et; c < 256; c += 128) bias_s[acc * 256 + c] = (c < p.BN && col0 + c < p.C) ? __ldg(p.bias + col0 + c) : 0.f;
+      for (int c = et; c < 256; c += 128) bias_s[acc * 256 + c] = (p.bias && c < p.BN && col0 + c < p.C) ? __ldg(p.bias + col0 + c) : 0.f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
       const int row0 = m_t * BM + q * 32;
       const int row = row0 + lane;
@@ -232,10 +246,10 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int t = (c0 >> 2) + j4;
               if (4 * t < p.C && ch * 32 + 4 * j4 < p.BN) {
                 float4 o;
-                o.x = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bs[4 * j4 + 0], 0.f) * sc;
-                o.y = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bs[4 * j4 + 1], 0.f) * sc;
-                o.z = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bs[4 * j4 + 2], 0.f) * sc;
-                o.w = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bs[4 * j4 + 3], 0.f) * sc;
+                o.x = epi1(__uint_as_float(v[4 * j4 + 0]), bs[4 * j4 + 0], sc, p.relu, p.round_out);
+                o.y = epi1(__uint_as_float(v[4 * j4 + 1]), bs[4 * j4 + 1], sc, p.relu, p.round_out);
+                o.z = epi1(__uint_as_float(v[4 * j4 + 2]), bs[4 * j4 + 2], sc, p.relu, p.round_out);
+                o.w = epi1(__uint_as_float(v[4 * j4 + 3]), bs[4 * j4 + 3], sc, p.relu, p.round_out);
                 *reinterpret_cast<float4*>(perm_row + (size_t)t * p.pB * p.pD) = o;
               }
             }
@@ -248,10 +262,15 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           float4 o;
-          o.x = fmaxf(__uint_as_float(v[4 * j4 + 0]) + bs[4 * j4 + 0], 0.f) * sc;
-          o.y = fmaxf(__uint_as_float(v[4 * j4 + 1]) + bs[4 * j4 + 1], 0.f) * sc;
-          o.z = fmaxf(__uint_as_float(v[4 * j4 + 2]) + bs[4 * j4 + 2], 0.f) * sc;
-          o.w = fmaxf(__uint_as_float(v[4 * j4 + 3]) + bs[4 * j4 + 3], 0.f) * sc;
+          o.x = epi1(__uint_as_float(v[4 * j4 + 0]), bs[4 * j4 + 0], sc, p.relu, p.round_out);
+          o.y = epi1(__uint_as_float(v[4 * j4 + 1]), bs[4 * j4 + 1], sc, p.relu, p.round_out);
+          o.z = epi1(__uint_as_float(v[4 * j4 + 2]), bs[4 * j4 + 2], sc, p.relu, p.round_out);
+          o.w = epi1(__uint_as_float(v[4 * j4 + 3]), bs[4 * j4 + 3], sc, p.relu, p.round_out);
+          if (p.gate) {   // backward: pass the gradient only where the forward output was positive
+            float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row < p.M && c0 + 4 * j4 < p.C) g = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)row * p.C + c0 + 4 * j4));
+            o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
+          }
           // [32 rows][128 B] with the 128B swizzle the tensor map expects
           const uint32_t off = (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) << 4));
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "f"(o.x), "f"(o.y), "f"(o.z), "f"(o.w) : "memory");
@@ -339,11 +358,30 @@ bool obprop_tc_supported(int C) {
   return env == 1 && C % 4 == 0 && C >= 16;
 }
 
-int obprop_tc_fwd(const float* x, const float* W, const float* b, const float* scale, int mod, int64_t rows, int C,
-                  float* out, int perm, int pB, int pN, int pdob, int pD, cudaStream_t st) {
+__global__ void round_tf32_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x[i]));
+    y[i] = __uint_as_float(r);
+  }
+}
+
+int round_tf32(const float* x, int64_t n, float* y, cudaStream_t st) {
+  if (n <= 0) return 0;
+  round_tf32_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(x, n, y);
+  RD_CHECK_LAUNCH("round_tf32_kernel");
+  return 0;
+}
+
+int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st) {
+  const float* x = a.x; const float* W = a.W; float* out = a.out;
+  const int64_t rows = a.rows; const int C = a.C; const int perm = a.perm, pB = a.pB, pN = a.pN, pdob = a.pdob, pD = a.pD;
   if (perm && pdob != 4) { set_error("obprop_tc_fwd: permuted store needs d_ob == 4"); return -2; }
+  if (perm && a.gate) { set_error("obprop_tc_fwd: gate is only built for the plain layout"); return -2; }
   if (rows > 0x7fffffffLL) { set_error("obprop_tc_fwd: too many rows"); return -2; }
-  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out)) & 15) {
+  if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(W) | reinterpret_cast<uintptr_t>(out) |
+       reinterpret_cast<uintptr_t>(a.gate)) & 15) {
     set_error("obprop_tc_fwd: pointers must be 16-byte aligned");
     return -2;
   }
@@ -358,7 +396,8 @@ int obprop_tc_fwd(const float* x, const float* W, const float* b, const float* s
   if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
   if (p.nstages < 2) { set_error("obprop_tc_fwd: not enough shared memory"); return -2; }
   const int smem_bytes = fixed + p.nstages * stage_bytes;
-  p.bias = b; p.scale = scale; p.scale_mod = mod;
+  p.bias = a.bias; p.scale = a.scale; p.scale_mod = a.scale_mod; p.gate = a.gate;
+  p.relu = a.relu; p.round_out = a.round_out;
   p.perm = perm; p.pB = pB; p.pN = pN; p.pD = pD; p.out = out;
 
   CUtensorMap tmA, tmW, tmOut;

@@ -7,10 +7,24 @@ namespace rd {
 // true when the tensor-core kernel handles this layer shape (C = T*d_ob channels)
 bool obprop_tc_supported(int C);
 
-// out[r, :] = relu(x[r, :] . W^T + b) * scale[r % mod], TF32 operands, fp32 accumulate in TMEM.
+// out[r, :] = epi(x[r, :] . W^T), W: [C, C] row-major ([out, in]); TF32 operands, fp32 accumulation
+// in TMEM.  The tensor core reads the top 19 bits of each fp32 operand (truncation), so callers
+// hand in operands that are already rounded to TF32 (round_tf32 below / round_out of the producing
+// layer); then the truncation is exact and the only error is the unbiased RN rounding.
+//   epi(v) = [relu](v + bias[c]) * scale[r % mod] * [gate[r, c] > 0], optionally RN-rounded to TF32
 // perm != 0: store into the encoder input [T, B, D] instead of [rows, C] (needs d_ob == 4):
 //   row r = b*pN + n, col c = t*4 + k  ->  out[((t*pB + b)*pD) + n*4 + k]
-int obprop_tc_fwd(const float* x, const float* W, const float* b, const float* scale, int mod, int64_t rows,
-                  int C, float* out, int perm, int pB, int pN, int pdob, int pD, cudaStream_t st);
+struct ObpropTcArgs {
+  const float* x = nullptr; const float* W = nullptr; const float* bias = nullptr;
+  const float* scale = nullptr; int scale_mod = 1;
+  const float* gate = nullptr;      // [rows, C] or null (plain layout only)
+  int relu = 1, round_out = 0;
+  int64_t rows = 0; int C = 0; float* out = nullptr;
+  int perm = 0, pB = 0, pN = 0, pdob = 0, pD = 0;
+};
+int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st);
+
+// y[i] = RN_tf32(x[i])
+int round_tf32(const float* x, int64_t n, float* y, cudaStream_t st);
 
 }  // namespace rd

@@ -114,7 +114,6 @@ class RaindropV2Function(torch.autograd.Function):
         ctx.plan, ctx.dims, ctx.P, ctx.ws = plan, dims, P, ws
         ctx.keep = (keep, static, lengths, plan.node_scale, plan.R_u)
         ctx.shapes = [tuple(t.shape) for t in params]
-        ctx.mark_non_differentiable()
         plan.last_workspace = ws
         plan.last_dims = dims
         return logits
@@ -162,8 +161,9 @@ class ObPropLayerFunction(torch.autograd.Function):
         x, weight, bias = _as_f32(x), _as_f32(weight), _as_f32(bias)
         rows, Cc = x.shape
         out = torch.empty_like(x)
+        sc = torch.empty(lib.rd_obprop_fwd_scratch_bytes(rows, Cc) // 4, dtype=torch.float32, device=x.device)
         rc = lib.rd_obprop_fwd(x.data_ptr(), weight.data_ptr(), bias.data_ptr(), node_scale.data_ptr(), int(mod),
-                               rows, Cc, out.data_ptr(), L.stream_ptr())
+                               rows, Cc, out.data_ptr(), sc.data_ptr(), L.stream_ptr())
         L.check(rc, "rd_obprop_fwd")
         ctx.save_for_backward(x, weight, out, node_scale)
         ctx.mod = int(mod)

@@ -62,8 +62,9 @@ SIGNATURES = {
     "rd_last_error_string": (C.c_char_p, []),
     "rd_launch_count": (C.c_uint64, []),
     "rd_node_scale": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "rd_obprop_fwd_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "rd_obprop_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int64,
-                                C.c_int32, C.c_void_p, C.c_void_p]),
+                                C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rd_obprop_bwd_scratch_bytes": (C.c_size_t, [C.c_int64, C.c_int32]),
     "rd_obprop_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
