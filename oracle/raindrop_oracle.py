@@ -313,7 +313,7 @@ class RaindropV2Oracle(nn.Module):
         return logits, distance, None
 
     # -- independent closed form -----------------------------------------------------------------
-    def forward_dense(self, src, static, times, lengths, stages=None):
+    def forward_dense(self, src, static, times, lengths, stages=None, tf32_model=False):
         T, B = src.shape[0], src.shape[1]
         N, d_ob = self.d_inp, self.d_ob
         h = self._lift(src)
@@ -322,13 +322,67 @@ class RaindropV2Oracle(nn.Module):
         edge_index, edge_w = self._graph()
         s = node_scale_from_graph(edge_index, edge_w, N, src.dtype)[None, :, None]   # [1, N, 1]
         x = h.reshape(T, B, N, d_ob).permute(1, 2, 0, 3).reshape(B, N, T * d_ob)
-        h1 = self.ob_propagation.forward_dense(x, s)
-        h2 = self.ob_propagation_layer2.forward_dense(h1, s)
+        if tf32_model:
+            rows = x.reshape(B * N, T * d_ob)
+            h1, h2 = obprop_two_layers_tf32(rows, self.ob_propagation, self.ob_propagation_layer2,
+                                            s.expand(B, N, 1).reshape(B * N, 1))
+            h1, h2 = h1.view(B, N, -1), h2.view(B, N, -1)
+        else:
+            h1 = self.ob_propagation.forward_dense(x, s)
+            h2 = self.ob_propagation_layer2.forward_dense(h1, s)
         obs = h2.view(B, N, T, d_ob).permute(2, 0, 1, 3).reshape(T, B, N * d_ob)
         logits, r = self._tail(obs, pe, static, lengths, pad)
         if stages is not None:
             stages.update(lift=h, pe=pe, x0=x, h1=h1, obs=obs, enc=r)
         return logits, torch.zeros((), dtype=src.dtype), None
+
+
+# --------------------------------------------------------------------------------------------
+# Precision model of the CUDA path (NOT part of the reference): the tensor-core observation
+# propagation kernels take TF32 operands.  `forward_dense(..., tf32_model=True)` rounds exactly what
+# the kernels round (lifted input, both lin_value weights, the layer-1 output; in backward the
+# layer-2 output gradient and W2) and keeps everything else fp32, so that the CUDA gradients can be
+# checked tightly even though a ReLU network's gradient is discontinuous in forward perturbations.
+# --------------------------------------------------------------------------------------------
+def round_tf32(t):
+    """Round-to-nearest (ties away) to 10 explicit mantissa bits, like cvt.rna.tf32.f32."""
+    i = t.detach().contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+class _RoundSTE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        return round_tf32(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+class _LinearTF32(torch.autograd.Function):
+    """y = x . rn(W)^T + b for an already-rounded x; dX = rn(dY) . rn(W) when `round_dy`."""
+
+    @staticmethod
+    def forward(ctx, x, W, b, round_dy):
+        Wr = round_tf32(W)
+        ctx.save_for_backward(x, Wr)
+        ctx.round_dy = round_dy
+        return x @ Wr.T + b
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, Wr = ctx.saved_tensors
+        dyr = round_tf32(dy) if ctx.round_dy else dy
+        return dyr @ Wr, dyr.T @ x, dyr.sum(0), None
+
+
+def obprop_two_layers_tf32(x, layer1, layer2, s):
+    """x [rows, C] fp32 -> (h1, h2) with the kernels' rounding points (see above)."""
+    x = _RoundSTE.apply(x)
+    h1 = _RoundSTE.apply(F.relu(_LinearTF32.apply(x, layer1.lin_value.weight, layer1.lin_value.bias, False)) * s)
+    h2 = F.relu(_LinearTF32.apply(h1, layer2.lin_value.weight, layer2.lin_value.bias, True)) * s
+    return h1, h2
 
 
 def build_oracle_model(cfg, seed=1):

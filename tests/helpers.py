@@ -49,18 +49,24 @@ def normwise(a, b):
     return float((a - b).abs().max() / (b.abs().max() + 1e-30))
 
 
-def check_against_golden(z, full, name, tensor, tol, errs):
+def rel_l2(a, b):
+    a = torch.as_tensor(a).double().cpu()
+    b = torch.as_tensor(b).double().cpu()
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def check_against_golden(z, full, name, tensor, tol, errs, metric=normwise):
     """Compares `tensor` with the golden entry `name` (full tensor or fingerprint)."""
     if full:
-        e = normwise(tensor, z[name])
+        e = metric(tensor, z[name])
     else:
         fp = fingerprint(tensor)
-        e = normwise(fp["sample"], z[name + "#sample"])
+        e = metric(fp["sample"], z[name + "#sample"])
         ref_stats = z[name + "#stats"]
         # l2 norm must agree too (catches errors outside the strided sample)
         e = max(e, abs(fp["stats"][2] - ref_stats[2]) / (ref_stats[2] + 1e-30))
     errs[name] = e
-    assert e < tol, "%s: normwise error %.3e >= %.1e" % (name, e, tol)
+    assert e < tol, "%s: %s error %.3e >= %.1e" % (name, metric.__name__, e, tol)
 
 
 def build_dropin(cfg, weight_seed, device="cuda"):
