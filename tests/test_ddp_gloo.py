@@ -1,0 +1,87 @@
+"""CPU, world_size 2, gloo: the sample-sharded data-parallel host logic.
+Each rank computes the gradient of ITS shard with the CPU oracle (our kernels need a GPU), exposes it
+the way RaindropV2Function.backward does (views into one flat bucket), and `allreduce_gradients` must
+turn it into the full-batch gradient with ONE collective; the gather fallback is exercised too."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+import torch.nn.functional as F
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+class _Shim(torch.nn.Module):
+    """Duck-types what allreduce_gradients needs from Raindrop_v2: used_parameters() and _flat_grad."""
+
+    def __init__(self, oracle, keys):
+        super().__init__()
+        self.oracle, self.keys, self._flat_grad = oracle, keys, None
+
+    def used_parameters(self):
+        sd = dict(self.oracle.named_parameters())
+        return [sd[k] for k in self.keys]
+
+
+def _worker(rank, world, port, alias, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    from oracle.raindrop_oracle import build_oracle_model
+    from raindrop_b200.synth import make_batch, model_config, synth_weights, used_param_keys
+    from raindrop_b200.train import allreduce_gradients
+    cfg = model_config("TINY", dropout=0.0)
+    B = 8
+    full = make_batch(cfg, B, seed=3)
+    oracle = build_oracle_model(cfg).eval()
+    synth_weights(oracle, cfg, seed=5)
+    keys = used_param_keys(cfg)
+    per = B // world
+    sl = slice(rank * per, (rank + 1) * per)
+    logits, _, _ = oracle.forward_dense(full["src"][:, sl], full["static"][sl], full["times"][:, sl], full["lengths"][sl])
+    F.cross_entropy(logits, full["y"][sl]).backward()
+    shim = _Shim(oracle, keys)
+    params = shim.used_parameters()
+    if alias:   # gradients are views of one flat bucket, like the CUDA backward hands them to autograd
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        off = 0
+        for p in params:
+            p.grad = flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+        shim._flat_grad = flat
+    allreduce_gradients(shim)
+    if rank == 0:
+        out_q.put({k: p.grad.clone() for k, p in zip(keys, params)})
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("alias", [True, False])
+def test_two_rank_gradients_equal_full_batch(alias):
+    from oracle.raindrop_oracle import build_oracle_model
+    from raindrop_b200.synth import make_batch, model_config, synth_weights, used_param_keys
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, alias, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    cfg = model_config("TINY", dropout=0.0)
+    full = make_batch(cfg, 8, seed=3)
+    oracle = build_oracle_model(cfg).eval()
+    synth_weights(oracle, cfg, seed=5)
+    logits, _, _ = oracle.forward_dense(full["src"], full["static"], full["times"], full["lengths"])
+    F.cross_entropy(logits, full["y"]).backward()
+    ref = dict(oracle.named_parameters())
+    for k in used_param_keys(cfg):
+        assert torch.allclose(got[k], ref[k].grad, rtol=1e-4, atol=1e-7), k
