@@ -165,6 +165,14 @@ int rd_raindrop_v2_bwd(const rd_dims* dims, const rd_params* params, const float
 int rd_positional_encoding(const float* times, int64_t n_tokens, const float* timescales_host,
                            float* out, int64_t ld, int32_t col0, void* stream);
 
+/* out[rows, out_f] = [relu](x[rows, in_f] . weight[out_f, in_f]^T + bias): the encoder's projection
+ * GEMM on its own (torch.nn.Linear inside nn.TransformerEncoderLayer, code/models_rd.py:232-237).
+ * Error-compensated TF32 on the tensor cores (fp32-level accuracy) when in_f % 4 == out_f % 4 == 0,
+ * CUDA cores otherwise.  scratch: rd_linear_scratch_bytes(in_f, out_f) bytes (weight remainder). */
+size_t rd_linear_scratch_bytes(int32_t in_features, int32_t out_features);
+int rd_linear_fwd(const float* x, const float* weight, const float* bias, int64_t rows, int32_t in_features,
+                  int32_t out_features, int32_t relu, float* out, void* scratch, void* stream);
+
 /* TransformerConv.forward (code/transformer_conv.py:139-207), concat=True, root_weight=True,
  * beta=False, no edge features.  x [n_nodes, in]; weights [H*F, in]; edge_w may be NULL (then the
  * logits are q_i.k_j/sqrt(F)).  out [n_nodes, H*F]; alpha [E, H] (post-softmax, as returned).

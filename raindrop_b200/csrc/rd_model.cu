@@ -11,6 +11,7 @@
 
 #include "rd_kernels.cuh"
 #include "rd_obprop_tc.cuh"
+#include "rd_tc_gemm.cuh"
 
 namespace rd {
 namespace {
@@ -50,6 +51,8 @@ struct Arena {
 struct WsLayout {
   int64_t rng, X0, H1, W1r, W2r, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
   struct { int64_t qkv, P, Pd, ctx, r1, st1, x1, f, r2, st2; } l[RD_MAX_LAYERS];
+  // error-compensation remainders and transposes of the encoder weights (rd_tc_gemm.cuh)
+  struct { int64_t in_lo, in_t, in_tlo, out_lo, out_t, out_tlo, l1_lo, l1_t, l1_tlo, l2_lo, l2_t, l2_tlo; } wsp[RD_MAX_LAYERS];
 };
 
 WsLayout ws_layout(const Shape& s) {
@@ -73,6 +76,11 @@ WsLayout ws_layout(const Shape& s) {
     w.l[i].f = a.take(s.M2 * s.nhid);
     w.l[i].r2 = a.take(s.M2 * s.D);
     w.l[i].st2 = a.take(s.M2 * 2);
+    const int64_t nin = 3LL * s.D * s.D, nout = (int64_t)s.D * s.D, nff = (int64_t)s.nhid * s.D;
+    w.wsp[i].in_lo = a.take(nin); w.wsp[i].in_t = a.take(nin); w.wsp[i].in_tlo = a.take(nin);
+    w.wsp[i].out_lo = a.take(nout); w.wsp[i].out_t = a.take(nout); w.wsp[i].out_tlo = a.take(nout);
+    w.wsp[i].l1_lo = a.take(nff); w.wsp[i].l1_t = a.take(nff); w.wsp[i].l1_tlo = a.take(nff);
+    w.wsp[i].l2_lo = a.take(nff); w.wsp[i].l2_t = a.take(nff); w.wsp[i].l2_tlo = a.take(nff);
   }
   w.feat = a.take((int64_t)s.B * s.Df);
   w.hpre = a.take((int64_t)s.B * s.Df);
@@ -161,6 +169,18 @@ int tn(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, flo
 
 }  // namespace
 
+// Y[M,N] = epi(X[M,K] . W[N,K]^T): error-compensated tensor-core GEMM when the shape allows it, else CUDA cores.
+static int linear_nt(const GemmP& g, const float* W_lo, cudaStream_t st) {
+  TcGemmArgs a;
+  a.A = g.A; a.lda = g.sAi; a.B = g.B; a.B_lo = W_lo; a.M = g.M; a.N = g.N; a.K = g.K; a.C = g.C;
+  a.bias = g.bias; a.relu = g.relu; a.gate = g.gate; a.gate_ld = g.gate_ld; a.gate_scale = g.gate_scale;
+  a.drop_p = g.drop_p; a.rng = g.rng; a.drop_site = g.drop_site; a.resid = g.resid; a.resid_ld = g.resid_ld;
+  const bool plain = g.ta == 0 && g.tb == 1 && g.sBj == g.K && g.sCi == g.N && g.sCj == 1 && g.nz == 1 && g.nsplit == 1 &&
+                     g.alpha == 1.f && !g.rowscale && !g.perm && !g.asum;
+  if (plain && W_lo && tc_gemm_supported(a)) return tc_gemm(a, st);
+  return gemm(g, st);
+}
+
 // ---- observation propagation layer (operator level) ---------------------------------------------
 // Forward goes to the tcgen05 kernel when the shape fits its tiling, otherwise to the generic
 // CUDA-core GEMM (same epilogue).
@@ -208,6 +228,18 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
   }
   RD_TRY(posenc(times, s.M2, dims->pe_timescales, Z0, s.D, s.Dm, st));
 
+  for (int l0 = 0; l0 < s.L; l0 += 4) {   // remainders + transposes of the encoder weights, <= 16 tensors per launch
+    WeightSplit items[16];
+    int n = 0;
+    for (int l = l0; l < s.L && l < l0 + 4; ++l) {
+      const rd_encoder_layer_params& E = P->layer[l];
+      items[n++] = {E.in_proj_weight, 3 * s.D, s.D, ws + w.wsp[l].in_lo, ws + w.wsp[l].in_t, ws + w.wsp[l].in_tlo};
+      items[n++] = {E.out_proj_weight, s.D, s.D, ws + w.wsp[l].out_lo, ws + w.wsp[l].out_t, ws + w.wsp[l].out_tlo};
+      items[n++] = {E.linear1_weight, s.nhid, s.D, ws + w.wsp[l].l1_lo, ws + w.wsp[l].l1_t, ws + w.wsp[l].l1_tlo};
+      items[n++] = {E.linear2_weight, s.D, s.nhid, ws + w.wsp[l].l2_lo, ws + w.wsp[l].l2_t, ws + w.wsp[l].l2_tlo};
+    }
+    RD_TRY(split_weights(items, n, st));
+  }
   const float scale = 1.f / sqrtf((float)s.hd);
   const int64_t row3 = (int64_t)s.B * 3 * s.D;
   const int64_t TT = (int64_t)s.T * s.T;
@@ -220,7 +252,7 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
     {
       GemmP g = nt(x, s.D, E.in_proj_weight, s.D, qkv, 3 * s.D, s.M2, 3 * s.D, s.D);
       g.bias = E.in_proj_bias;
-      RD_TRY(gemm(g, st));
+      RD_TRY(linear_nt(g, ws + w.wsp[l].in_lo, st));
     }
     {  // S[b,h] = scale * Q K^T
       GemmP g;
@@ -245,20 +277,20 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
       GemmP g = nt(ctx, s.D, E.out_proj_weight, s.D, r1, s.D, s.M2, s.D, s.D);
       g.bias = E.out_proj_bias; g.drop_p = s.p; g.rng = rng; g.drop_site = SITE_RESID1 + l;
       g.resid = x; g.resid_ld = s.D;
-      RD_TRY(gemm(g, st));
+      RD_TRY(linear_nt(g, ws + w.wsp[l].out_lo, st));
     }
     RD_TRY(layernorm_fwd(r1, E.norm1_weight, E.norm1_bias, s.M2, s.D, dims->ln_eps, x1, ws + w.l[l].st1, st));
     float* f = ws + w.l[l].f; float* r2 = ws + w.l[l].r2;
     {
       GemmP g = nt(x1, s.D, E.linear1_weight, s.D, f, s.nhid, s.M2, s.nhid, s.D);
       g.bias = E.linear1_bias; g.relu = 1; g.drop_p = s.p; g.rng = rng; g.drop_site = SITE_FFN + l;
-      RD_TRY(gemm(g, st));
+      RD_TRY(linear_nt(g, ws + w.wsp[l].l1_lo, st));
     }
     {
       GemmP g = nt(f, s.nhid, E.linear2_weight, s.nhid, r2, s.D, s.M2, s.D, s.nhid);
       g.bias = E.linear2_bias; g.drop_p = s.p; g.rng = rng; g.drop_site = SITE_RESID2 + l;
       g.resid = x1; g.resid_ld = s.D;
-      RD_TRY(gemm(g, st));
+      RD_TRY(linear_nt(g, ws + w.wsp[l].l2_lo, st));
     }
     RD_TRY(layernorm_fwd(r2, E.norm2_weight, E.norm2_bias, s.M2, s.D, dims->ln_eps, ws + w.Z[l + 1], ws + w.l[l].st2, st));
   }
@@ -327,23 +359,23 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     const float* dg = gB;
     if (s.p > 0.f) { RD_TRY(apply_dropout(gB, s.M2 * s.D, s.p, rng, SITE_RESID2 + l, gC, st)); dg = gC; }
     RD_TRY(tn(dg, s.D, f, s.nhid, GE.linear2_weight, GE.linear2_bias, s.D, s.nhid, s.M2, partial, st));
-    {
-      GemmP g = nn(dg, s.D, E.linear2_weight, s.nhid, gF, s.nhid, s.M2, s.nhid, s.D);
+    {   // gF = (dg . W2) * [f > 0] / (1-p)   ("NT" against W2^T so that the tensor-core kernel applies)
+      GemmP g = nt(dg, s.D, ws + w.wsp[l].l2_t, s.D, gF, s.nhid, s.M2, s.nhid, s.D);
       g.gate = f; g.gate_ld = s.nhid; g.gate_scale = ik;  // relu' and the FFN dropout mask in one
-      RD_TRY(gemm(g, st));
+      RD_TRY(linear_nt(g, ws + w.wsp[l].l2_tlo, st));
     }
     RD_TRY(tn(gF, s.nhid, x1, s.D, GE.linear1_weight, GE.linear1_bias, s.nhid, s.D, s.M2, partial, st));
     {
-      GemmP g = nn(gF, s.nhid, E.linear1_weight, s.D, gA, s.D, s.M2, s.D, s.nhid);
+      GemmP g = nt(gF, s.nhid, ws + w.wsp[l].l1_t, s.nhid, gA, s.D, s.M2, s.D, s.nhid);
       g.resid = gB; g.resid_ld = s.D;
-      RD_TRY(gemm(g, st));
+      RD_TRY(linear_nt(g, ws + w.wsp[l].l1_tlo, st));
     }
     // norm1 + self-attention block
     RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, gB, GE.norm1_weight, GE.norm1_bias, aux, st));
     const float* dy = gB;
     if (s.p > 0.f) { RD_TRY(apply_dropout(gB, s.M2 * s.D, s.p, rng, SITE_RESID1 + l, gC, st)); dy = gC; }
     RD_TRY(tn(dy, s.D, ctx, s.D, GE.out_proj_weight, GE.out_proj_bias, s.D, s.D, s.M2, partial, st));
-    RD_TRY(gemm(nn(dy, s.D, E.out_proj_weight, s.D, gD, s.D, s.M2, s.D, s.D), st));
+    RD_TRY(linear_nt(nt(dy, s.D, ws + w.wsp[l].out_t, s.D, gD, s.D, s.M2, s.D, s.D), ws + w.wsp[l].out_tlo, st));
     {  // dPd[b,h] = dctx V^T
       GemmP g;
       g.A = gD; g.ta = 0; g.sAi = (int64_t)s.B * s.D; g.sAk = 1; g.sAzo = s.D; g.sAzi = s.hd;
@@ -379,9 +411,9 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     }
     RD_TRY(tn(dqkv, 3 * s.D, x, s.D, GE.in_proj_weight, GE.in_proj_bias, 3 * s.D, s.D, s.M2, partial, st));
     {
-      GemmP g = nn(dqkv, 3 * s.D, E.in_proj_weight, s.D, gA, s.D, s.M2, s.D, 3 * s.D);
+      GemmP g = nt(dqkv, 3 * s.D, ws + w.wsp[l].in_t, 3 * s.D, gA, s.D, s.M2, s.D, 3 * s.D);
       g.resid = gB; g.resid_ld = s.D;
-      RD_TRY(gemm(g, st));
+      RD_TRY(linear_nt(g, ws + w.wsp[l].in_tlo, st));
     }
   }
   // ---- observation propagation: gA = d(loss)/d(Z0) [T,B,D]          code/models_rd.py:322-343
@@ -470,6 +502,25 @@ int rd_obprop_bwd(const float* x, const float* out, const float* d_out, const fl
   RD_TRY(tn(dpre, C, x, C, d_weight, d_bias, C, C, rows, partial, st));
   if (d_x) RD_TRY(gemm(nn(dpre, C, weight, C, d_x, C, rows, C, C), st));
   return 0;
+}
+
+size_t rd_linear_scratch_bytes(int32_t in_features, int32_t out_features) {
+  return (size_t)round_up((int64_t)in_features * out_features, 64) * sizeof(float);
+}
+
+int rd_linear_fwd(const float* x, const float* weight, const float* bias, int64_t rows, int32_t in_features,
+                  int32_t out_features, int32_t relu, float* out, void* scratch, void* stream) {
+  if (!x || !weight || !out || !scratch || rows < 0 || in_features < 1 || out_features < 1) {
+    set_error("rd_linear_fwd: bad arguments");
+    return -2;
+  }
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  WeightSplit it = {weight, out_features, in_features, (float*)scratch, nullptr, nullptr};
+  RD_TRY(split_weights(&it, 1, st));
+  GemmP g = nt(x, in_features, weight, in_features, out, out_features, rows, out_features, in_features);
+  g.bias = bias; g.relu = relu;
+  return linear_nt(g, (const float*)scratch, st);
 }
 
 size_t rd_workspace_bytes(const rd_dims* dims) {

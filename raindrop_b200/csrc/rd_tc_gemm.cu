@@ -1,0 +1,330 @@
+// fp32-accurate GEMM on the 5th-gen tensor cores for the temporal self-attention encoder: the dense
+// Wq/Wk/Wv/Wo and feed-forward projections (code/models_rd.py:232-237,358 -> nn.TransformerEncoder)
+// and their input gradients.  Single-pass TF32 is borderline for these layers (SURVEY.md section 7:
+// ~1e-3 on the logits), so every product is error-compensated: the MMA reads the top 19 bits of an
+// fp32 operand (= its "hi" part) and we feed the exact remainders as two more MMAs into the same TMEM
+// accumulator.  Warp roles (10 warps, one persistent CTA per SM):
+//   warp 0      TMA producer for the weight tile and its precomputed remainder (L2 resident)
+//   warp 1      one thread issuing 3 x tcgen05.mma.kind::tf32 per 8-wide k-step, TMEM accumulators
+//               double buffered so the epilogue of tile i overlaps the MMAs of tile i+1
+//   warps 2-5   epilogue: tcgen05.ld -> bias / relu / gate / dropout / residual -> swizzled smem ->
+//               TMA store (coalesced 128-byte lines)
+//   warps 6-9   A loaders: coalesced 128-bit global loads of the activation tile (register
+//               prefetch one k-block ahead), split into hi / lo on the fly, written straight into
+//               the 128B-swizzled K-major layout the UMMA descriptor expects
+#include <stdlib.h>
+
+#include "rd_tc_common.cuh"
+#include "rd_tc_gemm.cuh"
+
+namespace rd {
+using namespace tc;
+namespace {
+
+constexpr int BM = 128, BK = 32, MAX_STAGES = 4, NTHREADS = 320;
+constexpr int A_TILE = BM * BK * 4;        // 16 KB (hi) + 16 KB (lo)
+constexpr int STG_BYTES = 4096;
+constexpr int MAX_BN = 160;
+
+struct P {
+  const float* A; long long lda;
+  long long M; int N, K, BN, n_tiles, m_tiles, k_blocks, nstages;
+  const float* bias; int relu;
+  const float* gate; long long gate_ld; float gate_scale;
+  float drop_p; const uint64_t* rng; uint32_t drop_site;
+  const float* resid; long long resid_ld;
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const __grid_constant__ CUtensorMap tmC, const P p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b_tile = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
+  const uint32_t stg_base = base + (uint32_t)p.nstages * stage_bytes;
+  const uint32_t bias_base = stg_base + 8 * STG_BYTES;
+  const uint32_t bar_base = bias_base + 2 * 256 * 4;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
+  }
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }  // 1 TMA + 4 loader warps
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) {
+    // ===== TMA producer: weight tile (hi = the raw weight) and its remainder ======================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_t = tile % p.n_tiles;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), 2u * b_tile);
+          const uint32_t sb = base + (uint32_t)stage * stage_bytes + 2u * A_TILE;
+          tma_load_2d(&tmB, full_bar(stage), sb, kb * BK, n_t * p.BN);
+          tma_load_2d(&tmBlo, full_bar(stage), sb + b_tile, kb * BK, n_t * p.BN);
+          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ================================================================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < p.k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE);
+          const uint64_t b_hi = umma_desc_sw128(sa + 2u * A_TILE), b_lo = umma_desc_sw128(sa + 2u * A_TILE + b_tile);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint64_t o = (uint64_t)(kk * 2);
+            umma_tf32(d_tmem, a_lo + o, b_hi + o, idesc, (kb | kk) ? 1u : 0u);   // small terms first
+            umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
+            umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (warp < 6) {
+    // ===== epilogue ====================================================================================
+    const int q = warp & 3;
+    const int et = threadIdx.x - 64;
+    const uint32_t my_stg = stg_base + (uint32_t)(warp - 2) * 2u * STG_BYTES;
+    int acc = 0; uint32_t acc_phase = 0; int buf = 0;
+    const int n_chunks = (p.BN + 31) / 32;
+    const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int m_t = tile / p.n_tiles, n_t = tile - m_t * p.n_tiles;
+      const int col0 = n_t * p.BN;
+      for (int c = et; c < 256; c += 128) bias_s[acc * 256 + c] = (p.bias && c < p.BN && col0 + c < p.N) ? __ldg(p.bias + col0 + c) : 0.f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int row0 = m_t * BM + q * 32;
+      const long long row = (long long)row0 + lane;
+      const bool row_ok = row < p.M;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + ch * 32), v);
+        const float* bs = bias_s + acc * 256 + ch * 32;
+        const int c0 = col0 + ch * 32;
+        if (lane == 0) bulk_wait_read<1>();
+        __syncwarp();
+        const uint32_t stg = my_stg + (uint32_t)buf * STG_BYTES;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          float o[4];
+          const int c = c0 + 4 * j4;
+          const bool ok = row_ok && c < p.N;     // N % 4 == 0: a float4 is all in or all out
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            float x = __uint_as_float(v[4 * j4 + e]) + bs[4 * j4 + e];
+            o[e] = p.relu ? fmaxf(x, 0.f) : x;
+          }
+          if (p.gate && ok) {
+            float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + row * p.gate_ld + c));
+            o[0] = g.x > 0.f ? o[0] * p.gate_scale : 0.f; o[1] = g.y > 0.f ? o[1] * p.gate_scale : 0.f;
+            o[2] = g.z > 0.f ? o[2] * p.gate_scale : 0.f; o[3] = g.w > 0.f ? o[3] * p.gate_scale : 0.f;
+          }
+          if (p.drop_p > 0.f && ok) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] *= dropout_scale(p.rng, p.drop_site, (uint64_t)row * (uint64_t)p.N + (uint64_t)(c + e), p.drop_p, ik);
+          }
+          if (p.resid && ok) {
+            float4 r = __ldg(reinterpret_cast<const float4*>(p.resid + row * p.resid_ld + c));
+            o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+          }
+          const uint32_t off = (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) << 4));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&tmC, stg, c0, row0);
+          bulk_commit();
+        }
+        buf ^= 1;
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  } else {
+    // ===== A loaders: global -> registers -> hi/lo split -> swizzled smem ================================
+    const int lt = threadIdx.x - 192;           // 0..127
+    const int chunk = lt & 7, rsub = lt >> 3;   // 8 lanes cover one 128-byte row segment
+    int stage = 0; uint32_t phase = 0;
+    float4 cur[8], nxt[8];
+    auto issue = [&](int tile, int kb, float4 (&r)[8]) {
+      const long long m0 = (long long)(tile / p.n_tiles) * BM;
+      const int k = kb * BK + chunk * 4;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const long long gr = m0 + it * 16 + rsub;
+        r[it] = (gr < p.M && k < p.K) ? __ldg(reinterpret_cast<const float4*>(p.A + gr * p.lda + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    int tile = blockIdx.x, kb = 0;
+    if (tile < total_tiles) issue(tile, 0, cur);
+    while (tile < total_tiles) {
+      int ntile = tile, nkb = kb + 1;
+      if (nkb == p.k_blocks) { nkb = 0; ntile = tile + gridDim.x; }
+      if (ntile < total_tiles) issue(ntile, nkb, nxt);      // in flight while we wait and store
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 16 + rsub;
+        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
+        const float4 a = cur[it];
+        float4 lo;
+        lo.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
+        lo.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
+        lo.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
+        lo.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + A_TILE + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
+      if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) cur[it] = nxt[it];
+      tile = ntile; kb = nkb;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+struct SplitItems { WeightSplit it[16]; long long start[17]; int n; };
+
+__global__ void split_weights_kernel(SplitItems s) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= s.start[s.n]) return;
+  int t = 0;
+  while (t + 1 < s.n && i >= s.start[t + 1]) ++t;
+  const WeightSplit w = s.it[t];
+  long long e = i - s.start[t];
+  int r = (int)(e / w.cols), c = (int)(e - (long long)r * w.cols);
+  float v = w.w[e];
+  float lo = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+  if (w.lo) w.lo[e] = lo;
+  if (w.t) { w.t[(long long)c * w.rows + r] = v; w.t_lo[(long long)c * w.rows + r] = lo; }
+}
+
+void plan(long long M, int N, int* BN, int* n_tiles) {
+  const long long m_tiles = ceil_div(M, BM);
+  int nt = (int)ceil_div(N, MAX_BN);
+  while (m_tiles * nt < 120 && round_up(ceil_div(N, nt + 1), 32) >= 64) ++nt;   // spread over the SMs
+  *n_tiles = nt;
+  *BN = nt == 1 ? (int)round_up(N, 16) : (int)round_up(ceil_div(N, nt), 32);
+}
+
+}  // namespace
+
+bool tc_gemm_supported(const TcGemmArgs& a) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("RD_TC_GEMM"); env = (e && e[0] == '0') ? 0 : 1; }
+  if (env != 1) return false;
+  if (a.K % 4 || a.N % 4 || a.lda % 4 || a.K < 8 || a.N < 16 || a.M < 1 || a.M > 0x7fffffffLL) return false;
+  if ((a.gate && a.gate_ld % 4) || (a.resid && a.resid_ld % 4)) return false;
+  uintptr_t bits = reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B) | reinterpret_cast<uintptr_t>(a.B_lo) |
+                   reinterpret_cast<uintptr_t>(a.C) | reinterpret_cast<uintptr_t>(a.gate) | reinterpret_cast<uintptr_t>(a.resid);
+  return (bits & 15) == 0 && a.B_lo != nullptr;
+}
+
+int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
+  if (!tc_gemm_supported(a)) { set_error("tc_gemm: unsupported shape/alignment (M=%lld N=%d K=%d)", a.M, a.N, a.K); return -2; }
+  P p;
+  p.A = a.A; p.lda = a.lda; p.M = a.M; p.N = a.N; p.K = a.K;
+  plan(a.M, a.N, &p.BN, &p.n_tiles);
+  p.m_tiles = (int)ceil_div(a.M, BM);
+  p.k_blocks = (int)ceil_div(a.K, BK);
+  const int stage_bytes = 2 * A_TILE + 2 * p.BN * 128;
+  const int fixed = 1024 + 8 * STG_BYTES + 2 * 256 * 4 + 256;
+  p.nstages = (SMEM_LIMIT - fixed) / stage_bytes;
+  if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
+  if (p.nstages < 2) { set_error("tc_gemm: not enough shared memory"); return -2; }
+  const int smem_bytes = fixed + p.nstages * stage_bytes;
+  p.bias = a.bias; p.relu = a.relu; p.gate = a.gate; p.gate_ld = a.gate_ld; p.gate_scale = a.gate_scale;
+  p.drop_p = a.drop_p; p.rng = a.rng; p.drop_site = a.drop_site; p.resid = a.resid; p.resid_ld = a.resid_ld;
+
+  CUtensorMap tmB, tmBlo, tmC;
+  cuuint64_t bd[2] = {(cuuint64_t)a.K, (cuuint64_t)a.N};
+  cuuint64_t bs[1] = {(cuuint64_t)a.K * 4};
+  cuuint32_t bb[2] = {BK, (cuuint32_t)p.BN};
+  RD_TRY(encode(&tmB, a.B, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B, "B"));
+  RD_TRY(encode(&tmBlo, a.B_lo, 2, bd, bs, bb, CU_TENSOR_MAP_SWIZZLE_128B, "B_lo"));
+  cuuint64_t cd[2] = {(cuuint64_t)a.N, (cuuint64_t)a.M};
+  cuuint64_t cs[1] = {(cuuint64_t)a.N * 4};
+  cuuint32_t cb[2] = {32, 32};
+  RD_TRY(encode(&tmC, a.C, 2, cd, cs, cb, CU_TENSOR_MAP_SWIZZLE_128B, "C"));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  const int total = p.m_tiles * p.n_tiles;
+  const int grid = total < num_sms() ? total : num_sms();
+  tc_gemm_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmB, tmBlo, tmC, p);
+  RD_CHECK_LAUNCH("tc_gemm_kernel");
+  return 0;
+}
+
+int split_weights(const WeightSplit* items, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n > 16) { set_error("split_weights: at most 16 tensors per launch"); return -2; }
+  SplitItems s;
+  s.n = n; s.start[0] = 0;
+  for (int i = 0; i < n; ++i) { s.it[i] = items[i]; s.start[i + 1] = s.start[i] + (long long)items[i].rows * items[i].cols; }
+  split_weights_kernel<<<(unsigned)ceil_div(s.start[n], 256), 256, 0, st>>>(s);
+  RD_CHECK_LAUNCH("split_weights_kernel");
+  return 0;
+}
+
+}  // namespace rd

@@ -1,0 +1,29 @@
+// Error-compensated tensor-core GEMM for the temporal-attention encoder (rd_tc_gemm.cu).
+#pragma once
+#include "rd_common.cuh"
+
+namespace rd {
+
+// C[M,N] = epi( A[M,K] . B[N,K]^T ) with fp32-level accuracy on the TF32 tensor cores ("3xTF32"):
+//   A = A_hi + A_lo, B = B_hi + B_lo (hi = top 19 bits, what the MMA reads; lo = exact remainder)
+//   A.B^T ~= A_hi.B_hi^T + A_lo.B_hi^T + A_hi.B_lo^T          (dropped term ~2^-22 relative)
+// A (activations) is split on the fly by the loader warps; B (a weight) comes with its precomputed
+// remainder B_lo (split_weights below).  epi = +bias[j] -> relu -> *gate -> dropout -> +resid.
+struct TcGemmArgs {
+  const float* A = nullptr; long long lda = 0;
+  const float* B = nullptr; const float* B_lo = nullptr;   // [N, K] row-major, ld = K
+  long long M = 0; int N = 0, K = 0;
+  float* C = nullptr;                                        // [M, N] row-major, ld = N
+  const float* bias = nullptr; int relu = 0;
+  const float* gate = nullptr; long long gate_ld = 0; float gate_scale = 1.f;
+  float drop_p = 0.f; const uint64_t* rng = nullptr; uint32_t drop_site = 0;
+  const float* resid = nullptr; long long resid_ld = 0;
+};
+bool tc_gemm_supported(const TcGemmArgs& a);
+int tc_gemm(const TcGemmArgs& a, cudaStream_t st);
+
+// One launch for all weights of a step: lo = W - trunc19(W); t = W^T; t_lo = W^T - trunc19(W^T).
+struct WeightSplit { const float* w; int rows, cols; float* lo; float* t; float* t_lo; };
+int split_weights(const WeightSplit* items, int n, cudaStream_t st);   // n <= 16
+
+}  // namespace rd

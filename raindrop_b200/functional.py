@@ -209,6 +209,20 @@ def positional_encoding(times, max_len, d_pe=16):
     return out
 
 
+def linear(x, weight, bias=None, relu=False):
+    """x [rows, in] -> [rows, out] through the encoder's projection GEMM (rd_linear_fwd); inference only."""
+    lib = L.load()
+    x, weight = _as_f32(x), _as_f32(weight)
+    rows, in_f = x.shape
+    out_f = weight.shape[0]
+    out = torch.empty(rows, out_f, dtype=torch.float32, device=x.device)
+    sc = torch.empty(lib.rd_linear_scratch_bytes(in_f, out_f) // 4, dtype=torch.float32, device=x.device)
+    b = None if bias is None else _as_f32(bias)
+    L.check(lib.rd_linear_fwd(x.data_ptr(), weight.data_ptr(), L.ptr(b), rows, in_f, out_f, int(relu), out.data_ptr(),
+                              sc.data_ptr(), L.stream_ptr()), "rd_linear_fwd")
+    return out
+
+
 def transformer_conv(x, edge_index, edge_weights, heads, out_channels, wq, bq, wk, bk, wv, bv, ws, bs):
     """TransformerConv forward (inference; code/transformer_conv.py:139-207).  Returns (out, alpha)."""
     lib = L.load()

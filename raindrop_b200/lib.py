@@ -80,6 +80,9 @@ SIGNATURES = {
                                      C.c_void_p]),
     "rd_positional_encoding": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p,
                                          C.c_int64, C.c_int32, C.c_void_p]),
+    "rd_linear_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
+    "rd_linear_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                C.c_void_p, C.c_void_p, C.c_void_p]),
     "rd_transformer_conv_scratch_bytes": (C.c_size_t, [C.c_int32] * 5),
     "rd_transformer_conv_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] +

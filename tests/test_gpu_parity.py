@@ -239,6 +239,22 @@ def test_obprop_layer_shapes(rows, Cc):
     assert normwise(out, ref) < FWD_TOL
 
 
+@pytest.mark.parametrize("rows,in_f,out_f", [(7680, 152, 456), (7680, 152, 152), (7680, 272, 152), (300, 160, 288),
+                                              (1000, 84, 252), (129, 528, 1584), (64, 186, 186)])
+def test_projection_gemm_is_fp32_accurate(rows, in_f, out_f):
+    """Error-compensated tensor-core GEMM (3xTF32) vs fp64: must be at fp32 level, not TF32 level."""
+    from raindrop_b200 import functional as RF
+    g = torch.Generator().manual_seed(rows + in_f)
+    x = torch.randn(rows, in_f, generator=g)
+    W = torch.randn(out_f, in_f, generator=g) / in_f ** 0.5
+    b = torch.randn(out_f, generator=g)
+    ref = F.relu(x.double() @ W.double().T + b.double())
+    out = RF.linear(x.cuda(), W.cuda(), b.cuda(), relu=True)
+    fp32 = F.relu(x @ W.T + b)
+    e, e32 = normwise(out, ref), normwise(fp32, ref)
+    assert e < 3e-6 and e < 20 * e32 + 1e-7, (e, e32)
+
+
 def test_positional_encoding():
     from oracle.raindrop_oracle import positional_encoding
     from raindrop_b200.models_rd import PositionalEncodingTF
