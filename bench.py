@@ -287,7 +287,13 @@ def main():
     n0 = lib.rd_launch_count()
     ts._enqueue()                      # eager once: counts our launches per step
     launches_per_step = int(lib.rd_launch_count() - n0)
-    ts.capture(warmup=2)
+    graph_note = "one CUDA-graph replay (TrainStep)"
+    try:
+        ts.capture(warmup=2)
+    except Exception as exc:  # noqa: BLE001  (e.g. NCCL refusing stream capture): run the same step eagerly
+        ts.use_graph, ts.graph = False, None
+        graph_note = "eager TrainStep (graph capture failed: %r)" % (exc,)
+        torch.cuda.synchronize()
     for _ in range(args.warmup):
         ts.step()
     torch.cuda.synchronize()
@@ -357,7 +363,7 @@ def main():
                                "fwd + CrossEntropy + bwd + Adam, dropout 0.2", "global_batch": world * BATCH,
                    "per_gpu_batch": BATCH, "parallelism": "sample-sharded dp%d, 1 NCCL all-reduce of the flat grad bucket" % world,
                    "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)",
-                   "step": "one CUDA-graph replay (TrainStep)", "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4)},
+                   "step": graph_note, "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4)},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
                 "ms_per_step": round(e2e_ms / args.steps, 4),

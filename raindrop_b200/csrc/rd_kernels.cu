@@ -164,21 +164,32 @@ __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float
   }
 }
 
-constexpr int LN_ROWS = 32;
+constexpr int LN_ROWS = 256;   // rows per CTA: 8 row groups x 32 rows, reduced through shared memory
+// partial[chunk][0][j] = sum_rows dy * xhat, partial[chunk][1][j] = sum_rows dy
 __global__ void layernorm_bwd_param_kernel(const float* __restrict__ x, const float* __restrict__ stats,
                                            const float* __restrict__ dy, long long rows, int D,
                                            float* __restrict__ partial) {
-  int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= D) return;
-  long long r0 = (long long)blockIdx.y * LN_ROWS, r1 = min(rows, r0 + LN_ROWS);
+  __shared__ float sg[8][33], sb[8][33];
+  const int j = blockIdx.x * 32 + threadIdx.x;
+  const long long r0 = (long long)blockIdx.y * LN_ROWS + threadIdx.y * 32;
   float dg = 0.f, db = 0.f;
-  for (long long r = r0; r < r1; ++r) {
-    float d = dy[r * D + j];
-    dg += d * (x[r * D + j] - stats[2 * r]) * stats[2 * r + 1];
-    db += d;
+  if (j < D) {
+    const long long r1 = min(rows, r0 + 32);
+    for (long long r = r0; r < r1; ++r) {
+      float d = dy[r * D + j];
+      dg += d * (x[r * D + j] - stats[2 * r]) * stats[2 * r + 1];
+      db += d;
+    }
   }
-  partial[(long long)blockIdx.y * D + j] = dg;                  // [chunks][D] for dgamma
-  partial[((long long)gridDim.y + blockIdx.y) * D + j] = db;    // then [chunks][D] for dbeta
+  sg[threadIdx.y][threadIdx.x] = dg;
+  sb[threadIdx.y][threadIdx.x] = db;
+  __syncthreads();
+  if (threadIdx.y == 0 && j < D) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) { dg += sg[g][threadIdx.x]; db += sb[g][threadIdx.x]; }
+    partial[((long long)blockIdx.y * 2) * D + j] = dg;
+    partial[((long long)blockIdx.y * 2 + 1) * D + j] = db;
+  }
 }
 
 __global__ void attn_softmax_fwd_kernel(float* __restrict__ S, const int64_t* __restrict__ lengths, int B, int H,
@@ -392,12 +403,11 @@ int layernorm_bwd(const float* x, const float* stats, const float* gamma, const 
   RD_CHECK_LAUNCH("layernorm_bwd_dx_kernel");
   int chunks = (int)ceil_div(rows, LN_ROWS);
   if (chunks > 65535) { set_error("layernorm_bwd: too many row chunks"); return -2; }
-  dim3 grid((unsigned)ceil_div(D, 128), (unsigned)chunks);
-  layernorm_bwd_param_kernel<<<grid, 128, 0, st>>>(x, stats, dy, rows, D, scratch);
+  dim3 grid((unsigned)ceil_div(D, 32), (unsigned)chunks);
+  layernorm_bwd_param_kernel<<<grid, dim3(32, 8), 0, st>>>(x, stats, dy, rows, D, scratch);
   RD_CHECK_LAUNCH("layernorm_bwd_param_kernel");
-  RD_TRY(reduce_partials(scratch, chunks, D, dgamma, st));
-  RD_TRY(reduce_partials(scratch + (int64_t)chunks * D, chunks, D, dbeta, st));
-  return 0;
+  // [chunk][2][D] -> dgamma, dbeta in one deterministic pass
+  return reduce_partials2(scratch, chunks, D, dgamma, D, dbeta, st);
 }
 
 int attn_softmax_fwd(float* S, const int64_t* lengths, int B, int H, int T, float drop_p, const uint64_t* rng,
