@@ -350,8 +350,7 @@ def main():
     e2e_value = world * BATCH * args.steps / (e2e_ms * 1e-3)
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        _finish(world)
         return
     roof = roofline_leg(cfg, device)
     line = {
@@ -385,8 +384,17 @@ def main():
             line["cpu_baseline"] = {"value": None, "unit": "samples/s", "cores": os.cpu_count(), "kind": "port",
                                     "sample": "cpu leg failed or timed out: %r" % (exc,)}
     print(json.dumps(line), flush=True)
+    _finish(world)
+
+
+def _finish(world):
+    """destroy_process_group() was observed to hang on this pool after NCCL work has been captured in a
+    CUDA graph; every rank is done and synchronised here, so leave without tearing the communicator down."""
     if world > 1:
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 if __name__ == "__main__":

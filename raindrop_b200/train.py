@@ -48,7 +48,8 @@ def allreduce_gradients(model, group=None):
 class TrainStep:
     """fwd + loss + bwd + (all-reduce) + Adam for a fixed batch size on static device buffers."""
 
-    def __init__(self, model, batch_size, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None, use_graph=True):
+    def __init__(self, model, batch_size, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None, use_graph=True,
+                 distributed=True):
         lib = L.load()
         self.lib, self.model, self.B = lib, model, int(batch_size)
         dev = next(model.parameters()).device
@@ -58,7 +59,7 @@ class TrainStep:
         self.plan = model._prepare(dev)
         self.lr, self.betas, self.eps = float(lr), betas, float(eps)
         self.group = group
-        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.world = dist.get_world_size(group) if (distributed and dist.is_initialized()) else 1
         # ---- flatten the used parameters into one bucket (views keep the nn.Parameters alive) ----
         params = model.used_parameters()
         self.offsets, total = [], 0

@@ -33,7 +33,7 @@ for use_graph in (False, True):
         dist.all_reduce(l); losses.append(l.item() / world)
     if rank == 0:
         ref = build_dropin(cfg, 6).train()
-        rs = TrainStep(ref, B, lr=1e-3, use_graph=False)
+        rs = TrainStep(ref, B, lr=1e-3, use_graph=False, distributed=False)
         ref_losses = []
         for b in batches:
             rs.load_batch(to_dev(b)); ref_losses.append(rs.step().item())
@@ -44,5 +44,6 @@ for use_graph in (False, True):
         assert worst < 5e-3, worst
     dist.barrier()
 if rank == 0:
-    print("DDP_CHECK_OK")
-dist.destroy_process_group()
+    print("DDP_CHECK_OK", flush=True)
+torch.cuda.synchronize(); sys.stdout.flush()
+os._exit(0)   # destroy_process_group() hangs on this pool once NCCL work was graph-captured
