@@ -118,7 +118,10 @@ def build_model(cfg, device):
 
 
 def flush_l2(buf):
+    """Write a buffer larger than L2, then read it back: the write evicts everything, the read leaves the
+    cache full of CLEAN lines (otherwise the timed kernel pays for writing back ~126 MB of dirty zeros)."""
     buf.zero_()
+    buf.sum()
 
 
 def timed_steps(step_fn, steps, flush_buf):
@@ -361,7 +364,7 @@ def main():
         "config": {"workload": "P19 synthetic (batch=128 per GPU, 34 sensors, T_max=60) Raindrop_v2 training step: "
                                "fwd + CrossEntropy + bwd + Adam, dropout 0.2", "global_batch": world * BATCH,
                    "per_gpu_batch": BATCH, "parallelism": "sample-sharded dp%d, 1 NCCL all-reduce of the flat grad bucket" % world,
-                   "l2": "flushed between timed steps (256 MiB memset outside the per-step CUDA-event pairs)",
+                   "l2": "flushed between timed steps (256 MiB write + read-back, outside the per-step CUDA-event pairs)",
                    "step": graph_note, "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4)},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,

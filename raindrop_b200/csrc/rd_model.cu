@@ -95,7 +95,9 @@ struct BwLayout {
 
 int64_t tn_partial_floats(int Nout, int Kin, int64_t rows) {
   int ns;
-  return gemm_splitk_plan(Nout, Kin, (int)rows, &ns);
+  int64_t a = gemm_splitk_plan(Nout, Kin, (int)rows, &ns);
+  int64_t b = tc_wgrad_partial_floats(Nout, Kin, rows);     // tensor-core path (shape permitting)
+  return a > b ? a : b;
 }
 
 BwLayout bw_layout(const Shape& s) {
@@ -155,6 +157,8 @@ GemmP nn(const float* dY, int64_t ldy, const float* W, int64_t ldw, float* dX, i
 // dW[Nout,Kin] = sum_r dY[r,Nout]^T X[r,Kin]   (split over rows, deterministic two-stage reduce)
 int tn(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db, int Nout, int Kin, int64_t rows,
        float* partial, cudaStream_t st) {
+  if (rows >= 256 && tc_wgrad_supported(Nout, Kin, ldy, ldx, dY, X))
+    return tc_wgrad(dY, ldy, X, ldx, rows, Nout, Kin, dW, db, partial, st);
   GemmP g;
   g.A = dY; g.ta = 1; g.sAk = ldy; g.sAi = 1;
   g.B = X; g.tb = 0; g.sBk = ldx; g.sBj = 1;

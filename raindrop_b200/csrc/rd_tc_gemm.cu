@@ -240,6 +240,222 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   }
 }
 
+// =================================================================================================
+// weight-gradient kernel ("TN"): D[m, n] = sum_r A[r, m] * B[r, n] over this CTA's row range
+// =================================================================================================
+struct WP {
+  const float* A; long long lda;     // dY [rows, M]
+  const float* B; long long ldb;     // X  [rows, N]  (+ implicit ones column at n == N)
+  long long rows; int M, N, BN, n_tiles, m_tiles, nsplit, rows_per_split, nstages, Mpad;
+};
+
+__device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+// loads a 4(r) x 4(col) block, returns it transposed: out[e] = 4 consecutive r values of column e
+__device__ __forceinline__ void load_block_t(const float* __restrict__ src, long long ld, long long r0, long long r_end,
+                                             int col, bool col_ok, float4 (&out)[4]) {
+  float4 in[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    in[j] = (col_ok && r0 + j < r_end) ? __ldg(reinterpret_cast<const float4*>(src + (r0 + j) * ld + col))
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+  out[0] = make_float4(in[0].x, in[1].x, in[2].x, in[3].x);
+  out[1] = make_float4(in[0].y, in[1].y, in[2].y, in[3].y);
+  out[2] = make_float4(in[0].z, in[1].z, in[2].z, in[3].z);
+  out[3] = make_float4(in[0].w, in[1].w, in[2].w, in[3].w);
+}
+
+__device__ __forceinline__ void store_hi_lo(uint32_t hi_base, uint32_t lo_base, int row, int c, const float4& v) {
+  const uint32_t off = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(lo_part(v.x)), "f"(lo_part(v.y)),
+               "f"(lo_part(v.z)), "f"(lo_part(v.w)) : "memory");
+}
+
+__global__ void __launch_bounds__(448, 1)
+tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const WP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t b_tile = (uint32_t)p.BN * 128u;
+  const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
+  const uint32_t stg_base = base + (uint32_t)p.nstages * stage_bytes;
+  const uint32_t bar_base = stg_base + 8 * STG_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
+  const uint32_t tfull_bar = bar_base + 8u * (2 * MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  // work item of this CTA: (split, m tile, n tile)
+  const int item = blockIdx.x;
+  const int n_t = item % p.n_tiles, m_t = (item / p.n_tiles) % p.m_tiles, split = item / (p.n_tiles * p.m_tiles);
+  const long long r_begin = (long long)split * p.rows_per_split;
+  const long long r_end = min(p.rows, r_begin + p.rows_per_split);
+  const int k_blocks = (int)((r_end - r_begin + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
+  if (warp == 1) {
+    if (lane == 0) {
+      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 8); mbar_init(empty_bar(s), 1); }   // 8 loader warps
+      mbar_init(tfull_bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 1) {
+    // ===== MMA issuer ================================================================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        tc_fence_after();
+        const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+        const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE);
+        const uint64_t b_hi = umma_desc_sw128(sa + 2u * A_TILE), b_lo = umma_desc_sw128(sa + 2u * A_TILE + b_tile);
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk) {
+          const uint64_t o = (uint64_t)(kk * 2);
+          umma_tf32(tmem_base, a_lo + o, b_hi + o, idesc, (kb | kk) ? 1u : 0u);
+          umma_tf32(tmem_base, a_hi + o, b_lo + o, idesc, 1u);
+          umma_tf32(tmem_base, a_hi + o, b_hi + o, idesc, 1u);
+        }
+        umma_commit(empty_bar(stage));
+        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+      }
+      umma_commit(tfull_bar);
+    }
+  } else if (warp >= 2 && warp < 6) {
+    // ===== epilogue: accumulator tile -> partial buffer ==============================================
+    const int q = warp & 3;
+    const uint32_t my_stg = stg_base + (uint32_t)(warp - 2) * 2u * STG_BYTES;
+    const int n_chunks = (p.BN + 31) / 32;
+    const int row0 = split * p.Mpad + m_t * BM + q * 32;
+    int buf = 0;
+    mbar_wait(tfull_bar, 0);
+    tc_fence_after();
+    for (int ch = 0; ch < n_chunks; ++ch) {
+      uint32_t v[32];
+      if (k_blocks > 0) {
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 32; ++e) v[e] = 0u;
+      }
+      if (lane == 0) bulk_wait_read<1>();
+      __syncwarp();
+      const uint32_t stg = my_stg + (uint32_t)buf * STG_BYTES;
+#pragma unroll
+      for (int j4 = 0; j4 < 8; ++j4) {
+        const uint32_t off = (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) << 4));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(v[4 * j4]), "r"(v[4 * j4 + 1]),
+                     "r"(v[4 * j4 + 2]), "r"(v[4 * j4 + 3]) : "memory");
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(&tmP, stg, n_t * p.BN + ch * 32, row0);
+        bulk_commit();
+      }
+      buf ^= 1;
+    }
+    if (lane == 0) bulk_wait_read<0>();
+  }
+  // ===== loaders: warps 6..9 handle the A (dY^T) tile, warps 10..13 the B (X^T) tile
+  if (warp >= 6) {
+    const bool isA = warp < 10;
+    const int lt = (threadIdx.x - 192) & 127;          // 0..127 within the operand's loader group
+    const int c = lt & 7;                                 // which 4-row block of the 32-row k-block
+    const int g0 = lt >> 3;                               // first 4-column block
+    const float* __restrict__ src = isA ? p.A : p.B;
+    const long long ld = isA ? p.lda : p.ldb;
+    const int col_base = isA ? m_t * BM : n_t * p.BN;
+    const int col_lim = isA ? p.M : p.N;
+    const int tile_cols = isA ? BM : p.BN;
+    const int nblk = (tile_cols / 4 + 15) / 16;          // 4-column blocks per thread (2 for A, <= 3 for B)
+    int stage = 0; uint32_t phase = 0;
+    for (int kb = 0; kb < k_blocks; ++kb) {
+      const long long r0 = r_begin + (long long)kb * BK + 4 * c;
+      float4 blk[3][4];
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        if (it < nblk) {
+          const int g = g0 + 16 * it;
+          const int col = col_base + 4 * g;
+          load_block_t(src, ld, r0, r_end, col, 4 * g < tile_cols && col < col_lim, blk[it]);
+          if (!isA && col == p.N && 4 * g < tile_cols) {   // the ones column: db = sum_r dY[r, :] * 1
+            const float o0 = r0 + 0 < r_end ? 1.f : 0.f, o1 = r0 + 1 < r_end ? 1.f : 0.f;
+            const float o2 = r0 + 2 < r_end ? 1.f : 0.f, o3 = r0 + 3 < r_end ? 1.f : 0.f;
+            blk[it][0] = make_float4(o0, o1, o2, o3);
+          }
+        }
+      }
+      mbar_wait(empty_bar(stage), phase ^ 1u);
+      const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+      const uint32_t hi = isA ? sa : sa + 2u * A_TILE;
+      const uint32_t lo = isA ? sa + A_TILE : sa + 2u * A_TILE + b_tile;
+#pragma unroll
+      for (int it = 0; it < 3; ++it) {
+        if (it < nblk) {
+          const int g = g0 + 16 * it;
+          if (4 * g < tile_cols) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) store_hi_lo(hi, lo, 4 * g + e, c, blk[it][e]);
+          }
+        }
+      }
+      fence_async_smem();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full_bar(stage));
+      if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+  }
+}
+
+// dW[m, n] = sum_s partial[s][m][n] (n < N), db[m] = sum_s partial[s][m][N]; fixed order -> deterministic
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int M, int N, int Mpad, int Nld,
+                                    float* __restrict__ dW, float* __restrict__ db) {
+  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)M * (N + 1)) return;
+  int m = (int)(i / (N + 1)), n = (int)(i - (long long)m * (N + 1));
+  float s = 0.f;
+  for (int k = 0; k < nsplit; ++k) s += partial[((long long)k * Mpad + m) * Nld + n];
+  if (n < N) dW[(long long)m * N + n] = s; else if (db) db[m] = s;
+}
+
+struct WPlan { int BN, n_tiles, m_tiles, nsplit, rows_per_split, Mpad, Nld; };
+WPlan wgrad_plan(int M, int N, long long rows) {
+  WPlan w;
+  w.m_tiles = (int)ceil_div(M, BM);
+  w.Mpad = w.m_tiles * BM;
+  const int Ncols = N + 1;                                  // + the ones column
+  w.n_tiles = (int)ceil_div(Ncols, MAX_BN);
+  w.BN = w.n_tiles == 1 ? (int)round_up(Ncols, 16) : (int)round_up(ceil_div(Ncols, w.n_tiles), 32);
+  w.Nld = (int)round_up(w.n_tiles * w.BN, 4);
+  const int mn = w.m_tiles * w.n_tiles;
+  int ns = num_sms() / mn;
+  if (ns < 1) ns = 1;
+  const long long max_ns = ceil_div(rows, 64);
+  if (ns > max_ns) ns = (int)max_ns;
+  w.rows_per_split = (int)round_up(ceil_div(rows, ns), BK);
+  w.nsplit = (int)ceil_div(rows, w.rows_per_split);
+  return w;
+}
+
 struct SplitItems { WeightSplit it[16]; long long start[17]; int n; };
 
 __global__ void split_weights_kernel(SplitItems s) {
@@ -313,6 +529,53 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
   const int grid = total < num_sms() ? total : num_sms();
   tc_gemm_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmB, tmBlo, tmC, p);
   RD_CHECK_LAUNCH("tc_gemm_kernel");
+  return 0;
+}
+
+bool tc_wgrad_supported(int Nout, int Kin, long long ldy, long long ldx, const void* dY, const void* X) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("RD_TC_WGRAD"); env = (e && e[0] == '0') ? 0 : 1; }
+  if (env != 1) return false;
+  if (Nout % 4 || Kin % 4 || ldy % 4 || ldx % 4 || Nout < 16 || Kin < 16) return false;
+  return ((reinterpret_cast<uintptr_t>(dY) | reinterpret_cast<uintptr_t>(X)) & 15) == 0;
+}
+
+long long tc_wgrad_partial_floats(int Nout, int Kin, long long rows) {
+  WPlan w = wgrad_plan(Nout, Kin, rows);
+  return (long long)w.nsplit * w.Mpad * w.Nld;
+}
+
+int tc_wgrad(const float* dY, long long ldy, const float* X, long long ldx, long long rows, int Nout, int Kin,
+             float* dW, float* db, float* partial, cudaStream_t st) {
+  if (!tc_wgrad_supported(Nout, Kin, ldy, ldx, dY, X) || !partial) { set_error("tc_wgrad: unsupported shape/alignment"); return -2; }
+  WPlan w = wgrad_plan(Nout, Kin, rows);
+  WP p;
+  p.A = dY; p.lda = ldy; p.B = X; p.ldb = ldx; p.rows = rows; p.M = Nout; p.N = Kin;
+  p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = w.m_tiles; p.nsplit = w.nsplit; p.rows_per_split = w.rows_per_split;
+  p.Mpad = w.Mpad;
+  const int stage_bytes = 2 * A_TILE + 2 * p.BN * 128;
+  const int fixed = 1024 + 8 * STG_BYTES + 256;
+  p.nstages = (SMEM_LIMIT - fixed) / stage_bytes;
+  if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
+  if (p.nstages < 2) { set_error("tc_wgrad: not enough shared memory"); return -2; }
+  const int smem_bytes = fixed + p.nstages * stage_bytes;
+  CUtensorMap tmP;
+  cuuint64_t pd[2] = {(cuuint64_t)w.Nld, (cuuint64_t)w.nsplit * w.Mpad};
+  cuuint64_t ps[1] = {(cuuint64_t)w.Nld * 4};
+  cuuint32_t pb[2] = {32, 32};
+  RD_TRY(encode(&tmP, partial, 2, pd, ps, pb, CU_TENSOR_MAP_SWIZZLE_128B, "wgrad partial"));
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
+    attr_set = true;
+  }
+  const int grid = w.nsplit * w.m_tiles * w.n_tiles;
+  tc_wgrad_kernel<<<grid, 448, smem_bytes, st>>>(tmP, p);
+  RD_CHECK_LAUNCH("tc_wgrad_kernel");
+  const long long n = (long long)Nout * (Kin + 1);
+  wgrad_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, w.nsplit, Nout, Kin, w.Mpad, w.Nld, dW, db);
+  RD_CHECK_LAUNCH("wgrad_reduce_kernel");
   return 0;
 }
 

@@ -22,6 +22,16 @@ struct TcGemmArgs {
 bool tc_gemm_supported(const TcGemmArgs& a);
 int tc_gemm(const TcGemmArgs& a, cudaStream_t st);
 
+// Weight gradient on the tensor cores: dW[Nout, Kin] = sum_r dY[r, Nout]^T X[r, Kin], db[Nout] = sum_r dY[r, :]
+// (the bias gradient rides along as one extra "ones" column of X).  Both operands are activations: the
+// loader warps read them row-major (coalesced), transpose 4x4 blocks in registers, split hi/lo and write
+// the K-major swizzled tiles.  The row range is split across CTAs; partial tiles go to `partial`
+// (tc_wgrad_partial_floats(...) floats) and are summed in a fixed order (deterministic).
+bool tc_wgrad_supported(int Nout, int Kin, long long ldy, long long ldx, const void* dY, const void* X);
+long long tc_wgrad_partial_floats(int Nout, int Kin, long long rows);
+int tc_wgrad(const float* dY, long long ldy, const float* X, long long ldx, long long rows, int Nout, int Kin,
+             float* dW, float* db, float* partial, cudaStream_t st);
+
 // One launch for all weights of a step: lo = W - trunc19(W); t = W^T; t_lo = W^T - trunc19(W^T).
 struct WeightSplit { const float* w; int rows, cols; float* lo; float* t; float* t_lo; };
 int split_weights(const WeightSplit* items, int n, cudaStream_t st);   // n <= 16

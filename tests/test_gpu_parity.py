@@ -255,6 +255,29 @@ def test_projection_gemm_is_fp32_accurate(rows, in_f, out_f):
     assert e < 1e-5 and e < 20 * e32 + 1e-7, (e, e32)   # TF32 alone would be ~5e-4
 
 
+@pytest.mark.parametrize("rows,Cc", [(1000, 240), (4352, 240), (700, 860), (300, 64)])
+def test_obprop_operator_backward_weight_grads(rows, Cc):
+    """rd_obprop_bwd at sizes that take the tensor-core weight-gradient kernel (3xTF32, split over rows):
+    dW and db must be fp32-accurate given the same forward output."""
+    from oracle.raindrop_oracle import round_tf32
+    from raindrop_b200 import functional as RF
+    g = torch.Generator().manual_seed(rows * 3 + Cc)
+    x = round_tf32(torch.randn(rows, Cc, generator=g))
+    W = round_tf32(torch.randn(Cc, Cc, generator=g) / Cc ** 0.5)
+    b = torch.randn(Cc, generator=g) * 0.1
+    s = torch.rand(17, generator=g) + 0.5
+    xr, Wr, br = x.cuda().requires_grad_(True), W.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    out = RF.ObPropLayerFunction.apply(xr, Wr, br, s.cuda(), 17)
+    w = torch.randn(rows, Cc, generator=g)
+    (out * w.cuda()).sum().backward()
+    # reference gradient given the SAME gate pattern (out > 0), in fp64
+    gate = (out.detach().cpu() > 0).double()
+    dpre = w.double() * s.double()[torch.arange(rows) % 17][:, None] * gate
+    assert normwise(Wr.grad, dpre.T @ x.double()) < 1e-5
+    assert normwise(br.grad, dpre.sum(0)) < 1e-5
+    assert normwise(xr.grad, dpre @ W.double()) < 1e-5      # CUDA-core path for d_x in the operator
+
+
 def test_positional_encoding():
     from oracle.raindrop_oracle import positional_encoding
     from raindrop_b200.models_rd import PositionalEncodingTF
