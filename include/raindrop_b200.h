@@ -135,6 +135,18 @@ int rd_obprop_bwd(const float* x, const float* out, const float* d_out, const fl
                   const float* node_scale, int32_t scale_mod, int64_t rows, int32_t C,
                   float* d_x, float* d_weight, float* d_bias, void* scratch, void* stream);
 
+/* Observation_progation.forward with use_beta=True (code/Ob_propagation.py:161-186,191,195-228; dormant in
+ * Raindrop_v2, code/models_rd.py:317, but part of the operator's API).  One sample: x [N, C=T*d_ob],
+ * p_t [T, 16].  Keeps the K = E/2 edges with the highest mean gamma (in that order), regroups them by
+ * SOURCE for the per-channel segment softmax and scatters to the source (as the reference does).
+ * Outputs: out [N, C]; pruned edge list edge_src_out/edge_tgt_out [K]; alpha_out [K].  Forward only. */
+size_t rd_obprop_beta_scratch_bytes(int32_t N, int32_t T, int32_t d_ob, int32_t E);
+int rd_obprop_beta_fwd(const float* x, const float* p_t, const int64_t* edge_src, const int64_t* edge_tgt,
+                       const float* edge_w, int32_t E, int32_t N, int32_t T, int32_t d_ob,
+                       const float* increase_dim_w, const float* increase_dim_b, const float* map_weights,
+                       const float* value_w, const float* value_b, float* out, int64_t* edge_src_out,
+                       int64_t* edge_tgt_out, float* alpha_out, void* scratch, void* stream);
+
 /* ---- whole Raindrop_v2 forward / backward ---------------------------------------------------
  * Replaces Raindrop_v2.forward (code/models_rd.py:278-387) for the live configuration
  * (sensor_wise_mask=False, aggreg='mean', use_beta=False) and its autograd backward

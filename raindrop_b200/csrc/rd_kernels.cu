@@ -140,7 +140,8 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 
 __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ stats,
                                         const float* __restrict__ gamma, const float* __restrict__ dy,
-                                        long long rows, int D, float* __restrict__ dx) {
+                                        long long rows, int D, float* __restrict__ dx, float* __restrict__ dx_drop,
+                                        float drop_p, const uint64_t* __restrict__ rng, uint32_t site) {
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -160,7 +161,9 @@ __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float
   for (int j = lane; j < D; j += 32) {
     float g = dyr[j] * __ldg(gamma + j);
     float xh = (xr[j] - mean) * rstd;
-    dxr[j] = rstd * (g - s1 - xh * s2);
+    float v = rstd * (g - s1 - xh * s2);
+    dxr[j] = v;
+    if (dx_drop) dx_drop[row * D + j] = v * dropout_scale(rng, site, (uint64_t)row * D + j, drop_p, 1.f / (1.f - drop_p));
   }
 }
 
@@ -241,16 +244,25 @@ __global__ void attn_softmax_bwd_kernel(const float* __restrict__ P, float* __re
   }
 }
 
+// block (32 channels, 8 time groups): coalesced along d, the T reads of one channel are spread over 8
+// threads and reduced through shared memory (fixed order -> deterministic)
 __global__ void masked_mean_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengths, int T, int B,
                                        int D, float* __restrict__ out, long long ld) {
-  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= (long long)B * D) return;
-  int b = (int)(o / D), d = (int)(o - (long long)b * D);
-  long long len = lengths[b];
-  int nv = (int)(len < T ? (len < 0 ? 0 : len) : T);
+  __shared__ float red[8][33];
+  const int b = blockIdx.y;
+  const int d = blockIdx.x * 32 + threadIdx.x;
+  const long long len = lengths[b];
+  const int nv = (int)(len < T ? (len < 0 ? 0 : len) : T);
   float s = 0.f;
-  for (int t = 0; t < nv; ++t) s += x[((long long)t * B + b) * D + d];
-  out[(long long)b * ld + d] = s / (float)(len + 1);
+  if (d < D)
+    for (int t = threadIdx.y; t < nv; t += 8) s += x[((long long)t * B + b) * D + d];
+  red[threadIdx.y][threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.y == 0 && d < D) {
+#pragma unroll
+    for (int g = 1; g < 8; ++g) s += red[g][threadIdx.x];
+    out[(long long)b * ld + d] = s / (float)(len + 1);
+  }
 }
 
 __global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, long long ld,
@@ -398,8 +410,10 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t
 int64_t ln_bwd_scratch_floats(int64_t rows, int D) { return ceil_div(rows, LN_ROWS) * 2 * D; }
 
 int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows, int D,
-                  float* dx, float* dgamma, float* dbeta, float* scratch, cudaStream_t st) {
-  layernorm_bwd_dx_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, stats, gamma, dy, rows, D, dx);
+                  float* dx, float* dgamma, float* dbeta, float* scratch, float* dx_drop, float drop_p,
+                  const uint64_t* rng, uint32_t site, cudaStream_t st) {
+  layernorm_bwd_dx_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, stats, gamma, dy, rows, D, dx,
+                                                              drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site);
   RD_CHECK_LAUNCH("layernorm_bwd_dx_kernel");
   int chunks = (int)ceil_div(rows, LN_ROWS);
   if (chunks > 65535) { set_error("layernorm_bwd: too many row chunks"); return -2; }
@@ -428,7 +442,8 @@ int attn_softmax_bwd(const float* P, float* dP, int B, int H, int T, float drop_
 
 int masked_mean_fwd(const float* x, const int64_t* lengths, int T, int B, int D, float* out, int64_t ld,
                     cudaStream_t st) {
-  masked_mean_fwd_kernel<<<blocks_for((int64_t)B * D), TPB, 0, st>>>(x, lengths, T, B, D, out, ld);
+  if (B > 65535) { set_error("masked_mean_fwd: batch too large for one launch"); return -2; }
+  masked_mean_fwd_kernel<<<dim3((unsigned)ceil_div(D, 32), (unsigned)B), dim3(32, 8), 0, st>>>(x, lengths, T, B, D, out, ld);
   RD_CHECK_LAUNCH("masked_mean_fwd_kernel");
   return 0;
 }

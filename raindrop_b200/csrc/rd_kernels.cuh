@@ -24,8 +24,11 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t
                   float* y, float* stats, cudaStream_t st);
 // dx from dy; dgamma/dbeta via partials. scratch >= ln_bwd_scratch_floats(rows, D)
 int64_t ln_bwd_scratch_floats(int64_t rows, int D);
+// dx_drop (optional, used when drop_p > 0): dx with the dropout mask of `site` re-applied, i.e. the
+// gradient w.r.t. the sub-layer output that was dropped before the residual add
 int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows,
-                  int D, float* dx, float* dgamma, float* dbeta, float* scratch, cudaStream_t st);
+                  int D, float* dx, float* dgamma, float* dbeta, float* scratch, float* dx_drop, float drop_p,
+                  const uint64_t* rng, uint32_t site, cudaStream_t st);
 
 // in-place masked softmax over rows of S [B,H,T,T]; key j masked when j >= lengths[b].
 // If Pd != nullptr also writes the dropped probabilities (training).

@@ -359,9 +359,9 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     const float* ctx = ws + w.l[l].ctx; const float* r1 = ws + w.l[l].r1; const float* x1 = ws + w.l[l].x1;
     const float* f = ws + w.l[l].f; const float* r2 = ws + w.l[l].r2;
     // norm2 + feed-forward block
-    RD_TRY(layernorm_bwd(r2, ws + w.l[l].st2, E.norm2_weight, gA, s.M2, s.D, gB, GE.norm2_weight, GE.norm2_bias, aux, st));
-    const float* dg = gB;
-    if (s.p > 0.f) { RD_TRY(apply_dropout(gB, s.M2 * s.D, s.p, rng, SITE_RESID2 + l, gC, st)); dg = gC; }
+    RD_TRY(layernorm_bwd(r2, ws + w.l[l].st2, E.norm2_weight, gA, s.M2, s.D, gB, GE.norm2_weight, GE.norm2_bias, aux,
+                         gC, s.p, rng, SITE_RESID2 + l, st));
+    const float* dg = s.p > 0.f ? gC : gB;
     RD_TRY(tn(dg, s.D, f, s.nhid, GE.linear2_weight, GE.linear2_bias, s.D, s.nhid, s.M2, partial, st));
     {   // gF = (dg . W2) * [f > 0] / (1-p)   ("NT" against W2^T so that the tensor-core kernel applies)
       GemmP g = nt(dg, s.D, ws + w.wsp[l].l2_t, s.D, gF, s.nhid, s.M2, s.nhid, s.D);
@@ -375,9 +375,9 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
       RD_TRY(linear_nt(g, ws + w.wsp[l].l1_tlo, st));
     }
     // norm1 + self-attention block
-    RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, gB, GE.norm1_weight, GE.norm1_bias, aux, st));
-    const float* dy = gB;
-    if (s.p > 0.f) { RD_TRY(apply_dropout(gB, s.M2 * s.D, s.p, rng, SITE_RESID1 + l, gC, st)); dy = gC; }
+    RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, gB, GE.norm1_weight, GE.norm1_bias, aux,
+                         gC, s.p, rng, SITE_RESID1 + l, st));
+    const float* dy = s.p > 0.f ? gC : gB;
     RD_TRY(tn(dy, s.D, ctx, s.D, GE.out_proj_weight, GE.out_proj_bias, s.D, s.D, s.M2, partial, st));
     RD_TRY(linear_nt(nt(dy, s.D, ws + w.wsp[l].out_t, s.D, gD, s.D, s.M2, s.D, s.D), ws + w.wsp[l].out_tlo, st));
     {  // dPd[b,h] = dctx V^T

@@ -186,6 +186,29 @@ class ObPropLayerFunction(torch.autograd.Function):
         return d_x, d_w, d_b, None, None
 
 
+def obprop_beta(x, p_t, edge_index, edge_weights, d_ob, inc_w, inc_b, map_w, val_w, val_b):
+    """Observation_progation.forward(use_beta=True) for one sample (rd_obprop_beta_fwd); inference only.
+    Returns (out [N, C], edge_index_pruned [2, K], alpha [K])."""
+    lib = L.load()
+    x, p_t = _as_f32(x), _as_f32(p_t)
+    N, Cc = x.shape
+    T = Cc // d_ob
+    src_i, tgt_i = edge_index[0].contiguous().long(), edge_index[1].contiguous().long()
+    E = src_i.numel()
+    K = E // 2
+    w = _as_f32(edge_weights)
+    out = torch.empty(N, Cc, dtype=torch.float32, device=x.device)
+    ei = torch.empty(2, K, dtype=torch.int64, device=x.device)
+    alpha = torch.empty(K, dtype=torch.float32, device=x.device)
+    sc = torch.empty(lib.rd_obprop_beta_scratch_bytes(N, T, d_ob, E) // 4, dtype=torch.float32, device=x.device)
+    ps = [_as_f32(t) for t in (inc_w, inc_b, map_w, val_w, val_b)]
+    rc = lib.rd_obprop_beta_fwd(x.data_ptr(), p_t.data_ptr(), src_i.data_ptr(), tgt_i.data_ptr(), w.data_ptr(), E, N, T,
+                                d_ob, *[p.data_ptr() for p in ps], out.data_ptr(), ei[0].data_ptr(), ei[1].data_ptr(),
+                                alpha.data_ptr(), sc.data_ptr(), L.stream_ptr())
+    L.check(rc, "rd_obprop_beta_fwd")
+    return out, ei, alpha
+
+
 def node_scale(edge_index, edge_weights, n_nodes):
     """s[n] = sum over incoming edges of the segment softmax (rd_node_scale)."""
     lib = L.load()

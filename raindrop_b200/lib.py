@@ -69,6 +69,8 @@ SIGNATURES = {
     "rd_obprop_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32,
                                 C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                 C.c_void_p]),
+    "rd_obprop_beta_scratch_bytes": (C.c_size_t, [C.c_int32] * 4),
+    "rd_obprop_beta_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p] * 11),
     "rd_workspace_bytes": (C.c_size_t, [C.POINTER(RdDims)]),
     "rd_backward_scratch_bytes": (C.c_size_t, [C.POINTER(RdDims)]),
     "rd_workspace_offset": (C.c_int64, [C.POINTER(RdDims), C.c_int32, C.POINTER(C.c_int64)]),

@@ -95,14 +95,20 @@ class Observation_progation(nn.Module):
 
     def forward(self, x, p_t, edge_index, edge_weights=None, use_beta=False, edge_attr=None,
                 return_attention_weights=None):
-        if use_beta:
-            raise NotImplementedError("use_beta=True (code/Ob_propagation.py:161-186) is dormant in Raindrop_v2 "
-                                      "(code/models_rd.py:317) and not built yet")
         if edge_weights is None:
             raise ValueError("edge_weights is required (the reference fails without it, code/Ob_propagation.py:195)")
         if isinstance(x, (tuple, list)):
             x = x[1]
         n = x.shape[0]
+        if use_beta:
+            # dormant in Raindrop_v2 (code/models_rd.py:317) but part of the operator: forward only
+            with torch.no_grad():
+                out, ei, alpha = RF.obprop_beta(x, p_t, edge_index, edge_weights, self.ob_dim, self.increase_dim.weight,
+                                                self.increase_dim.bias, self.map_weights, self.lin_value.weight,
+                                                self.lin_value.bias)
+            if isinstance(return_attention_weights, bool):
+                return out, (ei, alpha)
+            return out
         s = RF.node_scale(edge_index, edge_weights, n)
         out = RF.ObPropLayerFunction.apply(x, self.lin_value.weight, self.lin_value.bias, s, n)
         if isinstance(return_attention_weights, bool):

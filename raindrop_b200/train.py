@@ -45,6 +45,33 @@ def allreduce_gradients(model, group=None):
         off += g.numel()
 
 
+def shard_slice(n, rank, world):
+    """Contiguous slice of `n` samples owned by `rank` (sizes differ by at most one)."""
+    base, extra = divmod(n, world)
+    start = rank * base + min(rank, extra)
+    return slice(start, start + base + (1 if rank < extra else 0))
+
+
+def evaluate_sharded(model, P, Pstatic, Ptime, group=None):
+    """`evaluate_standard` (code/utils_rd.py:310-320: the WHOLE validation set as one batch) with the samples
+    sharded over the ranks and the logits all-gathered, so every rank returns the full [n, n_classes]."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    n = P.shape[1]
+    sl = shard_slice(n, rank, world)
+    dev = next(model.parameters()).device
+    with torch.no_grad():
+        Pt = Ptime[:, sl].to(dev)
+        lengths = torch.sum(Pt > 0, dim=0)
+        out, _, _ = model.forward(P[:, sl].to(dev), None if Pstatic is None else Pstatic[sl].to(dev), Pt, lengths)
+    if world == 1:
+        return out
+    sizes = [shard_slice(n, r, world) for r in range(world)]
+    bufs = [torch.empty(s.stop - s.start, out.shape[1], dtype=out.dtype, device=out.device) for s in sizes]
+    dist.all_gather(bufs, out.contiguous(), group=group)
+    return torch.cat(bufs, 0)
+
+
 class TrainStep:
     """fwd + loss + bwd + (all-reduce) + Adam for a fixed batch size on static device buffers."""
 

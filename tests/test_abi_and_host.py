@@ -126,3 +126,14 @@ def test_synthetic_batch_conventions():
     assert int((z["src"][:, 0, :N].abs().sum(0) == 0).sum()) >= 10
     again = make_batch(cfg, 16, seed=3)
     assert all(torch.equal(b[k], again[k]) for k in ("src", "times", "lengths", "y", "static"))
+
+
+def test_shard_slices_partition_the_batch():
+    from raindrop_b200.train import shard_slice
+    for n in (1, 7, 128, 3880):
+        for world in (1, 2, 3, 8):
+            parts = [shard_slice(n, r, world) for r in range(world)]
+            assert parts[0].start == 0 and parts[-1].stop == n
+            assert all(a.stop == b.start for a, b in zip(parts, parts[1:]))
+            sizes = [p.stop - p.start for p in parts]
+            assert max(sizes) - min(sizes) <= 1
