@@ -38,6 +38,13 @@ int attn_softmax_fwd(float* S, const int64_t* lengths, int B, int H, int T, floa
 int attn_softmax_bwd(const float* P, float* dP, int B, int H, int T, float drop_p, const uint64_t* rng,
                      uint32_t site, cudaStream_t st);
 
+// fused attention for short sequences (rd_attn_small.cu): ctx from qkv in one launch, dqkv in one launch
+bool attn_small_supported(int T, int hd);
+int attn_small_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T, int hd, float drop_p,
+                   const uint64_t* rng, uint32_t site, float* ctx, cudaStream_t st);
+int attn_small_bwd(const float* qkv, const float* dctx, const int64_t* lengths, int B, int H, int T, int hd,
+                   float drop_p, const uint64_t* rng, uint32_t site, float* dqkv, cudaStream_t st);
+
 // pooled[b, d] = sum_{t < len_b} x[t,b,d] / (len_b + 1) -> out[b*ld + d]     code/models_rd.py:366-379
 int masked_mean_fwd(const float* x, const int64_t* lengths, int T, int B, int D, float* out, int64_t ld,
                     cudaStream_t st);
