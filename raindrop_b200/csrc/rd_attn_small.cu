@@ -6,14 +6,18 @@
 // the P19 shape (T = 60, hd = 76).  A 60 x 60 x 76 problem is far below one 128-row UMMA tile and needs
 // fp32 accuracy, so it runs on the CUDA cores with 4x4 / 4x5 register tiles; longer sequences take the
 // batched-GEMM path (rd_model.cu).
+#include <stdlib.h>
+
 #include "rd_kernels.cuh"
 
 namespace rd {
 namespace {
 
 constexpr int TM = 64;      // max sequence length
-constexpr int HDM = 96;     // max head dim
+constexpr int HDM = 96;     // max head dim (6 columns per thread x 16 threads)
 constexpr int NT = 256;
+constexpr int LDR = 100;    // row-major [t][d] stride (d < 96 zero padded; even -> float2 reads of 6 contiguous columns)
+constexpr int LDT = 68;     // transposed [d][t] / [j][i] stride (multiple of 4 -> float4 reads of 4 contiguous rows)
 
 struct AttnP {
   const float* qkv; float* ctx;            // forward
@@ -24,92 +28,102 @@ struct AttnP {
   const uint64_t* rng; uint32_t site;
 };
 
-// S = scale * Q K^T with key-padding mask, softmax -> Ps (probabilities) and Pd (dropped copy)
-__device__ __forceinline__ void scores_softmax(const AttnP& p, int b, int h, const float* Qs, const float* Ks, float* Ps,
-                                               float* Pd, int ldq) {
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const int T = p.T, hd = p.hd;
+// dst[t*LDR + d] (row-major, zero padded to 64 x 96)
+__device__ __forceinline__ void load_rm(const float* __restrict__ src, long long row_stride, int T, int hd, float* dst) {
+  for (int idx = threadIdx.x; idx < TM * HDM; idx += NT) {
+    int t = idx / HDM, d = idx - t * HDM;
+    dst[t * LDR + d] = (t < T && d < hd) ? __ldg(src + (long long)t * row_stride + d) : 0.f;
+  }
+}
+// dst[d*LDT + t] (transposed, t zero padded to 64)
+__device__ __forceinline__ void load_tr(const float* __restrict__ src, long long row_stride, int T, int hd, float* dst) {
+  for (int idx = threadIdx.x; idx < TM * hd; idx += NT) {
+    int t = idx / hd, d = idx - t * hd;
+    dst[d * LDT + t] = t < T ? __ldg(src + (long long)t * row_stride + d) : 0.f;
+  }
+}
+
+// out[i][j] = alpha * sum_d At[d][i] * Bt[d][j]   (both operands transposed in smem: 2 LDS.128 per 16 FMA)
+__device__ __forceinline__ void gemm_tt(const float* At, const float* Bt, int hd, float alpha, float* out) {
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
   for (int d = 0; d < hd; ++d) {
-    float q[4], k[4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r) q[r] = Qs[(4 * ty + r) * ldq + d];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) k[c] = Ks[(4 * tx + c) * ldq + d];
+    const float4 a = *reinterpret_cast<const float4*>(At + d * LDT + 4 * ty);
+    const float4 b = *reinterpret_cast<const float4*>(Bt + d * LDT + 4 * tx);
+    const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(q[r], k[c], acc[r][c]);
+      for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r)
-#pragma unroll
-    for (int c = 0; c < 4; ++c) Ps[(4 * ty + r) * (TM + 1) + 4 * tx + c] = acc[r][c] * p.scale;
-  __syncthreads();
+    *reinterpret_cast<float4*>(out + (4 * ty + r) * LDT + 4 * tx) =
+        make_float4(acc[r][0] * alpha, acc[r][1] * alpha, acc[r][2] * alpha, acc[r][3] * alpha);
+}
+
+// key-padding-masked softmax of the rows of Ps (in place -> probabilities); the dropped copy goes to
+// Pd[i*pd_si + j*pd_sj] (row-major or transposed, whatever the consumer wants)
+__device__ __forceinline__ void softmax_rows(const AttnP& p, int b, int h, float* Ps, float* Pd, int pd_si, int pd_sj) {
+  const int T = p.T;
   const long long len = p.lengths[b];
   const int nv = (int)(len < T ? (len < 0 ? 0 : len) : T);
   const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-  const int warp = tid >> 5, lane = tid & 31;
-  for (int i = warp; i < T; i += NT / 32) {
-    float* row = Ps + i * (TM + 1);
-    float v0 = lane < nv ? row[lane] : -INFINITY, v1 = lane + 32 < nv ? row[lane + 32] : -INFINITY;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = warp; i < TM; i += NT / 32) {
+    float* row = Ps + i * LDT;
+    float v0 = (i < T && lane < nv) ? row[lane] : -INFINITY, v1 = (i < T && lane + 32 < nv) ? row[lane + 32] : -INFINITY;
     float mx = warp_max(fmaxf(v0, v1));
-    float e0 = lane < nv ? expf(v0 - mx) : 0.f, e1 = lane + 32 < nv ? expf(v1 - mx) : 0.f;
+    float e0 = (i < T && lane < nv) ? expf(v0 - mx) : 0.f, e1 = (i < T && lane + 32 < nv) ? expf(v1 - mx) : 0.f;
     float sum = warp_sum(e0 + e1);
-    float inv = nv > 0 ? 1.f / sum : 0.f;
+    float inv = (i < T && nv > 0) ? 1.f / sum : 0.f;
     const uint64_t base = ((uint64_t)(b * p.H + h) * T + i) * T;     // index space [B, H, T, T]
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      int j = lane + 32 * half;
-      if (j < TM) {
-        float pr = (half ? e1 : e0) * inv;
-        row[j] = pr;
-        float m = (p.drop_p > 0.f && j < T) ? dropout_scale(p.rng, p.site, base + j, p.drop_p, ik) : 1.f;
-        Pd[i * (TM + 1) + j] = pr * m;
-      }
+      const int j = lane + 32 * half;
+      const float pr = (half ? e1 : e0) * inv;
+      row[j] = pr;
+      const float m = (p.drop_p > 0.f && i < T && j < T) ? dropout_scale(p.rng, p.site, base + j, p.drop_p, ik) : 1.f;
+      Pd[i * pd_si + j * pd_sj] = pr * m;
     }
-  }
-  __syncthreads();
-}
-
-__device__ __forceinline__ void load_head(const float* __restrict__ src, long long row_stride, int T, int hd, float* dst,
-                                          int ld) {
-  for (int idx = threadIdx.x; idx < TM * ld; idx += NT) {
-    int t = idx / ld, d = idx - t * ld;
-    dst[idx] = (t < T && d < hd) ? __ldg(src + (long long)t * row_stride + d) : 0.f;
   }
 }
 
 __global__ void __launch_bounds__(NT) attn_small_fwd_kernel(AttnP p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
-  const int ld = p.hd + 1;
-  float* Qs = sm; float* Ks = Qs + TM * ld; float* Vs = Ks + TM * ld;
-  float* Ps = Vs + TM * ld; float* Pd = Ps + TM * (TM + 1);
+  float* Qt = sm; float* Kt = Qt + HDM * LDT; float* Vs = Kt + HDM * LDT;
+  float* Ps = Vs + TM * LDR; float* PdT = Ps + TM * LDT;
   const long long rs = (long long)p.B * 3 * p.D;
   const float* base = p.qkv + (long long)b * 3 * p.D + h * p.hd;
-  load_head(base, rs, p.T, p.hd, Qs, ld);
-  load_head(base + p.D, rs, p.T, p.hd, Ks, ld);
-  load_head(base + 2 * p.D, rs, p.T, p.hd, Vs, ld);
+  load_tr(base, rs, p.T, p.hd, Qt);
+  load_tr(base + p.D, rs, p.T, p.hd, Kt);
+  load_rm(base + 2 * p.D, rs, p.T, p.hd, Vs);
   __syncthreads();
-  scores_softmax(p, b, h, Qs, Ks, Ps, Pd, ld);
-  // ctx[i, d] = sum_j Pd[i, j] V[j, d]
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  gemm_tt(Qt, Kt, p.hd, p.scale, Ps);
+  __syncthreads();
+  softmax_rows(p, b, h, Ps, PdT, 1, LDT);      // dropped probabilities transposed: PdT[j][i]
+  __syncthreads();
+  // ctx[i, d] = sum_j Pd[i, j] V[j, d]; thread tile 4 rows x 6 contiguous columns
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float acc[4][6];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc[r][c] = 0.f;
   for (int j = 0; j < p.T; ++j) {
-    float pv[4], vv[6];
+    const float4 p4 = *reinterpret_cast<const float4*>(PdT + j * LDT + 4 * ty);
+    const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
+    float vv[6];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) pv[r] = Pd[(4 * ty + r) * (TM + 1) + j];
-#pragma unroll
-    for (int c = 0; c < 6; ++c) vv[c] = Vs[j * ld + tx + 16 * c];     // columns >= hd are zero padding or unused
+    for (int c = 0; c < 3; ++c) {
+      const float2 v2 = *reinterpret_cast<const float2*>(Vs + j * LDR + 6 * tx + 2 * c);
+      vv[2 * c] = v2.x; vv[2 * c + 1] = v2.y;
+    }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -117,94 +131,87 @@ __global__ void __launch_bounds__(NT) attn_small_fwd_kernel(AttnP p) {
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    int i = 4 * ty + r;
+    const int i = 4 * ty + r;
     if (i >= p.T) continue;
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      int d = tx + 16 * c;
+      const int d = 6 * tx + c;
       if (d < p.hd) p.ctx[((long long)i * p.B + b) * p.D + h * p.hd + d] = acc[r][c];
     }
   }
 }
 
 __global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnP p) {
-  extern __shared__ float sm[];
+  extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
-  const int ld = p.hd + 1;
-  float* Qs = sm; float* Ks = Qs + TM * ld; float* Vs = Ks + TM * ld; float* Gs = Vs + TM * ld;   // Gs = d(ctx)
-  float* Ps = Gs + TM * ld; float* Pd = Ps + TM * (TM + 1); float* dS = Pd + TM * (TM + 1);
+  float* Qs = sm; float* Ks = Qs + TM * LDR; float* Gs = Ks + TM * LDR;             // row-major Q, K, d(ctx)
+  float* At = Gs + TM * LDR; float* Bt = At + HDM * LDT;                             // transposed scratch pair
+  float* Ps = Bt + HDM * LDT; float* Pd = Ps + TM * LDT; float* dS = Pd + TM * LDT; float* dST = dS + TM * LDT;
   const long long rs = (long long)p.B * 3 * p.D;
   const float* base = p.qkv + (long long)b * 3 * p.D + h * p.hd;
-  load_head(base, rs, p.T, p.hd, Qs, ld);
-  load_head(base + p.D, rs, p.T, p.hd, Ks, ld);
-  load_head(base + 2 * p.D, rs, p.T, p.hd, Vs, ld);
-  load_head(p.dctx + (long long)b * p.D + h * p.hd, (long long)p.B * p.D, p.T, p.hd, Gs, ld);
+  const float* gsrc = p.dctx + (long long)b * p.D + h * p.hd;
+  const long long grs = (long long)p.B * p.D;
+  load_tr(base, rs, p.T, p.hd, At);
+  load_tr(base + p.D, rs, p.T, p.hd, Bt);
+  load_rm(base, rs, p.T, p.hd, Qs);
+  load_rm(base + p.D, rs, p.T, p.hd, Ks);
+  load_rm(gsrc, grs, p.T, p.hd, Gs);
   __syncthreads();
-  scores_softmax(p, b, h, Qs, Ks, Ps, Pd, ld);            // recompute P and the dropped copy
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  {  // dPd[i, j] = sum_d G[i, d] V[j, d]
-    float acc[4][4];
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-    for (int d = 0; d < p.hd; ++d) {
-      float g[4], v[4];
-#pragma unroll
-      for (int r = 0; r < 4; ++r) g[r] = Gs[(4 * ty + r) * ld + d];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) v[c] = Vs[(4 * tx + c) * ld + d];
-#pragma unroll
-      for (int r = 0; r < 4; ++r)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(g[r], v[c], acc[r][c]);
-    }
-#pragma unroll
-    for (int r = 0; r < 4; ++r)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) dS[(4 * ty + r) * (TM + 1) + 4 * tx + c] = acc[r][c];
-  }
+  gemm_tt(At, Bt, p.hd, p.scale, Ps);                     // recompute the scores ...
   __syncthreads();
-  {  // dS = P * (dP - rowsum(dP * P)),  dP = dPd * mask/(1-p) = dPd * Pd / P where P > 0
-    const int warp = tid >> 5, lane = tid & 31;
+  load_tr(gsrc, grs, p.T, p.hd, At);                      // scratch pair now holds G^T and V^T
+  load_tr(base + 2 * p.D, rs, p.T, p.hd, Bt);
+  softmax_rows(p, b, h, Ps, Pd, LDT, 1);                  // ... and the probabilities (row-major dropped copy)
+  __syncthreads();
+  gemm_tt(At, Bt, p.hd, 1.f, dS);                         // dPd[i, j] = sum_d G[i, d] V[j, d]
+  __syncthreads();
+  {  // dS = P * (dP - rowsum(dP * P)), dP = dPd * mask/(1-p); written row-major and transposed
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    for (int i = warp; i < p.T; i += NT / 32) {
+    for (int i = warp; i < TM; i += NT / 32) {
       const uint64_t ibase = ((uint64_t)(b * p.H + h) * p.T + i) * p.T;
       float dp[2], pr[2];
       float dot = 0.f;
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        int j = lane + 32 * half;
-        pr[half] = j < p.T ? Ps[i * (TM + 1) + j] : 0.f;
-        float m = (p.drop_p > 0.f && j < p.T) ? dropout_scale(p.rng, p.site, ibase + j, p.drop_p, ik) : 1.f;
-        dp[half] = j < p.T ? dS[i * (TM + 1) + j] * m : 0.f;
+        const int j = lane + 32 * half;
+        const bool ok = i < p.T && j < p.T;
+        pr[half] = ok ? Ps[i * LDT + j] : 0.f;
+        const float m = (p.drop_p > 0.f && ok) ? dropout_scale(p.rng, p.site, ibase + j, p.drop_p, ik) : 1.f;
+        dp[half] = ok ? dS[i * LDT + j] * m : 0.f;
         dot += dp[half] * pr[half];
       }
       dot = warp_sum(dot);
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
-        int j = lane + 32 * half;
-        if (j < TM) dS[i * (TM + 1) + j] = pr[half] * (dp[half] - dot);
+        const int j = lane + 32 * half;
+        const float v = pr[half] * (dp[half] - dot);
+        dS[i * LDT + j] = v;
+        dST[j * LDT + i] = v;
       }
     }
   }
   __syncthreads();
-  // dQ[i, d] = scale * sum_j dS[i, j] K[j, d];  dK[j, d] = scale * sum_i dS[i, j] Q[i, d];  dV[j, d] = sum_i Pd[i, j] G[i, d]
+  // dQ[i, d] = scale * sum_j dS[i, j] K[j, d];  dK[j', d] = scale * sum_i dS[i, j'] Q[i, d];  dV[j', d] = sum_i Pd[i, j'] G[i, d]
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
   float aq[4][6], ak[4][6], av[4][6];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 6; ++c) { aq[r][c] = 0.f; ak[r][c] = 0.f; av[r][c] = 0.f; }
   for (int j = 0; j < p.T; ++j) {
-    float s_row[4], s_col[4], p_col[4], kk[6], qq[6], gg[6];
+    const float4 s4 = *reinterpret_cast<const float4*>(dST + j * LDT + 4 * ty);   // dS[i = 4ty.., j]
+    const float4 t4 = *reinterpret_cast<const float4*>(dS + j * LDT + 4 * ty);    // dS[i = j, j' = 4ty..]
+    const float4 q4 = *reinterpret_cast<const float4*>(Pd + j * LDT + 4 * ty);    // Pd[i = j, j' = 4ty..]
+    const float s_row[4] = {s4.x, s4.y, s4.z, s4.w}, s_col[4] = {t4.x, t4.y, t4.z, t4.w}, p_col[4] = {q4.x, q4.y, q4.z, q4.w};
+    float kk[6], qq[6], gg[6];
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
-      s_row[r] = dS[(4 * ty + r) * (TM + 1) + j];      // dS[i = 4ty+r, j]
-      s_col[r] = dS[j * (TM + 1) + 4 * ty + r];        // dS[i = j, j' = 4ty+r]  (transposed use)
-      p_col[r] = Pd[j * (TM + 1) + 4 * ty + r];
+    for (int c = 0; c < 3; ++c) {
+      const float2 k2 = *reinterpret_cast<const float2*>(Ks + j * LDR + 6 * tx + 2 * c);
+      const float2 q2 = *reinterpret_cast<const float2*>(Qs + j * LDR + 6 * tx + 2 * c);
+      const float2 g2 = *reinterpret_cast<const float2*>(Gs + j * LDR + 6 * tx + 2 * c);
+      kk[2 * c] = k2.x; kk[2 * c + 1] = k2.y; qq[2 * c] = q2.x; qq[2 * c + 1] = q2.y; gg[2 * c] = g2.x; gg[2 * c + 1] = g2.y;
     }
-#pragma unroll
-    for (int c = 0; c < 6; ++c) { int d = tx + 16 * c; kk[c] = Ks[j * ld + d]; qq[c] = Qs[j * ld + d]; gg[c] = Gs[j * ld + d]; }
 #pragma unroll
     for (int r = 0; r < 4; ++r)
 #pragma unroll
@@ -216,19 +223,19 @@ __global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnP p) {
   }
 #pragma unroll
   for (int r = 0; r < 4; ++r) {
-    int i = 4 * ty + r;
+    const int i = 4 * ty + r;
     if (i >= p.T) continue;
     float* o = p.dqkv + ((long long)i * p.B + b) * 3 * p.D + h * p.hd;
 #pragma unroll
     for (int c = 0; c < 6; ++c) {
-      int d = tx + 16 * c;
+      const int d = 6 * tx + c;
       if (d < p.hd) { o[d] = aq[r][c] * p.scale; o[p.D + d] = ak[r][c] * p.scale; o[2 * p.D + d] = av[r][c]; }
     }
   }
 }
 
-size_t fwd_smem(int hd) { return sizeof(float) * (3 * TM * (hd + 1) + 2 * TM * (TM + 1)); }
-size_t bwd_smem(int hd) { return sizeof(float) * (4 * TM * (hd + 1) + 3 * TM * (TM + 1)); }
+size_t fwd_smem(int) { return sizeof(float) * (2 * HDM * LDT + TM * LDR + 2 * TM * LDT); }
+size_t bwd_smem(int) { return sizeof(float) * (3 * TM * LDR + 2 * HDM * LDT + 4 * TM * LDT); }
 
 }  // namespace
 
