@@ -28,18 +28,45 @@ struct AttnP {
   const uint64_t* rng; uint32_t site;
 };
 
-// dst[t*LDR + d] (row-major, zero padded to 64 x 96)
-__device__ __forceinline__ void load_rm(const float* __restrict__ src, long long row_stride, int T, int hd, float* dst) {
-  for (int idx = threadIdx.x; idx < TM * HDM; idx += NT) {
-    int t = idx / HDM, d = idx - t * HDM;
-    dst[t * LDR + d] = (t < T && d < hd) ? __ldg(src + (long long)t * row_stride + d) : 0.f;
+// One [T x hd] head slice -> shared memory, row-major (rm[t*LDR + d], zero padded to 64 x 96) and/or
+// transposed (tr[d*LDT + t], t zero padded to 64).  All global loads of a thread are issued before the
+// first store (6 independent 128-bit loads in flight per thread: the slice is latency-, not bandwidth-bound).
+__device__ __forceinline__ void load_head(const float* __restrict__ src, long long row_stride, int T, int hd, bool vec,
+                                          float* rm, float* tr) {
+  if (vec) {
+    const int nvec = hd >> 2;
+    float4 v[6];
+    int tt[6], cc[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      const int idx = threadIdx.x + k * NT;
+      tt[k] = idx / nvec; cc[k] = idx - tt[k] * nvec;
+      v[k] = (tt[k] < T) ? __ldg(reinterpret_cast<const float4*>(src + (long long)tt[k] * row_stride + 4 * cc[k]))
+                         : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k) {
+      if (tt[k] >= TM) continue;
+      if (rm) *reinterpret_cast<float4*>(rm + tt[k] * LDR + 4 * cc[k]) = v[k];
+      if (tr) {
+        float* o = tr + (4 * cc[k]) * LDT + tt[k];
+        o[0] = v[k].x; o[LDT] = v[k].y; o[2 * LDT] = v[k].z; o[3 * LDT] = v[k].w;
+      }
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < TM * hd; idx += NT) {
+      const int t = idx / hd, d = idx - t * hd;
+      const float x = t < T ? __ldg(src + (long long)t * row_stride + d) : 0.f;
+      if (rm) rm[t * LDR + d] = x;
+      if (tr) tr[d * LDT + t] = x;
+    }
   }
-}
-// dst[d*LDT + t] (transposed, t zero padded to 64)
-__device__ __forceinline__ void load_tr(const float* __restrict__ src, long long row_stride, int T, int hd, float* dst) {
-  for (int idx = threadIdx.x; idx < TM * hd; idx += NT) {
-    int t = idx / hd, d = idx - t * hd;
-    dst[d * LDT + t] = t < T ? __ldg(src + (long long)t * row_stride + d) : 0.f;
+  if (rm) {   // zero the padding columns hd..95 (read by the 6-column register tiles)
+    const int npad = HDM - hd;
+    for (int idx = threadIdx.x; idx < TM * npad; idx += NT) {
+      const int t = idx / npad, d = hd + idx - t * npad;
+      rm[t * LDR + d] = 0.f;
+    }
   }
 }
 
@@ -100,9 +127,10 @@ __global__ void __launch_bounds__(NT) attn_small_fwd_kernel(AttnP p) {
   float* Ps = Vs + TM * LDR; float* PdT = Ps + TM * LDT;
   const long long rs = (long long)p.B * 3 * p.D;
   const float* base = p.qkv + (long long)b * 3 * p.D + h * p.hd;
-  load_tr(base, rs, p.T, p.hd, Qt);
-  load_tr(base + p.D, rs, p.T, p.hd, Kt);
-  load_rm(base + 2 * p.D, rs, p.T, p.hd, Vs);
+  const bool vec = (p.hd % 4 == 0) && (p.D % 4 == 0);
+  load_head(base, rs, p.T, p.hd, vec, nullptr, Qt);
+  load_head(base + p.D, rs, p.T, p.hd, vec, nullptr, Kt);
+  load_head(base + 2 * p.D, rs, p.T, p.hd, vec, Vs, nullptr);
   __syncthreads();
   gemm_tt(Qt, Kt, p.hd, p.scale, Ps);
   __syncthreads();
@@ -151,16 +179,15 @@ __global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnP p) {
   const float* base = p.qkv + (long long)b * 3 * p.D + h * p.hd;
   const float* gsrc = p.dctx + (long long)b * p.D + h * p.hd;
   const long long grs = (long long)p.B * p.D;
-  load_tr(base, rs, p.T, p.hd, At);
-  load_tr(base + p.D, rs, p.T, p.hd, Bt);
-  load_rm(base, rs, p.T, p.hd, Qs);
-  load_rm(base + p.D, rs, p.T, p.hd, Ks);
-  load_rm(gsrc, grs, p.T, p.hd, Gs);
+  const bool vec = (p.hd % 4 == 0) && (p.D % 4 == 0);
+  load_head(base, rs, p.T, p.hd, vec, Qs, At);            // Q: row-major for dK, transposed for the scores
+  load_head(base + p.D, rs, p.T, p.hd, vec, Ks, Bt);      // K
+  load_head(gsrc, grs, p.T, p.hd, vec, Gs, nullptr);      // d(ctx)
   __syncthreads();
   gemm_tt(At, Bt, p.hd, p.scale, Ps);                     // recompute the scores ...
   __syncthreads();
-  load_tr(gsrc, grs, p.T, p.hd, At);                      // scratch pair now holds G^T and V^T
-  load_tr(base + 2 * p.D, rs, p.T, p.hd, Bt);
+  load_head(gsrc, grs, p.T, p.hd, vec, nullptr, At);      // scratch pair now holds G^T and V^T
+  load_head(base + 2 * p.D, rs, p.T, p.hd, vec, nullptr, Bt);
   softmax_rows(p, b, h, Ps, Pd, LDT, 1);                  // ... and the probabilities (row-major dropped copy)
   __syncthreads();
   gemm_tt(At, Bt, p.hd, 1.f, dS);                         // dPd[i, j] = sum_d G[i, d] V[j, d]

@@ -202,19 +202,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         r[it] = (gr < p.M && k < p.K) ? __ldg(reinterpret_cast<const float4*>(p.A + gr * p.lda + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     };
-    int tile = blockIdx.x, kb = 0;
-    if (tile < total_tiles) issue(tile, 0, cur);
-    while (tile < total_tiles) {
-      int ntile = tile, nkb = kb + 1;
-      if (nkb == p.k_blocks) { nkb = 0; ntile = tile + gridDim.x; }
-      if (ntile < total_tiles) issue(ntile, nkb, nxt);      // in flight while we wait and store
+    // (tile, k-block) work units in order; loads run TWO units ahead of the stores (three rotating
+    // register buffers) so that an L2 round trip is hidden behind two MMA k-blocks
+    int lt_tile = blockIdx.x, lt_kb = 0;          // next unit to LOAD
+    auto advance = [&](int& t, int& k) { if (++k == p.k_blocks) { k = 0; t += gridDim.x; } };
+    auto store = [&](const float4 (&r)[8]) {
       mbar_wait(empty_bar(stage), phase ^ 1u);
       const uint32_t sa = base + (uint32_t)stage * stage_bytes;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
-        const int r = it * 16 + rsub;
-        const uint32_t off = (uint32_t)(r * 128 + ((chunk ^ (r & 7)) << 4));
-        const float4 a = cur[it];
+        const int row = it * 16 + rsub;
+        const uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
+        const float4 a = r[it];
         float4 lo;
         lo.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
         lo.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
@@ -227,9 +226,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
       if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
-#pragma unroll
-      for (int it = 0; it < 8; ++it) cur[it] = nxt[it];
-      tile = ntile; kb = nkb;
+    };
+    float4 r2[8];
+    int st_tile = blockIdx.x, st_kb = 0;          // next unit to STORE
+    if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, cur); advance(lt_tile, lt_kb); }
+    if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, nxt); advance(lt_tile, lt_kb); }
+    while (st_tile < total_tiles) {
+      if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, r2); advance(lt_tile, lt_kb); }
+      store(cur); advance(st_tile, st_kb);
+      if (st_tile >= total_tiles) break;
+      if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, cur); advance(lt_tile, lt_kb); }
+      store(nxt); advance(st_tile, st_kb);
+      if (st_tile >= total_tiles) break;
+      if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, nxt); advance(lt_tile, lt_kb); }
+      store(r2); advance(st_tile, st_kb);
     }
   }
   tc_fence_before();
