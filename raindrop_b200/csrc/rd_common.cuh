@@ -39,8 +39,7 @@ enum DropSite : uint32_t {
 // ---- Philox4x32-10, counter based: (seed, step) x (site, element index) ---------------------
 __device__ __forceinline__ uint32_t mulhi32(uint32_t a, uint32_t b) { return __umulhi(a, b); }
 
-__device__ __forceinline__ uint32_t philox_first(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1,
-                                                 uint32_t c2, uint32_t c3) {
+__device__ __forceinline__ uint4 philox4(uint32_t k0, uint32_t k1, uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3) {
   const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
 #pragma unroll
   for (int r = 0; r < 10; ++r) {
@@ -50,17 +49,33 @@ __device__ __forceinline__ uint32_t philox_first(uint32_t k0, uint32_t k1, uint3
     c0 = n0; c1 = n1; c2 = n2; c3 = n3;
     k0 += W0; k1 += W1;
   }
-  return c0;
+  return make_uint4(c0, c1, c2, c3);
 }
 
-// rng[0] = seed, rng[1] = step counter captured by the forward.  Returns 0 or 1/(1-p).
-__device__ __forceinline__ float dropout_scale(const uint64_t* __restrict__ rng, uint32_t site,
-                                               uint64_t idx, float p, float inv_keep) {
-  uint64_t seed = rng[0], step = rng[1];
-  uint32_t x = philox_first((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32),
-                            (uint32_t)idx, (uint32_t)(idx >> 32), site, (uint32_t)step);
-  float u = (float)(x >> 8) * (1.0f / 16777216.0f);
-  return u >= p ? inv_keep : 0.0f;
+// One Philox block serves FOUR consecutive element indices: element idx uses word (idx & 3) of the block
+// with counter idx >> 2.  rng[0] = seed, rng[1] = step counter captured by the forward.
+__device__ __forceinline__ uint4 dropout_block(const uint64_t* __restrict__ rng, uint32_t site, uint64_t idx) {
+  const uint64_t seed = rng[0], step = rng[1], blk = idx >> 2;
+  return philox4((uint32_t)seed, (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32), (uint32_t)blk, (uint32_t)(blk >> 32),
+                 site, (uint32_t)step);
+}
+__device__ __forceinline__ float keep_scale(uint32_t word, float p, float inv_keep) {
+  return (float)(word >> 8) * (1.0f / 16777216.0f) >= p ? inv_keep : 0.0f;
+}
+// Returns 0 or 1/(1-p) for element idx.
+__device__ __forceinline__ float dropout_scale(const uint64_t* __restrict__ rng, uint32_t site, uint64_t idx, float p,
+                                               float inv_keep) {
+  const uint4 b = dropout_block(rng, site, idx);
+  const uint32_t sel = (uint32_t)idx & 3u;
+  const uint32_t w = sel == 0 ? b.x : (sel == 1 ? b.y : (sel == 2 ? b.z : b.w));
+  return keep_scale(w, p, inv_keep);
+}
+// Four consecutive elements idx .. idx+3 (idx % 4 == 0) from one Philox block.
+__device__ __forceinline__ float4 dropout_scale4(const uint64_t* __restrict__ rng, uint32_t site, uint64_t idx, float p,
+                                                 float inv_keep) {
+  const uint4 b = dropout_block(rng, site, idx);
+  return make_float4(keep_scale(b.x, p, inv_keep), keep_scale(b.y, p, inv_keep), keep_scale(b.z, p, inv_keep),
+                     keep_scale(b.w, p, inv_keep));
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

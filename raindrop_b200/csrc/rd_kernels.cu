@@ -148,7 +148,36 @@ __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float
   const float* xr = x + row * D;
   const float* dyr = dy + row * D;
   float mean = stats[2 * row], rstd = stats[2 * row + 1];
+  const float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float s1 = 0.f, s2 = 0.f;
+  if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
+                        reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_drop)) & 15) == 0) {   // 128-bit path: lane owns columns 4*lane + 128*it
+    for (int j = 4 * lane; j < D; j += 128) {
+      const float4 d4 = *reinterpret_cast<const float4*>(dyr + j), x4 = *reinterpret_cast<const float4*>(xr + j);
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + j));
+      const float g[4] = {d4.x * g4.x, d4.y * g4.y, d4.z * g4.z, d4.w * g4.w};
+      const float xh[4] = {(x4.x - mean) * rstd, (x4.y - mean) * rstd, (x4.z - mean) * rstd, (x4.w - mean) * rstd};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { s1 += g[e]; s2 += g[e] * xh[e]; }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+    for (int j = 4 * lane; j < D; j += 128) {
+      const float4 d4 = *reinterpret_cast<const float4*>(dyr + j), x4 = *reinterpret_cast<const float4*>(xr + j);
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(gamma + j));
+      float4 o;
+      o.x = rstd * (d4.x * g4.x - s1 - (x4.x - mean) * rstd * s2);
+      o.y = rstd * (d4.y * g4.y - s1 - (x4.y - mean) * rstd * s2);
+      o.z = rstd * (d4.z * g4.z - s1 - (x4.z - mean) * rstd * s2);
+      o.w = rstd * (d4.w * g4.w - s1 - (x4.w - mean) * rstd * s2);
+      *reinterpret_cast<float4*>(dx + row * D + j) = o;
+      if (dx_drop) {
+        const float4 m = dropout_scale4(rng, site, (uint64_t)row * D + j, drop_p, ik);
+        *reinterpret_cast<float4*>(dx_drop + row * D + j) = make_float4(o.x * m.x, o.y * m.y, o.z * m.z, o.w * m.w);
+      }
+    }
+    return;
+  }
   for (int j = lane; j < D; j += 32) {
     float g = dyr[j] * __ldg(gamma + j);
     float xh = (xr[j] - mean) * rstd;
@@ -163,7 +192,7 @@ __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float
     float xh = (xr[j] - mean) * rstd;
     float v = rstd * (g - s1 - xh * s2);
     dxr[j] = v;
-    if (dx_drop) dx_drop[row * D + j] = v * dropout_scale(rng, site, (uint64_t)row * D + j, drop_p, 1.f / (1.f - drop_p));
+    if (dx_drop) dx_drop[row * D + j] = v * dropout_scale(rng, site, (uint64_t)row * D + j, drop_p, ik);
   }
 }
 

@@ -161,10 +161,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             o[0] = g.x > 0.f ? o[0] * p.gate_scale : 0.f; o[1] = g.y > 0.f ? o[1] * p.gate_scale : 0.f;
             o[2] = g.z > 0.f ? o[2] * p.gate_scale : 0.f; o[3] = g.w > 0.f ? o[3] * p.gate_scale : 0.f;
           }
-          if (p.drop_p > 0.f && ok) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e)
-              o[e] *= dropout_scale(p.rng, p.drop_site, (uint64_t)row * (uint64_t)p.N + (uint64_t)(c + e), p.drop_p, ik);
+          if (p.drop_p > 0.f && ok) {   // row*N + c is a multiple of 4: one Philox block for the four columns
+            const float4 m = dropout_scale4(p.rng, p.drop_site, (uint64_t)row * (uint64_t)p.N + (uint64_t)c, p.drop_p, ik);
+            o[0] *= m.x; o[1] *= m.y; o[2] *= m.z; o[3] *= m.w;
           }
           if (p.resid && ok) {
             float4 r = __ldg(reinterpret_cast<const float4*>(p.resid + row * p.resid_ld + c));
