@@ -96,6 +96,7 @@ def test_golden_fixture(golden_dir, name):
 @pytest.mark.parametrize("cfg_name,B,opts", [
     ("P19", 1, {}), ("P19", 37, {}), ("P19", 100, {"first_time_zero": True}), ("P19", 128, {"zero_sensors": 10}),
     ("P12", 5, {}), ("PAM", 3, {}), ("TINY", 7, {"full_length": True}), ("TINY8", 9, {}),
+    ("LARGE", 2, {}),      # BASELINE configs[4] shape: 128 sensors, T=256 (C=1024, D=528, head dim 264)
 ])
 def test_against_oracle(cfg_name, B, opts):
     """Seeded inputs, sizes the dense oracle finishes in seconds (arbitrary B incl. remainder batches)."""
