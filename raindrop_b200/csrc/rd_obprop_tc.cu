@@ -56,6 +56,8 @@ __device__ __forceinline__ float epi1(float acc, float bias, float sc, int relu,
   return rnd ? rn_tf32(v) : v;
 }
 
+// PERM / GATE / RELU / ROUND are compile-time so the streaming epilogue carries no runtime branches
+template <bool PERM, bool GATE, bool RELU, bool ROUND>
 __global__ void __launch_bounds__(NTHREADS, 1)
 obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
@@ -156,7 +158,7 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       // contiguous bytes of out[t, b, n*4 .. n*4+3] and consecutive lanes are consecutive sensors,
       // so one st.global.v4 per timestamp is a fully coalesced 512-byte warp store (no staging).
       float* perm_row = nullptr;
-      if (p.perm && row < p.M) {
+      if (PERM && row < p.M) {
         const int b = row / p.pN, n = row - b * p.pN;
         perm_row = p.out + (size_t)b * p.pD + (size_t)n * 4;
       }
@@ -165,17 +167,17 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + ch * 32), v);
         const float* bs = bias_s + acc * 256 + ch * 32;
         const int c0 = col0 + ch * 32;
-        if (p.perm) {
+        if (PERM) {
           if (perm_row) {
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
               const int t = (c0 >> 2) + j4;
               if (4 * t < p.C && ch * 32 + 4 * j4 < p.BN) {
                 float4 o;
-                o.x = epi1(__uint_as_float(v[4 * j4 + 0]), bs[4 * j4 + 0], sc, p.relu, p.round_out);
-                o.y = epi1(__uint_as_float(v[4 * j4 + 1]), bs[4 * j4 + 1], sc, p.relu, p.round_out);
-                o.z = epi1(__uint_as_float(v[4 * j4 + 2]), bs[4 * j4 + 2], sc, p.relu, p.round_out);
-                o.w = epi1(__uint_as_float(v[4 * j4 + 3]), bs[4 * j4 + 3], sc, p.relu, p.round_out);
+                o.x = epi1(__uint_as_float(v[4 * j4 + 0]), bs[4 * j4 + 0], sc, RELU, ROUND);
+                o.y = epi1(__uint_as_float(v[4 * j4 + 1]), bs[4 * j4 + 1], sc, RELU, ROUND);
+                o.z = epi1(__uint_as_float(v[4 * j4 + 2]), bs[4 * j4 + 2], sc, RELU, ROUND);
+                o.w = epi1(__uint_as_float(v[4 * j4 + 3]), bs[4 * j4 + 3], sc, RELU, ROUND);
                 *reinterpret_cast<float4*>(perm_row + (size_t)t * p.pB * p.pD) = o;
               }
             }
@@ -188,11 +190,11 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           float4 o;
-          o.x = epi1(__uint_as_float(v[4 * j4 + 0]), bs[4 * j4 + 0], sc, p.relu, p.round_out);
-          o.y = epi1(__uint_as_float(v[4 * j4 + 1]), bs[4 * j4 + 1], sc, p.relu, p.round_out);
-          o.z = epi1(__uint_as_float(v[4 * j4 + 2]), bs[4 * j4 + 2], sc, p.relu, p.round_out);
-          o.w = epi1(__uint_as_float(v[4 * j4 + 3]), bs[4 * j4 + 3], sc, p.relu, p.round_out);
-          if (p.gate) {   // backward: pass the gradient only where the forward output was positive
+          o.x = epi1(__uint_as_float(v[4 * j4 + 0]), bs[4 * j4 + 0], sc, RELU, ROUND);
+          o.y = epi1(__uint_as_float(v[4 * j4 + 1]), bs[4 * j4 + 1], sc, RELU, ROUND);
+          o.z = epi1(__uint_as_float(v[4 * j4 + 2]), bs[4 * j4 + 2], sc, RELU, ROUND);
+          o.w = epi1(__uint_as_float(v[4 * j4 + 3]), bs[4 * j4 + 3], sc, RELU, ROUND);
+          if (GATE) {   // backward: pass the gradient only where the forward output was positive
             float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row < p.M && c0 + 4 * j4 < p.C) g = __ldg(reinterpret_cast<const float4*>(p.gate + (size_t)row * p.C + c0 + 4 * j4));
             o.x = g.x > 0.f ? o.x : 0.f; o.y = g.y > 0.f ? o.y : 0.f; o.z = g.z > 0.f ? o.z : 0.f; o.w = g.w > 0.f ? o.w : 0.f;
@@ -305,15 +307,26 @@ int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st) {
   } else {
     tmOut = tmA;   // permuted output is written with plain vector stores; the map is not used
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(obprop_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
-    attr_set = true;
-  }
   int total = p.m_tiles * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
-  obprop_tc_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmA, tmW, tmOut, p);
+  static bool attr_done[4] = {false, false, false, false};
+  auto launch = [&](auto kern, int id) -> int {
+    if (!attr_done[id]) {   // once per instantiation (and never inside a stream capture after warm-up)
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
+      attr_done[id] = true;
+    }
+    kern<<<grid, NTHREADS, smem_bytes, st>>>(tmA, tmW, tmOut, p);
+    return 0;
+  };
+  int rc;
+  const bool relu = a.relu != 0, rnd = a.round_out != 0;
+  if (perm && !a.gate && relu && !rnd) rc = launch(obprop_tc_kernel<true, false, true, false>, 0);        // layer 2 -> encoder input
+  else if (!perm && !a.gate && relu && rnd) rc = launch(obprop_tc_kernel<false, false, true, true>, 1);   // layer 1
+  else if (!perm && !a.gate && relu && !rnd) rc = launch(obprop_tc_kernel<false, false, true, false>, 2); // operator
+  else if (!perm && a.gate && !relu && !rnd) rc = launch(obprop_tc_kernel<false, true, false, false>, 3); // backward d(input)
+  else { set_error("obprop_tc_fwd: epilogue combination not instantiated"); return -2; }
+  if (rc != 0) return rc;
   RD_CHECK_LAUNCH("obprop_tc_kernel");
   return 0;
 }

@@ -35,6 +35,8 @@ struct P {
   const float* resid; long long resid_ld;
 };
 
+// epilogue features are compile-time: the epilogue is on the critical path of these small GEMMs
+template <bool RELU, bool GATE, bool DROP, bool RESID>
 __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmC, const P p) {
@@ -154,18 +156,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
             float x = __uint_as_float(v[4 * j4 + e]) + bs[4 * j4 + e];
-            o[e] = p.relu ? fmaxf(x, 0.f) : x;
+            o[e] = RELU ? fmaxf(x, 0.f) : x;
           }
-          if (p.gate && ok) {
+          if (GATE && ok) {
             float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + row * p.gate_ld + c));
             o[0] = g.x > 0.f ? o[0] * p.gate_scale : 0.f; o[1] = g.y > 0.f ? o[1] * p.gate_scale : 0.f;
             o[2] = g.z > 0.f ? o[2] * p.gate_scale : 0.f; o[3] = g.w > 0.f ? o[3] * p.gate_scale : 0.f;
           }
-          if (p.drop_p > 0.f && ok) {   // row*N + c is a multiple of 4: one Philox block for the four columns
+          if (DROP && ok) {   // row*N + c is a multiple of 4: one Philox block for the four columns
             const float4 m = dropout_scale4(p.rng, p.drop_site, (uint64_t)row * (uint64_t)p.N + (uint64_t)c, p.drop_p, ik);
             o[0] *= m.x; o[1] *= m.y; o[2] *= m.z; o[3] *= m.w;
           }
-          if (p.resid && ok) {
+          if (RESID && ok) {
             float4 r = __ldg(reinterpret_cast<const float4*>(p.resid + row * p.resid_ld + c));
             o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
           }
@@ -499,7 +501,9 @@ bool tc_gemm_supported(const TcGemmArgs& a) {
   if ((a.gate && a.gate_ld % 4) || (a.resid && a.resid_ld % 4)) return false;
   uintptr_t bits = reinterpret_cast<uintptr_t>(a.A) | reinterpret_cast<uintptr_t>(a.B) | reinterpret_cast<uintptr_t>(a.B_lo) |
                    reinterpret_cast<uintptr_t>(a.C) | reinterpret_cast<uintptr_t>(a.gate) | reinterpret_cast<uintptr_t>(a.resid);
-  return (bits & 15) == 0 && a.B_lo != nullptr;
+  const int id = (a.relu ? 8 : 0) | (a.gate ? 4 : 0) | (a.drop_p > 0.f ? 2 : 0) | (a.resid ? 1 : 0);
+  const bool combo = id == 0 || id == 1 || id == 2 || id == 3 || id == 4 || id == 8 || id == 10;
+  return combo && (bits & 15) == 0 && a.B_lo != nullptr;
 }
 
 int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
@@ -528,15 +532,31 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
   cuuint64_t cs[1] = {(cuuint64_t)a.N * 4};
   cuuint32_t cb[2] = {32, 32};
   RD_TRY(encode(&tmC, a.C, 2, cd, cs, cb, CU_TENSOR_MAP_SWIZZLE_128B, "C"));
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
-    attr_set = true;
-  }
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  tc_gemm_kernel<<<grid, NTHREADS, smem_bytes, st>>>(tmB, tmBlo, tmC, p);
+  static bool attr_done[16] = {};
+  auto launch = [&](auto kern, int id) -> int {
+    if (!attr_done[id]) {
+      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
+      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
+      attr_done[id] = true;
+    }
+    kern<<<grid, NTHREADS, smem_bytes, st>>>(tmB, tmBlo, tmC, p);
+    return 0;
+  };
+  const int id = (a.relu ? 8 : 0) | (a.gate ? 4 : 0) | (a.drop_p > 0.f ? 2 : 0) | (a.resid ? 1 : 0);
+  int rc = -2;
+  switch (id) {   // the combinations the encoder uses (forward: bias[,relu][,dropout][,residual]; backward: [gate][,residual])
+    case 0: rc = launch(tc_gemm_kernel<false, false, false, false>, id); break;
+    case 1: rc = launch(tc_gemm_kernel<false, false, false, true>, id); break;
+    case 2: rc = launch(tc_gemm_kernel<false, false, true, false>, id); break;
+    case 3: rc = launch(tc_gemm_kernel<false, false, true, true>, id); break;
+    case 4: rc = launch(tc_gemm_kernel<false, true, false, false>, id); break;
+    case 8: rc = launch(tc_gemm_kernel<true, false, false, false>, id); break;
+    case 10: rc = launch(tc_gemm_kernel<true, false, true, false>, id); break;
+    default: set_error("tc_gemm: epilogue combination %d not instantiated", id); return -2;
+  }
+  if (rc != 0) return rc;
   RD_CHECK_LAUNCH("tc_gemm_kernel");
   return 0;
 }
