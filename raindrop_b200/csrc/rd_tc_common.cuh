@@ -107,8 +107,31 @@ inline EncodeTiledFn get_encode() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled costs a few microseconds of host time; a training step re-encodes the same
+// ~90 maps every step (same buffers, same shapes), so keep them in a small direct-mapped cache.
+struct TmapKey {
+  const void* addr; int rank; int swizzle; cuuint64_t dims[4]; cuuint64_t strides[3]; cuuint32_t box[4];
+  bool operator==(const TmapKey& o) const {
+    if (addr != o.addr || rank != o.rank || swizzle != o.swizzle) return false;
+    for (int i = 0; i < 4; ++i) if (dims[i] != o.dims[i] || box[i] != o.box[i]) return false;
+    for (int i = 0; i < 3; ++i) if (strides[i] != o.strides[i]) return false;
+    return true;
+  }
+};
+struct TmapSlot { bool valid = false; TmapKey key; CUtensorMap map; };
+
 inline int encode(CUtensorMap* m, const void* addr, int rank, const cuuint64_t* dims, const cuuint64_t* strides_bytes,
-           const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what) {
+                  const cuuint32_t* box, CUtensorMapSwizzle sw, const char* what) {
+  constexpr int NSLOT = 512;
+  static thread_local TmapSlot cache[NSLOT];
+  TmapKey k{};
+  k.addr = addr; k.rank = rank; k.swizzle = (int)sw;
+  for (int i = 0; i < rank; ++i) { k.dims[i] = dims[i]; k.box[i] = box[i]; }
+  for (int i = 0; i + 1 < rank; ++i) k.strides[i] = strides_bytes[i];
+  uint64_t h = reinterpret_cast<uintptr_t>(addr) * 0x9E3779B97F4A7C15ull;
+  h ^= (dims[0] * 0xC2B2AE3D27D4EB4Full) ^ ((uint64_t)box[rank - 1] << 17) ^ (rank > 1 ? dims[1] * 0x165667B19E3779F9ull : 0);
+  TmapSlot& slot = cache[(h >> 40) % NSLOT];
+  if (slot.valid && slot.key == k) { *m = slot.map; return 0; }
   EncodeTiledFn fn = get_encode();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available from the driver"); return -3; }
   cuuint32_t es[5] = {1, 1, 1, 1, 1};
@@ -116,6 +139,7 @@ inline int encode(CUtensorMap* m, const void* addr, int rank, const cuuint64_t* 
                   box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(%s) failed: CUresult %d", what, (int)r); return -3; }
+  slot.valid = true; slot.key = k; slot.map = *m;
   return 0;
 }
 

@@ -220,7 +220,13 @@ class Raindrop_v2(nn.Module):
         super()._apply(fn, recurse)
         self.R_u = fn(self.R_u)       # moves with the module; the reference creates it on the GPU (:241)
         self.adj = fn(self.adj)
+        self.__dict__.pop("_used_params", None)
         return self
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.__dict__.pop("_used_params", None)      # `assign=True` may have replaced Parameter objects
+        return out
 
     # ---- host-side graph prologue, cached (code/models_rd.py:307-311) ---------------------------
     def _prepare(self, device):
@@ -247,8 +253,12 @@ class Raindrop_v2(nn.Module):
 
     def used_parameters(self):
         """The tensors that receive gradient, in flat-bucket order."""
-        sd = dict(self.named_parameters())
-        return [sd[k] for k, _ in self._plan.fields]
+        cached = self.__dict__.get("_used_params")
+        if cached is None:
+            sd = dict(self.named_parameters())
+            cached = [sd[k] for k, _ in self._plan.fields]
+            self.__dict__["_used_params"] = cached      # plain attribute: not a registered sub-module/parameter
+        return cached
 
     def forward(self, src, static, times, lengths):
         """src [T, B, 2*d_inp]; static [B, d_static] or None; times [T, B]; lengths [B] (int64).
