@@ -62,6 +62,15 @@ class Plan:
         self.owner = None           # weakref to the module (receives the flat gradient bucket)
 
     def dims(self, B, training):
+        key = (B, bool(training))
+        cache = self.__dict__.setdefault("_dims_cache", {})
+        d = cache.get(key)
+        if d is not None:
+            return d
+        d = cache[key] = self._make_dims(B, training)
+        return d
+
+    def _make_dims(self, B, training):
         d = L.RdDims()
         d.B, d.T, d.N, d.d_ob = B, self.T, self.N, self.d_ob
         d.nhead, d.nhid, d.nlayers = self.nhead, self.nhid, self.nlayers
@@ -93,15 +102,23 @@ class RaindropV2Function(torch.autograd.Function):
         if T != plan.T or src.shape[2] != 2 * plan.N:
             raise ValueError("src must be [max_len=%d, B, 2*d_inp=%d], got %s" % (plan.T, 2 * plan.N, tuple(src.shape)))
         dims = plan.dims(B, training)
-        P = L.RdParams()
-        P.R_u = plan.R_u.data_ptr()
-        keep = []
-        for (key, path), t in zip(plan.fields, params):
-            if t.dtype != torch.float32 or not t.is_contiguous():
-                t = _as_f32(t)
-            keep.append(t)
-            _set_field(P, path, t.data_ptr())
-        ws_bytes = lib.rd_workspace_bytes(C.byref(dims))
+        keep = [t if (t.dtype == torch.float32 and t.is_contiguous()) else _as_f32(t) for t in params]
+        ptrs = (plan.R_u.data_ptr(),) + tuple(t.data_ptr() for t in keep)
+        cached = plan.__dict__.get("_param_struct")
+        if cached is not None and cached[0] == ptrs:
+            P = cached[1]
+        else:
+            P = L.RdParams()
+            P.R_u = ptrs[0]
+            for (key, path), ptr_ in zip(plan.fields, ptrs[1:]):
+                _set_field(P, path, ptr_)
+            plan.__dict__["_param_struct"] = (ptrs, P)
+        sizes = plan.__dict__.setdefault("_ws_bytes", {})
+        ws_bytes = sizes.get((B, bool(training)))
+        if ws_bytes is None:
+            ws_bytes = sizes[(B, bool(training))] = (lib.rd_workspace_bytes(C.byref(dims)),
+                                                     lib.rd_backward_scratch_bytes(C.byref(dims)))
+        ws_bytes, sc_bytes = ws_bytes
         if ws_bytes == 0:
             L.check(-2, "rd_workspace_bytes")
         ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=src.device)
@@ -113,7 +130,7 @@ class RaindropV2Function(torch.autograd.Function):
         L.check(rc, "rd_raindrop_v2_fwd")
         ctx.plan, ctx.dims, ctx.P, ctx.ws = plan, dims, P, ws
         ctx.keep = (keep, static, lengths, plan.node_scale, plan.R_u)
-        ctx.shapes = [tuple(t.shape) for t in params]
+        ctx.sc_bytes = sc_bytes
         plan.last_workspace = ws
         plan.last_dims = dims
         return logits
@@ -125,26 +142,31 @@ class RaindropV2Function(torch.autograd.Function):
         keep, static, lengths, node_scale, _ = ctx.keep
         d_logits = _as_f32(d_logits)
         dev = d_logits.device
-        offs, total = [], 0
-        for shp in ctx.shapes:
-            n = int(np.prod(shp))
-            offs.append(total)
-            total += (n + 3) // 4 * 4
+        params = keep
+        layout = plan.__dict__.get("_grad_layout")
+        if layout is None:      # tightly packed flat bucket, one offset per used parameter
+            offs, total = [], 0
+            for t in params:
+                offs.append(total)
+                total += t.numel()
+            layout = plan.__dict__["_grad_layout"] = (offs, total)
+        offs, total = layout
         flat = torch.empty(total, dtype=torch.float32, device=dev)
-        G = L.RdGrads()
         base = flat.data_ptr()
-        for (key, path), off in zip(plan.fields, offs):
-            _set_field(G, path, base + 4 * off)
-        sc_bytes = lib.rd_backward_scratch_bytes(C.byref(dims))
-        scratch = torch.empty(sc_bytes // 4, dtype=torch.float32, device=dev)
+        cachedG = plan.__dict__.get("_grad_struct")
+        if cachedG is not None and cachedG[0] == base:
+            G = cachedG[1]
+        else:
+            G = L.RdGrads()
+            for (key, path), off in zip(plan.fields, offs):
+                _set_field(G, path, base + 4 * off)
+            plan.__dict__["_grad_struct"] = (base, G)
+        scratch = torch.empty(ctx.sc_bytes // 4, dtype=torch.float32, device=dev)
         rc = lib.rd_raindrop_v2_bwd(C.byref(dims), C.byref(ctx.P), L.ptr(static), lengths.data_ptr(),
                                     node_scale.data_ptr(), ctx.ws.data_ptr(), d_logits.data_ptr(), C.byref(G),
                                     scratch.data_ptr(), L.stream_ptr())
         L.check(rc, "rd_raindrop_v2_bwd")
-        grads = []
-        for shp, off in zip(ctx.shapes, offs):
-            n = int(np.prod(shp))
-            grads.append(flat[off:off + n].view(shp))
+        grads = torch._utils._unflatten_dense_tensors(flat, params)      # views, one C++ call
         owner = plan.owner() if plan.owner is not None else None
         if owner is not None:
             owner._flat_grad = flat          # the DDP bucket: one all-reduce covers every gradient
