@@ -198,6 +198,13 @@ int rd_transformer_conv_fwd(const float* x, int32_t n_nodes, int32_t in_ch, int3
                             const float* ws, const float* bs, float* out, float* alpha,
                             void* scratch, void* stream);
 
+/* ---- device-side batch assembly ---------------------------------------------------
+ * out[t, j, :] = src[t, idx[j], :] for t < T, j < B: selects a batch out of a training set that stays
+ * resident in HBM, replacing the host-side `Ptrain_tensor[:, idx, :].cuda()` copies of
+ * code/Raindrop.py:311-315 (T = 1 for the [n, d_static] statics and labels viewed as float rows). */
+int rd_gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_total, int32_t width, int32_t B,
+                    float* out, void* stream);
+
 /* ---- training-step helpers (the caller-side ops of code/Raindrop.py:321-324) ----------------
  * mean cross entropy + d(loss)/d(logits), torch.nn.CrossEntropyLoss semantics. */
 int rd_cross_entropy_fwd_bwd(const float* logits, const int64_t* y, int32_t B, int32_t n_classes,

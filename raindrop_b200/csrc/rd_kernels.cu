@@ -57,6 +57,22 @@ __global__ void transpose_round_kernel(const float* __restrict__ x, int rows, in
   }
 }
 
+// out[t, j, :] = src[t, idx[j], :]  (rows of `width` floats; 128-bit copies when width % 4 == 0)
+__global__ void gather_batch_kernel(const float* __restrict__ src, const int64_t* __restrict__ idx, long long T,
+                                    long long n_total, int width, int B, float* __restrict__ out) {
+  const int vec = (width & 3) == 0 ? 4 : 1;
+  const long long per_row = width / vec;
+  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= T * B * per_row) return;
+  const long long c = o % per_row, tj = o / per_row, j = tj % B, t = tj / B;
+  const long long s = idx[j];
+  if (s < 0 || s >= n_total) return;                      // out-of-range indices leave the row untouched
+  const float* in = src + (t * n_total + s) * width;
+  float* dst = out + (t * B + j) * width;
+  if (vec == 4) reinterpret_cast<float4*>(dst)[c] = __ldg(reinterpret_cast<const float4*>(in) + c);
+  else dst[c] = __ldg(in + c);
+}
+
 __global__ void rng_capture_kernel(uint64_t* state, uint64_t* cap, int advance) {
   cap[0] = state[0];
   cap[1] = state[1];
@@ -403,6 +419,19 @@ int transpose_round(const float* x, int rows, int cols, float* y, cudaStream_t s
   dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32));
   transpose_round_kernel<<<grid, dim3(32, 8), 0, st>>>(x, rows, cols, y);
   RD_CHECK_LAUNCH("transpose_round_kernel");
+  return 0;
+}
+
+int gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_total, int width, int B, float* out,
+                 cudaStream_t st) {
+  if ((width & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+    set_error("gather_batch: 16-byte aligned buffers required when width %% 4 == 0");
+    return -2;
+  }
+  const int64_t n = T * B * (int64_t)(width / ((width & 3) == 0 ? 4 : 1));
+  if (n <= 0) return 0;
+  gather_batch_kernel<<<blocks_for(n), TPB, 0, st>>>(src, idx, T, n_total, width, B, out);
+  RD_CHECK_LAUNCH("gather_batch_kernel");
   return 0;
 }
 

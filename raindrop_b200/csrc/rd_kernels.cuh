@@ -4,6 +4,10 @@
 
 namespace rd {
 
+// out[t, j, :] = src[t, idx[j], :] for a device-resident training set (code/Raindrop.py:311-315 does this on the host)
+int gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_total, int width, int B, float* out,
+                 cudaStream_t st);
+
 int rng_capture(uint64_t* rng_state, uint64_t* captured, int advance, cudaStream_t st);
 
 // X0[(b*N+n), t*d_ob+k] = dropout(relu(src[t,b,n] * R_u[n*d_ob+k]))    code/models_rd.py:285-296,323-327

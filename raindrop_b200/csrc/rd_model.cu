@@ -594,6 +594,12 @@ int rd_positional_encoding(const float* times, int64_t n_tokens, const float* ti
   return posenc(times, n_tokens, timescales_host, out, ld, col0, (cudaStream_t)stream);
 }
 
+int rd_gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_total, int32_t width, int32_t B, float* out,
+                    void* stream) {
+  if (!src || !idx || !out || T < 0 || n_total < 1 || width < 1 || B < 0) { set_error("rd_gather_batch: bad arguments"); return -2; }
+  return gather_batch(src, idx, T, n_total, width, B, out, (cudaStream_t)stream);
+}
+
 int rd_cross_entropy_fwd_bwd(const float* logits, const int64_t* y, int32_t B, int32_t ncls, float* loss,
                              float* d_logits, void* stream) {
   if (!logits || !y || !loss || B < 1 || ncls < 1) { set_error("rd_cross_entropy_fwd_bwd: bad arguments"); return -2; }

@@ -309,6 +309,25 @@ def test_transformer_conv(golden_dir):
         assert normwise(alpha, z[tag + "alpha"]) < 1e-5
 
 
+def test_device_dataset_gather_is_bit_exact():
+    """rd_gather_batch == torch indexing of the host tensors (index work: bit exact), incl. odd widths."""
+    from raindrop_b200.train import DeviceDataset, TrainStep
+    cfg = model_config("P19", dropout=0.0)
+    full = make_batch(cfg, 300, seed=4)
+    ds = DeviceDataset(full["src"], full["static"], full["times"], full["y"], "cuda")
+    ts = TrainStep(build_dropin(cfg, 2).train(), 64, use_graph=False)
+    idx = torch.randperm(300, generator=torch.Generator().manual_seed(1))[:64]
+    ds.fill(ts, idx)
+    assert torch.equal(ts.src.cpu(), full["src"][:, idx])
+    assert torch.equal(ts.times.cpu(), full["times"][:, idx])
+    assert torch.equal(ts.static.cpu(), full["static"][idx])
+    assert torch.equal(ts.y.cpu(), full["y"][idx]) and torch.equal(ts.lengths.cpu(), full["lengths"][idx])
+    l0 = ts.step().item()
+    ts2 = TrainStep(build_dropin(cfg, 2).train(), 64, use_graph=False)
+    ts2.load_batch(to_dev({k: (v[:, idx] if k in ("src", "times") else v[idx]) for k, v in full.items()}))
+    assert ts2.step().item() == l0
+
+
 def test_cross_entropy_and_adam():
     import ctypes as C
     from raindrop_b200 import lib as L
