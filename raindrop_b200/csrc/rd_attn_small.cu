@@ -37,9 +37,10 @@ __device__ __forceinline__ void load_head(const float* __restrict__ src, long lo
     const int nvec = hd >> 2;
     float4 v[6];
     int tt[6], cc[6];
+    const int nthr = blockDim.x;
 #pragma unroll
     for (int k = 0; k < 6; ++k) {
-      const int idx = threadIdx.x + k * NT;
+      const int idx = threadIdx.x + k * nthr;     // 6 x blockDim >= 64 * 24 float4 for both CTA sizes
       tt[k] = idx / nvec; cc[k] = idx - tt[k] * nvec;
       v[k] = (tt[k] < T) ? __ldg(reinterpret_cast<const float4*>(src + (long long)tt[k] * row_stride + 4 * cc[k]))
                          : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -54,7 +55,7 @@ __device__ __forceinline__ void load_head(const float* __restrict__ src, long lo
       }
     }
   } else {
-    for (int idx = threadIdx.x; idx < TM * hd; idx += NT) {
+    for (int idx = threadIdx.x; idx < TM * hd; idx += blockDim.x) {
       const int t = idx / hd, d = idx - t * hd;
       const float x = t < T ? __ldg(src + (long long)t * row_stride + d) : 0.f;
       if (rm) rm[t * LDR + d] = x;
@@ -63,7 +64,7 @@ __device__ __forceinline__ void load_head(const float* __restrict__ src, long lo
   }
   if (rm) {   // zero the padding columns hd..95 (read by the 6-column register tiles)
     const int npad = HDM - hd;
-    for (int idx = threadIdx.x; idx < TM * npad; idx += NT) {
+    for (int idx = threadIdx.x; idx < TM * npad; idx += blockDim.x) {
       const int t = idx / npad, d = hd + idx - t * npad;
       rm[t * LDR + d] = 0.f;
     }
@@ -71,14 +72,18 @@ __device__ __forceinline__ void load_head(const float* __restrict__ src, long lo
 }
 
 // out[i][j] = alpha * sum_d At[d][i] * Bt[d][j]   (both operands transposed in smem: 2 LDS.128 per 16 FMA)
+// With 512 threads the reduction range is split between the two 256-thread groups (group 1 adds its
+// partial into `out` after a barrier): twice the warps per SM to hide shared-memory latency.
 __device__ __forceinline__ void gemm_tt(const float* At, const float* Bt, int hd, float alpha, float* out) {
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int t256 = threadIdx.x & 255, grp = threadIdx.x >> 8, ngrp = blockDim.x >> 8;
+  const int tx = t256 & 15, ty = t256 >> 4;
   float acc[4][4];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 4; ++c) acc[r][c] = 0.f;
-  for (int d = 0; d < hd; ++d) {
+  const int d0 = grp * ((hd + ngrp - 1) / ngrp), d1 = min(hd, d0 + (hd + ngrp - 1) / ngrp);
+  for (int d = d0; d < d1; ++d) {
     const float4 a = *reinterpret_cast<const float4*>(At + d * LDT + 4 * ty);
     const float4 b = *reinterpret_cast<const float4*>(Bt + d * LDT + 4 * tx);
     const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
@@ -87,10 +92,24 @@ __device__ __forceinline__ void gemm_tt(const float* At, const float* Bt, int hd
 #pragma unroll
       for (int c = 0; c < 4; ++c) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
   }
+  if (grp == 0) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r)
-    *reinterpret_cast<float4*>(out + (4 * ty + r) * LDT + 4 * tx) =
-        make_float4(acc[r][0] * alpha, acc[r][1] * alpha, acc[r][2] * alpha, acc[r][3] * alpha);
+    for (int r = 0; r < 4; ++r)
+      *reinterpret_cast<float4*>(out + (4 * ty + r) * LDT + 4 * tx) =
+          make_float4(acc[r][0] * alpha, acc[r][1] * alpha, acc[r][2] * alpha, acc[r][3] * alpha);
+  }
+  if (ngrp > 1) {
+    __syncthreads();
+    if (grp == 1) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) {
+        float4* o = reinterpret_cast<float4*>(out + (4 * ty + r) * LDT + 4 * tx);
+        float4 v = *o;
+        v.x += acc[r][0] * alpha; v.y += acc[r][1] * alpha; v.z += acc[r][2] * alpha; v.w += acc[r][3] * alpha;
+        *o = v;
+      }
+    }
+  }
 }
 
 // key-padding-masked softmax of the rows of Ps (in place -> probabilities); the dropped copy goes to
@@ -101,7 +120,7 @@ __device__ __forceinline__ void softmax_rows(const AttnP& p, int b, int h, float
   const int nv = (int)(len < T ? (len < 0 ? 0 : len) : T);
   const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = warp; i < TM; i += NT / 32) {
+  for (int i = warp; i < TM; i += (int)(blockDim.x >> 5)) {
     float* row = Ps + i * LDT;
     float v0 = (i < T && lane < nv) ? row[lane] : -INFINITY, v1 = (i < T && lane + 32 < nv) ? row[lane + 32] : -INFINITY;
     float mx = warp_max(fmaxf(v0, v1));
@@ -169,7 +188,8 @@ __global__ void __launch_bounds__(NT) attn_small_fwd_kernel(AttnP p) {
   }
 }
 
-__global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnP p) {
+constexpr int NTB = 512;   // backward: two 256-thread groups split every reduction
+__global__ void __launch_bounds__(NTB) attn_small_bwd_kernel(AttnP p) {
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
   float* Qs = sm; float* Ks = Qs + TM * LDR; float* Gs = Ks + TM * LDR;             // row-major Q, K, d(ctx)
@@ -195,7 +215,7 @@ __global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnP p) {
   {  // dS = P * (dP - rowsum(dP * P)), dP = dPd * mask/(1-p); written row-major and transposed
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    for (int i = warp; i < TM; i += NT / 32) {
+    for (int i = warp; i < TM; i += NTB / 32) {
       const uint64_t ibase = ((uint64_t)(b * p.H + h) * p.T + i) * p.T;
       float dp[2], pr[2];
       float dot = 0.f;
@@ -220,13 +240,16 @@ __global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnP p) {
   }
   __syncthreads();
   // dQ[i, d] = scale * sum_j dS[i, j] K[j, d];  dK[j', d] = scale * sum_i dS[i, j'] Q[i, d];  dV[j', d] = sum_i Pd[i, j'] G[i, d]
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int t256 = threadIdx.x & 255, grp = threadIdx.x >> 8;
+  const int tx = t256 & 15, ty = t256 >> 4;
   float aq[4][6], ak[4][6], av[4][6];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 6; ++c) { aq[r][c] = 0.f; ak[r][c] = 0.f; av[r][c] = 0.f; }
-  for (int j = 0; j < p.T; ++j) {
+  const int jh = (p.T + 1) >> 1;
+  const int j0 = grp * jh, j1 = min(p.T, j0 + jh);        // each group reduces over half of the sequence
+  for (int j = j0; j < j1; ++j) {
     const float4 s4 = *reinterpret_cast<const float4*>(dST + j * LDT + 4 * ty);   // dS[i = 4ty.., j]
     const float4 t4 = *reinterpret_cast<const float4*>(dS + j * LDT + 4 * ty);    // dS[i = j, j' = 4ty..]
     const float4 q4 = *reinterpret_cast<const float4*>(Pd + j * LDT + 4 * ty);    // Pd[i = j, j' = 4ty..]
@@ -248,15 +271,31 @@ __global__ void __launch_bounds__(NT) attn_small_bwd_kernel(AttnP p) {
         av[r][c] = fmaf(p_col[r], gg[c], av[r][c]);
       }
   }
+  __syncthreads();                                          // all reads of Qs / Ks / Gs are done: reuse them
+  if (grp == 1) {                                           // group 1 parks its partial sums in shared memory ...
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i = 4 * ty + r;
-    if (i >= p.T) continue;
-    float* o = p.dqkv + ((long long)i * p.B + b) * 3 * p.D + h * p.hd;
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      const int d = 6 * tx + c;
-      if (d < p.hd) { o[d] = aq[r][c] * p.scale; o[p.D + d] = ak[r][c] * p.scale; o[2 * p.D + d] = av[r][c]; }
+      for (int c = 0; c < 6; ++c) {
+        const int o = (4 * ty + r) * LDR + 6 * tx + c;
+        Qs[o] = aq[r][c]; Ks[o] = ak[r][c]; Gs[o] = av[r][c];
+      }
+  }
+  __syncthreads();
+  if (grp == 0) {                                           // ... group 0 adds them (fixed order) and writes dqkv
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = 4 * ty + r;
+      if (i >= p.T) continue;
+      float* o = p.dqkv + ((long long)i * p.B + b) * 3 * p.D + h * p.hd;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int d = 6 * tx + c;
+        const int so = i * LDR + d;
+        if (d < p.hd) {
+          o[d] = (aq[r][c] + Qs[so]) * p.scale; o[p.D + d] = (ak[r][c] + Ks[so]) * p.scale; o[2 * p.D + d] = av[r][c] + Gs[so];
+        }
+      }
     }
   }
 }
@@ -293,7 +332,7 @@ int attn_small_bwd(const float* qkv, const float* dctx, const int64_t* lengths, 
   AttnP p{};
   p.qkv = qkv; p.dctx = dctx; p.dqkv = dqkv; p.lengths = lengths; p.B = B; p.H = H; p.T = T; p.hd = hd; p.D = H * hd;
   p.scale = 1.f / sqrtf((float)hd); p.drop_p = drop_p; p.rng = rng; p.site = site;
-  attn_small_bwd_kernel<<<B * H, NT, bwd_smem(hd), st>>>(p);
+  attn_small_bwd_kernel<<<B * H, NTB, bwd_smem(hd), st>>>(p);
   RD_CHECK_LAUNCH("attn_small_bwd_kernel");
   return 0;
 }
