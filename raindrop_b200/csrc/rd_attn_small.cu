@@ -15,7 +15,6 @@ namespace {
 
 constexpr int TM = 64;      // max sequence length
 constexpr int HDM = 96;     // max head dim (6 columns per thread x 16 threads)
-constexpr int NT = 256;
 constexpr int LDR = 100;    // row-major [t][d] stride (d < 96 zero padded; even -> float2 reads of 6 contiguous columns)
 constexpr int LDT = 68;     // transposed [d][t] / [j][i] stride (multiple of 4 -> float4 reads of 4 contiguous rows)
 
@@ -139,7 +138,7 @@ __device__ __forceinline__ void softmax_rows(const AttnP& p, int b, int h, float
   }
 }
 
-__global__ void __launch_bounds__(NT) attn_small_fwd_kernel(AttnP p) {
+__global__ void __launch_bounds__(512) attn_small_fwd_kernel(AttnP p) {
   extern __shared__ __align__(16) float sm[];
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
   float* Qt = sm; float* Kt = Qt + HDM * LDT; float* Vs = Kt + HDM * LDT;
@@ -155,14 +154,18 @@ __global__ void __launch_bounds__(NT) attn_small_fwd_kernel(AttnP p) {
   __syncthreads();
   softmax_rows(p, b, h, Ps, PdT, 1, LDT);      // dropped probabilities transposed: PdT[j][i]
   __syncthreads();
-  // ctx[i, d] = sum_j Pd[i, j] V[j, d]; thread tile 4 rows x 6 contiguous columns
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  // ctx[i, d] = sum_j Pd[i, j] V[j, d]; thread tile 4 rows x 6 contiguous columns; the two 256-thread groups
+  // each reduce over half of the keys, group 1 parks its partial in shared memory, group 0 adds and stores
+  const int t256 = threadIdx.x & 255, grp = threadIdx.x >> 8;
+  const int tx = t256 & 15, ty = t256 >> 4;
   float acc[4][6];
 #pragma unroll
   for (int r = 0; r < 4; ++r)
 #pragma unroll
     for (int c = 0; c < 6; ++c) acc[r][c] = 0.f;
-  for (int j = 0; j < p.T; ++j) {
+  const int jh = (p.T + 1) >> 1;
+  const int j0 = grp * jh, j1 = min(p.T, j0 + jh);
+  for (int j = j0; j < j1; ++j) {
     const float4 p4 = *reinterpret_cast<const float4*>(PdT + j * LDT + 4 * ty);
     const float pv[4] = {p4.x, p4.y, p4.z, p4.w};
     float vv[6];
@@ -176,14 +179,24 @@ __global__ void __launch_bounds__(NT) attn_small_fwd_kernel(AttnP p) {
 #pragma unroll
       for (int c = 0; c < 6; ++c) acc[r][c] = fmaf(pv[r], vv[c], acc[r][c]);
   }
+  float* park = Qt;                       // Q^T / K^T are dead after the scores: 64 x LDR floats fit in Q^T + K^T
+  if (grp == 1) {
 #pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    const int i = 4 * ty + r;
-    if (i >= p.T) continue;
+    for (int r = 0; r < 4; ++r)
 #pragma unroll
-    for (int c = 0; c < 6; ++c) {
-      const int d = 6 * tx + c;
-      if (d < p.hd) p.ctx[((long long)i * p.B + b) * p.D + h * p.hd + d] = acc[r][c];
+      for (int c = 0; c < 6; ++c) park[(4 * ty + r) * LDR + 6 * tx + c] = acc[r][c];
+  }
+  __syncthreads();
+  if (grp == 0) {
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int i = 4 * ty + r;
+      if (i >= p.T) continue;
+#pragma unroll
+      for (int c = 0; c < 6; ++c) {
+        const int d = 6 * tx + c;
+        if (d < p.hd) p.ctx[((long long)i * p.B + b) * p.D + h * p.hd + d] = acc[r][c] + park[i * LDR + d];
+      }
     }
   }
 }
@@ -322,7 +335,7 @@ int attn_small_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T
     cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(HDM));
     attr = true;
   }
-  attn_small_fwd_kernel<<<B * H, NT, fwd_smem(hd), st>>>(p);
+  attn_small_fwd_kernel<<<B * H, 512, fwd_smem(hd), st>>>(p);
   RD_CHECK_LAUNCH("attn_small_fwd_kernel");
   return 0;
 }

@@ -154,6 +154,82 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
   if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
 }
 
+// LayerNorm backward, one pass over (x, dy): every warp walks LNB_ROWS/8 rows, writes dx (and the
+// dropout-masked copy the sub-layer's weight gradient needs) and keeps per-lane column sums of
+// dy*xhat / dy in registers; the 8 warps of a CTA combine them through shared memory into one
+// partial row [2][D] per CTA (summed later in a fixed order).  128-bit accesses (D % 4 == 0).
+constexpr int LNB_ROWS = 64;    // rows per CTA
+constexpr int LNB_MAXIT = 5;    // D <= 640
+__global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(
+    const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
+    const float* __restrict__ dy, long long rows, int D, float* __restrict__ dx, float* __restrict__ dx_drop,
+    float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial) {
+  extern __shared__ float lsm[];                     // [8 warps][2][D]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  float4 ag[LNB_MAXIT], ab[LNB_MAXIT];
+#pragma unroll
+  for (int it = 0; it < LNB_MAXIT; ++it) { ag[it] = make_float4(0.f, 0.f, 0.f, 0.f); ab[it] = ag[it]; }
+  const long long r0 = (long long)blockIdx.x * LNB_ROWS;
+  for (int rr = warp; rr < LNB_ROWS; rr += 8) {
+    const long long row = r0 + rr;
+    if (row >= rows) break;
+    const float* xr = x + row * D;
+    const float* dyr = dy + row * D;
+    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
+    float4 d4[LNB_MAXIT], xh[LNB_MAXIT], g4[LNB_MAXIT];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int it = 0; it < LNB_MAXIT; ++it) {
+      const int j = 4 * lane + 128 * it;
+      if (j < D) {
+        d4[it] = *reinterpret_cast<const float4*>(dyr + j);
+        const float4 x4 = *reinterpret_cast<const float4*>(xr + j);
+        g4[it] = __ldg(reinterpret_cast<const float4*>(gamma + j));
+        xh[it] = make_float4((x4.x - mean) * rstd, (x4.y - mean) * rstd, (x4.z - mean) * rstd, (x4.w - mean) * rstd);
+        s1 += d4[it].x * g4[it].x + d4[it].y * g4[it].y + d4[it].z * g4[it].z + d4[it].w * g4[it].w;
+        s2 += d4[it].x * g4[it].x * xh[it].x + d4[it].y * g4[it].y * xh[it].y + d4[it].z * g4[it].z * xh[it].z +
+              d4[it].w * g4[it].w * xh[it].w;
+      }
+    }
+    s1 = warp_sum(s1) / (float)D;
+    s2 = warp_sum(s2) / (float)D;
+#pragma unroll
+    for (int it = 0; it < LNB_MAXIT; ++it) {
+      const int j = 4 * lane + 128 * it;
+      if (j < D) {
+        float4 o;
+        o.x = rstd * (d4[it].x * g4[it].x - s1 - xh[it].x * s2);
+        o.y = rstd * (d4[it].y * g4[it].y - s1 - xh[it].y * s2);
+        o.z = rstd * (d4[it].z * g4[it].z - s1 - xh[it].z * s2);
+        o.w = rstd * (d4[it].w * g4[it].w - s1 - xh[it].w * s2);
+        *reinterpret_cast<float4*>(dx + row * D + j) = o;
+        if (dx_drop) {
+          const float4 m = dropout_scale4(rng, site, (uint64_t)row * D + j, drop_p, ik);
+          *reinterpret_cast<float4*>(dx_drop + row * D + j) = make_float4(o.x * m.x, o.y * m.y, o.z * m.z, o.w * m.w);
+        }
+        ag[it].x += d4[it].x * xh[it].x; ag[it].y += d4[it].y * xh[it].y; ag[it].z += d4[it].z * xh[it].z; ag[it].w += d4[it].w * xh[it].w;
+        ab[it].x += d4[it].x; ab[it].y += d4[it].y; ab[it].z += d4[it].z; ab[it].w += d4[it].w;
+      }
+    }
+  }
+#pragma unroll
+  for (int it = 0; it < LNB_MAXIT; ++it) {
+    const int j = 4 * lane + 128 * it;
+    if (j < D) {
+      *reinterpret_cast<float4*>(lsm + (warp * 2) * D + j) = ag[it];
+      *reinterpret_cast<float4*>(lsm + (warp * 2 + 1) * D + j) = ab[it];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += lsm[w * 2 * D + c];     // c < D: dgamma column, else dbeta column
+    partial[(long long)blockIdx.x * 2 * D + c] = s;
+  }
+}
+
 __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ stats,
                                         const float* __restrict__ gamma, const float* __restrict__ dy,
                                         long long rows, int D, float* __restrict__ dx, float* __restrict__ dx_drop,
@@ -465,11 +541,23 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t
   return 0;
 }
 
-int64_t ln_bwd_scratch_floats(int64_t rows, int D) { return ceil_div(rows, LN_ROWS) * 2 * D; }
+int64_t ln_bwd_scratch_floats(int64_t rows, int D) {
+  int64_t a = ceil_div(rows, LN_ROWS), b = ceil_div(rows, LNB_ROWS);
+  return (a > b ? a : b) * 2 * D;
+}
 
 int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows, int D,
                   float* dx, float* dgamma, float* dbeta, float* scratch, float* dx_drop, float drop_p,
                   const uint64_t* rng, uint32_t site, cudaStream_t st) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
+                         reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_drop);
+  if ((D & 3) == 0 && D <= 128 * LNB_MAXIT && (bits & 15) == 0) {     // fused single pass
+    const int chunks = (int)ceil_div(rows, LNB_ROWS);
+    layernorm_bwd_fused_kernel<<<chunks, 256, 8 * 2 * D * sizeof(float), st>>>(
+        x, stats, gamma, dy, rows, D, dx, drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site, scratch);
+    RD_CHECK_LAUNCH("layernorm_bwd_fused_kernel");
+    return reduce_partials2(scratch, chunks, D, dgamma, D, dbeta, st);
+  }
   layernorm_bwd_dx_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, stats, gamma, dy, rows, D, dx,
                                                               drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site);
   RD_CHECK_LAUNCH("layernorm_bwd_dx_kernel");

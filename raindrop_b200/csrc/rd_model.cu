@@ -49,7 +49,7 @@ struct Arena {
 };
 
 struct WsLayout {
-  int64_t rng, X0, H1, W1r, W2r, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
+  int64_t rng, X0, H1, W1r, W2r, W2t, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
   struct { int64_t qkv, P, Pd, ctx, r1, st1, x1, f, r2, st2; } l[RD_MAX_LAYERS];
   // error-compensation remainders and transposes of the encoder weights (rd_tc_gemm.cuh)
   struct { int64_t in_lo, in_t, in_tlo, out_lo, out_t, out_tlo, l1_lo, l1_t, l1_tlo, l2_lo, l2_t, l2_tlo; } wsp[RD_MAX_LAYERS];
@@ -63,6 +63,7 @@ WsLayout ws_layout(const Shape& s) {
   w.H1 = a.take(s.M1 * s.C);
   w.W1r = a.take((int64_t)s.C * s.C);   // TF32-rounded copies of the two lin_value weights
   w.W2r = a.take((int64_t)s.C * s.C);
+  w.W2t = a.take((int64_t)s.C * s.C);   // rounded W2^T for the backward d(input) GEMM
   for (int i = 0; i <= s.L; ++i) w.Z[i] = a.take(s.M2 * s.D);
   int64_t pp = (int64_t)s.B * s.H * s.T * s.T;
   for (int i = 0; i < s.L; ++i) {
@@ -214,10 +215,22 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
   // epilogue, rounded weight copies) so the MMA's operand truncation is exact.
   const int tc = obprop_tc_supported(s.C) ? 1 : 0;
   const float* W1 = P->ob1_value_weight; const float* W2 = P->ob2_value_weight;
-  if (tc) {
-    RD_TRY(round_tf32(W1, (int64_t)s.C * s.C, ws + w.W1r, st));
-    RD_TRY(round_tf32(W2, (int64_t)s.C * s.C, ws + w.W2r, st));
-    W1 = ws + w.W1r; W2 = ws + w.W2r;
+  if (tc) { W1 = ws + w.W1r; W2 = ws + w.W2r; }   // rounded copies, produced by the weight-prep launch just below
+  for (int l0 = 0; l0 < s.L; l0 += 3) {   // every derived weight tensor of the step in one launch (<= 16 tensors each)
+    WeightSplit items[16];
+    int n = 0;
+    if (l0 == 0 && tc) {
+      items[n] = {P->ob1_value_weight, s.C, s.C, nullptr, nullptr, nullptr}; items[n++].rn = ws + w.W1r;
+      items[n] = {P->ob2_value_weight, s.C, s.C, nullptr, nullptr, nullptr}; items[n].rn = ws + w.W2r; items[n++].rn_t = ws + w.W2t;
+    }
+    for (int l = l0; l < s.L && l < l0 + 3; ++l) {
+      const rd_encoder_layer_params& E = P->layer[l];
+      items[n++] = {E.in_proj_weight, 3 * s.D, s.D, ws + w.wsp[l].in_lo, ws + w.wsp[l].in_t, ws + w.wsp[l].in_tlo};
+      items[n++] = {E.out_proj_weight, s.D, s.D, ws + w.wsp[l].out_lo, ws + w.wsp[l].out_t, ws + w.wsp[l].out_tlo};
+      items[n++] = {E.linear1_weight, s.nhid, s.D, ws + w.wsp[l].l1_lo, ws + w.wsp[l].l1_t, ws + w.wsp[l].l1_tlo};
+      items[n++] = {E.linear2_weight, s.D, s.nhid, ws + w.wsp[l].l2_lo, ws + w.wsp[l].l2_t, ws + w.wsp[l].l2_tlo};
+    }
+    RD_TRY(split_weights(items, n, st));
   }
   RD_TRY(lift(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, tc, X0, st));
   float* Z0 = ws + w.Z[0];
@@ -232,18 +245,6 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
   }
   RD_TRY(posenc(times, s.M2, dims->pe_timescales, Z0, s.D, s.Dm, st));
 
-  for (int l0 = 0; l0 < s.L; l0 += 4) {   // remainders + transposes of the encoder weights, <= 16 tensors per launch
-    WeightSplit items[16];
-    int n = 0;
-    for (int l = l0; l < s.L && l < l0 + 4; ++l) {
-      const rd_encoder_layer_params& E = P->layer[l];
-      items[n++] = {E.in_proj_weight, 3 * s.D, s.D, ws + w.wsp[l].in_lo, ws + w.wsp[l].in_t, ws + w.wsp[l].in_tlo};
-      items[n++] = {E.out_proj_weight, s.D, s.D, ws + w.wsp[l].out_lo, ws + w.wsp[l].out_t, ws + w.wsp[l].out_tlo};
-      items[n++] = {E.linear1_weight, s.nhid, s.D, ws + w.wsp[l].l1_lo, ws + w.wsp[l].l1_t, ws + w.wsp[l].l1_tlo};
-      items[n++] = {E.linear2_weight, s.D, s.nhid, ws + w.wsp[l].l2_lo, ws + w.wsp[l].l2_t, ws + w.wsp[l].l2_tlo};
-    }
-    RD_TRY(split_weights(items, n, st));
-  }
   const float scale = 1.f / sqrtf((float)s.hd);
   const int64_t row3 = (int64_t)s.B * 3 * s.D;
   const int64_t TT = (int64_t)s.T * s.T;
@@ -436,8 +437,7 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
   RD_TRY(tn(gO2, s.C, H1, s.C, G->ob2_value_weight, G->ob2_value_bias, s.C, s.C, s.M1, partial, st));
   if (tc) {
     // dZ1 = (dZ2 . W2) * s * [H1 > 0] on the tensor cores: "NT" form against a transposed, TF32-rounded W2
-    float* W2t = sc + b.W2t;
-    RD_TRY(transpose_round(P->ob2_value_weight, s.C, s.C, W2t, st));
+    const float* W2t = ws + w.W2t;      // written by the forward's weight-prep launch
     ObpropTcArgs a;
     a.x = gO2; a.W = W2t; a.bias = nullptr; a.relu = 0; a.scale = nscale; a.scale_mod = s.N; a.gate = H1;
     a.rows = s.M1; a.C = s.C; a.out = gO1;

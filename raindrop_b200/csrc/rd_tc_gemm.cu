@@ -481,6 +481,11 @@ __global__ void split_weights_kernel(SplitItems s) {
   float lo = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
   if (w.lo) w.lo[e] = lo;
   if (w.t) { w.t[(long long)c * w.rows + r] = v; w.t_lo[(long long)c * w.rows + r] = lo; }
+  if (w.rn || w.rn_t) {
+    const float rn = rn_tf32(v);
+    if (w.rn) w.rn[e] = rn;
+    if (w.rn_t) w.rn_t[(long long)c * w.rows + r] = rn;
+  }
 }
 
 void plan(long long M, int N, int* BN, int* n_tiles) {

@@ -33,7 +33,8 @@ int tc_wgrad(const float* dY, long long ldy, const float* X, long long ldx, long
              float* dW, float* db, float* partial, cudaStream_t st);
 
 // One launch for all weights of a step: lo = W - trunc19(W); t = W^T; t_lo = W^T - trunc19(W^T).
-struct WeightSplit { const float* w; int rows, cols; float* lo; float* t; float* t_lo; };
+// optional extras for the single-pass-TF32 layers: rn = RN_tf32(W), rn_t = RN_tf32(W)^T
+struct WeightSplit { const float* w; int rows, cols; float* lo; float* t; float* t_lo; float* rn = nullptr; float* rn_t = nullptr; };
 int split_weights(const WeightSplit* items, int n, cudaStream_t st);   // n <= 16
 
 }  // namespace rd
