@@ -158,7 +158,7 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 // dropout-masked copy the sub-layer's weight gradient needs) and keeps per-lane column sums of
 // dy*xhat / dy in registers; the 8 warps of a CTA combine them through shared memory into one
 // partial row [2][D] per CTA (summed later in a fixed order).  128-bit accesses (D % 4 == 0).
-constexpr int LNB_ROWS = 64;    // rows per CTA
+constexpr int LNB_ROWS = 32;    // rows per CTA (4 per warp: enough CTAs to fill the SMs at B = 128)
 constexpr int LNB_MAXIT = 5;    // D <= 640
 __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(
     const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
