@@ -173,6 +173,28 @@ def test_full_size_properties():
     assert torch.isfinite(a).all()
 
 
+@pytest.mark.parametrize("cfg_name", ["P12", "PAM", "LARGE"])
+def test_full_size_other_baseline_configs(cfg_name):
+    """BASELINE configs[0], [2] and [4] (per-GPU batch) at FULL size: size-independent properties only
+    (finite, deterministic, samples independent, one training step produces finite gradients)."""
+    cfg = model_config(cfg_name, dropout=0.2)
+    B = cfg["batch"]
+    model = build_dropin(cfg, 4).eval()
+    d = to_dev(make_batch(cfg, B, seed=31))
+    st = lambda sl: None if d["static"] is None else d["static"][sl]
+    with torch.no_grad():
+        a, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+        b, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+        part, _, _ = model.forward(d["src"][:, 5:13], st(slice(5, 13)), d["times"][:, 5:13], d["lengths"][5:13])
+    assert a.shape == (B, cfg["n_classes"]) and torch.isfinite(a).all() and torch.equal(a, b)
+    assert normwise(part, a[5:13]) < 1e-5
+    model.train()
+    logits, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+    F.cross_entropy(logits, d["y"]).backward()
+    for p_ in model.used_parameters():
+        assert p_.grad is not None and torch.isfinite(p_.grad).all()
+
+
 def test_whole_validation_set_batch():
     """evaluate_standard pushes the whole validation set through in one batch (code/utils_rd.py:310-320)."""
     cfg = model_config("P19", dropout=0.2)
