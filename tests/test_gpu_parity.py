@@ -135,6 +135,34 @@ def test_against_oracle(cfg_name, B, opts):
             assert e < MODEL_TOL, (k, "vs tf32 precision model", e)
 
 
+@pytest.mark.parametrize("seed", list(range(12)))
+def test_random_shapes_against_oracle(seed):
+    """Seeded sweep over model shapes the BASELINE configs do not hit: odd sensor counts (head dim not a
+    multiple of 4), tiny and ragged T, 1..8 classes, with / without statics, random sparse weighted graphs,
+    batch sizes around the 128-row tile edges."""
+    from oracle.raindrop_oracle import build_oracle_model
+    g = torch.Generator().manual_seed(1000 + seed)
+    ri = lambda lo, hi: int(torch.randint(lo, hi + 1, (1,), generator=g))
+    N, T, B = ri(1, 13), ri(2, 70), [1, 2, 3, 5, 9, 17, 33, 64, 130][ri(0, 8)]
+    static = bool(ri(0, 1))
+    cfg = dict(name="RND", d_inp=N, max_len=T, d_static=ri(1, 7) if static else 0, n_classes=ri(2, 8), static=static,
+               batch=B, p_obs=0.5, d_ob=4, d_model=4 * N, nhid=8 * N, nlayers=ri(1, 3), nhead=2, dropout=0.2, MAX=100)
+    if ri(0, 1):
+        a = (torch.rand(N, N, generator=g) < 0.4).float() * torch.rand(N, N, generator=g)
+        cfg["global_structure"] = a
+    batch = make_batch(cfg, B, seed=seed, first_time_zero=bool(ri(0, 1)))
+    oracle = build_oracle_model(cfg).eval()
+    synth_weights(oracle, cfg, seed=40 + seed)
+    ref, _, _ = oracle.forward_dense(batch["src"], batch["static"], batch["times"], batch["lengths"], tf32_model=True)
+    F.cross_entropy(ref, batch["y"]).backward()
+    model, logits, _, loss, enc_in, _ = _run_dropin(cfg, batch, 40 + seed)
+    assert normwise(logits, ref.detach()) < 2e-4, (cfg, normwise(logits, ref.detach()))
+    gp, go = dict(model.named_parameters()), dict(oracle.named_parameters())
+    for k in used_param_keys(cfg):
+        e = rel_l2(gp[k].grad, go[k].grad)
+        assert e < 5e-2, (k, e, {kk: cfg[kk] for kk in ("d_inp", "max_len", "batch", "nlayers", "n_classes", "static")})
+
+
 def test_edge_cases():
     """lengths = 1, a sensor never observed, a sensor always observed, isolated graph node."""
     from oracle.raindrop_oracle import build_oracle_model
