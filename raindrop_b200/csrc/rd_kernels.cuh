@@ -42,6 +42,14 @@ int attn_softmax_fwd(float* S, const int64_t* lengths, int B, int H, int T, floa
 int attn_softmax_bwd(const float* P, float* dP, int B, int H, int T, float drop_p, const uint64_t* rng,
                      uint32_t site, cudaStream_t st);
 
+// fused classification head (rd_head.cu): feat[:, :D] must hold the pooled encoder output
+int head_fwd(int B, int D, int N, int ds, int ncls, const float* statics, const float* emb_w, const float* emb_b,
+             const float* w0, const float* b0, const float* w2, const float* b2, float* feat, float* hpre, float* logits,
+             cudaStream_t st);
+int head_bwd(int B, int D, int N, int ds, int ncls, const float* statics, const float* w0, const float* w2,
+             const float* feat, const float* hpre, const float* dlogits, float* dh, float* dfeat, float* g_w0, float* g_b0,
+             float* g_w2, float* g_b2, float* g_emb_w, float* g_emb_b, cudaStream_t st);
+
 // fused attention for short sequences (rd_attn_small.cu): ctx from qkv in one launch, dqkv in one launch
 bool attn_small_supported(int T, int hd);
 int attn_small_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T, int hd, float drop_p,

@@ -305,21 +305,8 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
   }
   float* feat = ws + w.feat; float* hpre = ws + w.hpre;
   RD_TRY(masked_mean_fwd(ws + w.Z[s.L], lengths, s.T, s.B, s.D, feat, s.Df, st));
-  if (s.ds > 0) {
-    GemmP g = nt(statics, s.ds, P->emb_weight, s.ds, feat + s.D, s.Df, s.B, s.N, s.ds);
-    g.bias = P->emb_bias;
-    RD_TRY(gemm(g, st));
-  }
-  {
-    GemmP g = nt(feat, s.Df, P->mlp0_weight, s.Df, hpre, s.Df, s.B, s.Df, s.Df);
-    g.bias = P->mlp0_bias; g.relu = 1;
-    RD_TRY(gemm(g, st));
-  }
-  {
-    GemmP g = nt(hpre, s.Df, P->mlp2_weight, s.Df, logits, s.ncls, s.B, s.ncls, s.Df);
-    g.bias = P->mlp2_bias;
-    RD_TRY(gemm(g, st));
-  }
+  RD_TRY(head_fwd(s.B, s.D, s.N, s.ds, s.ncls, statics, P->emb_weight, P->emb_bias, P->mlp0_weight, P->mlp0_bias,
+                  P->mlp2_weight, P->mlp2_bias, feat, hpre, logits, st));
   return 0;
 }
 
@@ -337,17 +324,8 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
   // ---- head: logits = mlp2(relu(mlp0(feat)))                      code/models_rd.py:383-385
   const float* feat = ws + w.feat; const float* hpre = ws + w.hpre;
   float* dfeat = sc + b.dfeat; float* dhpre = sc + b.dhpre;
-  RD_TRY(tn(dlogits, s.ncls, hpre, s.Df, G->mlp2_weight, G->mlp2_bias, s.ncls, s.Df, s.B, partial, st));
-  {
-    GemmP g = nn(dlogits, s.ncls, P->mlp2_weight, s.Df, dhpre, s.Df, s.B, s.Df, s.ncls);
-    g.gate = hpre; g.gate_ld = s.Df;
-    RD_TRY(gemm(g, st));
-  }
-  RD_TRY(tn(dhpre, s.Df, feat, s.Df, G->mlp0_weight, G->mlp0_bias, s.Df, s.Df, s.B, partial, st));
-  RD_TRY(gemm(nn(dhpre, s.Df, P->mlp0_weight, s.Df, dfeat, s.Df, s.B, s.Df, s.Df), st));
-  if (s.ds > 0) {
-    RD_TRY(tn(dfeat + s.D, s.Df, statics, s.ds, G->emb_weight, G->emb_bias, s.N, s.ds, s.B, partial, st));
-  }
+  RD_TRY(head_bwd(s.B, s.D, s.N, s.ds, s.ncls, statics, P->mlp0_weight, P->mlp2_weight, feat, hpre, dlogits, dhpre, dfeat,
+                  G->mlp0_weight, G->mlp0_bias, G->mlp2_weight, G->mlp2_bias, G->emb_weight, G->emb_bias, st));
   float* gA = sc + b.gA; float* gB = sc + b.gB; float* gC = sc + b.gC; float* gF = sc + b.gF; float* gD = sc + b.gD;
   float* dqkv = sc + b.dqkv; float* dP = sc + b.dP;
   RD_TRY(masked_mean_bwd(dfeat, s.Df, lengths, s.T, s.B, s.D, gA, st));
