@@ -33,15 +33,23 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadP p, float* __restrict
     }
   }
   __syncthreads();
-  for (int j = warp; j < p.Df; j += HT / 32) {    // one warp per hidden unit: coalesced weight row, shuffle reduce
-    const float* wr = p.w0 + (long long)j * p.Df;
-    float a = 0.f;
-    for (int k = lane; k < p.Df; k += 32) a = fmaf(fs[k], __ldg(wr + k), a);
-    a = warp_sum(a);
-    if (lane == 0) {
-      a = fmaxf(a + __ldg(p.b0 + j), 0.f);
-      hs[j] = a;
-      hpre[(long long)b * p.Df + j] = a;
+  // a warp owns 4 hidden units at a time (4 independent coalesced weight-row streams in flight), shuffle reduce
+  for (int j0 = warp * 4; j0 < p.Df; j0 += (HT / 32) * 4) {
+    float a[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k = lane; k < p.Df; k += 32) {
+      const float f = fs[k];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (j0 + u < p.Df) a[u] = fmaf(f, __ldg(p.w0 + (long long)(j0 + u) * p.Df + k), a[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float v = warp_sum(a[u]);
+      if (lane == 0 && j0 + u < p.Df) {
+        const float h = fmaxf(v + __ldg(p.b0 + j0 + u), 0.f);
+        hs[j0 + u] = h;
+        hpre[(long long)b * p.Df + j0 + u] = h;
+      }
     }
   }
   __syncthreads();
@@ -71,6 +79,7 @@ __global__ void __launch_bounds__(HT) head_bwd_sample_kernel(HeadP p, const floa
   __syncthreads();
   for (int k = tid; k < p.Df; k += HT) {          // column k of W0: coalesced across threads
     float a = 0.f;
+#pragma unroll 8
     for (int j = 0; j < p.Df; ++j) a = fmaf(ds_[j], __ldg(p.w0 + (long long)j * p.Df + k), a);
     dfeat[(long long)b * p.Df + k] = a;
   }
@@ -83,10 +92,12 @@ __global__ void head_outer_kernel(const float* __restrict__ Lm, long long ldl, c
   if (j >= J) return;
   float a = 0.f, s = 0.f;
   const bool kin = k < K;
-  for (int b = 0; b < B; ++b) {
+  const int kk = kin ? k : 0;                 // out-of-range lanes read a valid column and discard the result
+#pragma unroll 8
+  for (int b = 0; b < B; ++b) {                // 8 independent load pairs in flight per thread, fixed summation order
     const float l = __ldg(Lm + (long long)b * ldl + j);
     s += l;
-    if (kin) a = fmaf(l, __ldg(Rm + (long long)b * ldr + k), a);
+    a = fmaf(l, __ldg(Rm + (long long)b * ldr + kk), a);
   }
   if (kin) out[(long long)j * K + k] = a;
   if (bias && k == 0) bias[j] = s;
