@@ -324,17 +324,26 @@ bool attn_small_supported(int T, int hd) {
   return env == 1 && T <= TM && hd <= HDM;
 }
 
+static int ensure_smem_attrs() {
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e1 = cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(HDM));
+    cudaError_t e2 = cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(HDM));
+    if (e1 != cudaSuccess || e2 != cudaSuccess) {
+      set_error("attn_small: cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+      return -1;
+    }
+    attr = true;
+  }
+  return 0;
+}
+
 int attn_small_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T, int hd, float drop_p,
                    const uint64_t* rng, uint32_t site, float* ctx, cudaStream_t st) {
   AttnP p{};
   p.qkv = qkv; p.ctx = ctx; p.lengths = lengths; p.B = B; p.H = H; p.T = T; p.hd = hd; p.D = H * hd;
   p.scale = 1.f / sqrtf((float)hd); p.drop_p = drop_p; p.rng = rng; p.site = site;
-  static bool attr = false;
-  if (!attr) {
-    cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(HDM));
-    cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(HDM));
-    attr = true;
-  }
+  RD_TRY(ensure_smem_attrs());
   attn_small_fwd_kernel<<<B * H, 512, fwd_smem(hd), st>>>(p);
   RD_CHECK_LAUNCH("attn_small_fwd_kernel");
   return 0;
@@ -345,6 +354,7 @@ int attn_small_bwd(const float* qkv, const float* dctx, const int64_t* lengths, 
   AttnP p{};
   p.qkv = qkv; p.dctx = dctx; p.dqkv = dqkv; p.lengths = lengths; p.B = B; p.H = H; p.T = T; p.hd = hd; p.D = H * hd;
   p.scale = 1.f / sqrtf((float)hd); p.drop_p = drop_p; p.rng = rng; p.site = site;
+  RD_TRY(ensure_smem_attrs());
   attn_small_bwd_kernel<<<B * H, NTB, bwd_smem(hd), st>>>(p);
   RD_CHECK_LAUNCH("attn_small_bwd_kernel");
   return 0;

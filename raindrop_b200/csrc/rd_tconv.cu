@@ -106,7 +106,7 @@ extern "C" int rd_transformer_conv_fwd(const float* x, int32_t n_nodes, int32_t 
   tconv_logits_kernel<<<(unsigned)ceil_div((int64_t)E * heads * 32, 256), 256, 0, st>>>(q, k, edge_src, edge_tgt, edge_w,
                                                                                       E, heads, out_ch, logit);
   RD_CHECK_LAUNCH("tconv_logits_kernel");
-  cudaMemsetAsync(alpha, 0, sizeof(float) * (size_t)E * heads, st);
+  if (cudaMemsetAsync(alpha, 0, sizeof(float) * (size_t)E * heads, st) != cudaSuccess) { set_error("rd_transformer_conv_fwd: memset failed"); return -1; }
   tconv_softmax_kernel<<<(unsigned)ceil_div((int64_t)n_nodes * heads * 32, 256), 256, 0, st>>>(logit, edge_tgt, E, heads,
                                                                                              n_nodes, alpha);
   RD_CHECK_LAUNCH("tconv_softmax_kernel");

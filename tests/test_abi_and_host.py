@@ -137,3 +137,22 @@ def test_shard_slices_partition_the_batch():
             assert all(a.stop == b.start for a, b in zip(parts, parts[1:]))
             sizes = [p.stop - p.start for p in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_root_module_is_the_drop_in():
+    """`from models_rd import *` (code/Raindrop.py:19) with this repository's root on sys.path."""
+    import importlib
+    import sys
+    sys.modules.pop("models_rd", None)
+    mod = importlib.import_module("models_rd")
+    assert mod.__file__.startswith(ROOT)
+    ns = {}
+    exec("from models_rd import *", ns)
+    for name in ("Raindrop_v2", "Raindrop", "PositionalEncodingTF", "Observation_progation", "TransformerConv"):
+        assert name in ns, name
+    import inspect
+    sig = inspect.signature(ns["Raindrop_v2"].__init__)
+    assert list(sig.parameters)[1:] == ["d_inp", "d_model", "nhead", "nhid", "nlayers", "dropout", "max_len", "d_static",
+                                        "MAX", "perc", "aggreg", "n_classes", "global_structure", "sensor_wise_mask",
+                                        "static"]          # code/models_rd.py:208-209
+    assert list(inspect.signature(ns["Raindrop_v2"].forward).parameters)[1:] == ["src", "static", "times", "lengths"]
