@@ -95,10 +95,13 @@ def evaluate_sharded(model, P, Pstatic, Ptime, group=None):
         out, _, _ = model.forward(P[:, sl].to(dev), None if Pstatic is None else Pstatic[sl].to(dev), Pt, lengths)
     if world == 1:
         return out
-    sizes = [shard_slice(n, r, world) for r in range(world)]
-    bufs = [torch.empty(s.stop - s.start, out.shape[1], dtype=out.dtype, device=out.device) for s in sizes]
-    dist.all_gather(bufs, out.contiguous(), group=group)
-    return torch.cat(bufs, 0)
+    sizes = [s_.stop - s_.start for s_ in (shard_slice(n, r, world) for r in range(world))]
+    biggest = max(sizes)                       # all_gather needs equal shapes: pad the short shards, trim afterwards
+    padded = torch.zeros(biggest, out.shape[1], dtype=out.dtype, device=out.device)
+    padded[: out.shape[0]] = out
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded, group=group)
+    return torch.cat([b_[:k] for b_, k in zip(bufs, sizes)], 0)
 
 
 class TrainStep:

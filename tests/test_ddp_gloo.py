@@ -85,3 +85,44 @@ def test_two_rank_gradients_equal_full_batch(alias):
     ref = dict(oracle.named_parameters())
     for k in used_param_keys(cfg):
         assert torch.allclose(got[k], ref[k].grad, rtol=1e-4, atol=1e-7), k
+
+
+def _eval_worker(rank, world, port, out_q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from raindrop_b200.train import evaluate_sharded
+
+    class Stub(torch.nn.Module):            # stands in for Raindrop_v2 on CPU: any per-sample function will do
+        def __init__(self):
+            super().__init__()
+            self.w = torch.nn.Parameter(torch.arange(6.0).view(3, 2))
+
+        def forward(self, P, Pstatic, Ptime, lengths):
+            feat = torch.stack([P.sum((0, 2)), Ptime.sum(0), lengths.float()], 1)
+            return feat @ self.w, torch.zeros(()), None
+
+    g = torch.Generator().manual_seed(0)
+    P, Pt = torch.randn(5, 11, 4, generator=g), torch.rand(5, 11, generator=g)
+    out = evaluate_sharded(Stub(), P, None, Pt)
+    if rank == 0:
+        out_q.put(out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_sharded_evaluation_gathers_the_whole_set_in_order():
+    """evaluate_sharded (uneven shards: 11 samples on 2 ranks) == the single-process result, same order."""
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    g = torch.Generator().manual_seed(0)
+    P, Pt = torch.randn(5, 11, 4, generator=g), torch.rand(5, 11, generator=g)
+    feat = torch.stack([P.sum((0, 2)), Pt.sum(0), (Pt > 0).sum(0).float()], 1)
+    assert got.shape == (11, 2) and torch.allclose(got, feat @ torch.arange(6.0).view(3, 2), atol=1e-5)
