@@ -370,11 +370,13 @@ def main():
     line = {
         "metric": "samples/sec (P19-shape synthetic) training step", "value": round(value, 1), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (ob-prop GEMM operands TF32)",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
         "config": {"workload": "P19 synthetic (batch=128 per GPU, 34 sensors, T_max=60) Raindrop_v2 training step: "
                                "fwd + CrossEntropy + bwd + Adam, dropout 0.2", "global_batch": world * BATCH,
-                   "per_gpu_batch": BATCH, "parallelism": "sample-sharded dp%d, 1 NCCL all-reduce of the flat grad bucket" % world,
+                   "per_gpu_batch": BATCH,
+                   "precision": "fp32 storage and accumulation; ob-prop GEMM operands rounded to TF32 (forward error 3e-4), "
+                                "encoder GEMMs error-compensated 3xTF32 (fp32-level)", "parallelism": "sample-sharded dp%d, 1 NCCL all-reduce of the flat grad bucket" % world,
                    "l2": "flushed between timed steps (256 MiB write + read-back, outside the per-step CUDA-event pairs)",
                    "step": graph_note, "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4)},
         "clocks": clocks,
