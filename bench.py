@@ -1,19 +1,33 @@
 #!/usr/bin/env python
 """Benchmark of the Raindrop hot path on B200 (driver contract: see the task statement).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config NAME]
     torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
 A "step" is one training step of Raindrop_v2 (forward + CrossEntropy + backward + Adam, dropout 0.2,
-code/Raindrop.py:311-324) on one batch of P19-shape synthetic data (BASELINE.json configs[1]:
-B = 128 samples per GPU, 34 sensors, T_max = 60).  Weak scaling: every rank owns its own 128 samples;
-the only collective is one NCCL all-reduce over the flat gradient bucket.
+code/Raindrop.py:311-324) on one batch of synthetic data of the named configuration.  The default
+configuration is the one BASELINE.json's metric is quoted on (configs[1]: P19 shape, B = 128 samples per
+GPU, 34 sensors, T_max = 60); `--config` selects the other BASELINE configurations:
+
+    P12      configs[0]  B = 32,  36 sensors, T = 215   (the reference's CPU-runnable case)
+    P19      configs[1]  B = 128, 34 sensors, T = 60    (default; the driver's line)
+    PAM      configs[2]  B = 256, 17 sensors, T = 600, 8 classes, no static branch
+    P19x4    configs[3]  B = 256 per GPU (1024 over 4 GPUs), leave-10-sensors-out mask
+    LARGEx8  configs[4]  B = 512 per GPU (4096 over 8 GPUs), 128 sensors, T = 256
+
+Weak scaling: every rank owns its own per-GPU batch; the only collective is the NCCL all-reduce of the
+flat gradient bucket (two buckets, the first overlapped with the observation-propagation backward).
+
+Timing protocol: W >= 3 warm-up steps; K timed steps, each bracketed by CUDA events on the launching stream
+with an L2 flush (256 MiB write + read-back) before it, outside the event pair; the per-step times of all
+ranks are all-gathered, each step counts as the MAX over ranks, `ms_per_step` is the MEDIAN over steps
+(p90 / max / mean and the per-rank medians are reported next to it); value = global batch / median.
 
 Printed JSON line (rank 0):
   value     samples/s, whole job, inputs resident in HBM, step = one CUDA-graph replay of TrainStep
-  e2e       samples/s through the drop-in nn.Module API (model.forward -> criterion -> backward ->
-            optimizer.step) with pinned HOST batches, H2D copies and the loss read-back inside the
-            timed region
+  e2e       samples/s through the drop-in nn.Module API (model.forward -> CrossEntropyLoss -> backward ->
+            FlatAdam.step) with pinned HOST batches; one batch upload (H2D, on a copy stream, overlapping the
+            previous step) and the loss read-back (D2H) inside every timed step
   roofline  the observation-propagation (message-passing) layer kernel: algorithmic bytes
             8*N*C per (sample, layer) / CUDA-event time, at a row count with >= 1 GiB of traffic
             (`rows`) and at the configuration's own batch (`at_config`)
@@ -38,20 +52,34 @@ import torch  # noqa: E402
 import torch.distributed as dist  # noqa: E402
 import torch.nn.functional as F  # noqa: E402
 
-from raindrop_b200.synth import make_batch, model_config, synth_weights  # noqa: E402
+from raindrop_b200.synth import make_batch, model_config  # noqa: E402
+from raindrop_b200.synth import synth_weights  # noqa: E402
 
 warnings.filterwarnings("ignore")
-CFG_NAME = "P19"
-BATCH = 128
 L2_FLUSH_BYTES = 256 << 20   # > 126 MB L2
+
+# name -> (synthetic model config, per-GPU batch, GPUs the BASELINE config names, make_batch options, workload string)
+BENCH_CONFIGS = {
+    "P12": ("P12", 32, 1, {}, "P12 synthetic (batch=32 per GPU, 36 sensors, T_max=215)"),
+    "P19": ("P19", 128, 1, {}, "P19 synthetic (batch=128 per GPU, 34 sensors, T_max=60)"),
+    "PAM": ("PAM", 256, 1, {}, "PAM synthetic (batch=256 per GPU, 17 sensors, T_max=600, 8-class, no static)"),
+    "P19x4": ("P19", 256, 4, {"zero_sensors": 10},
+              "P19 synthetic batch=1024 over 4 GPUs (256 per GPU), 34 sensors, leave-10-sensors-out mask"),
+    "LARGEx8": ("LARGE", 512, 8, {}, "Synthetic large batch=4096 over 8 GPUs (512 per GPU), 128 sensors, T_max=256, dense sensor graph"),
+}
+STEP_DESC = "Raindrop_v2 training step: fwd + CrossEntropy + bwd + Adam, dropout 0.2"
+
+
+def workload_string(name):
+    return "%s %s" % (BENCH_CONFIGS[name][4], STEP_DESC)
 
 
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(path):
         p = json.load(open(path))
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
-    return 6650.0, "fallback (B200_PROFILING.md)"
+        return float(p["hbm_gbs"]), float(p.get("bf16_tflops", 0.0)) or None, "measured (MEASURED_PEAKS.json)"
+    return 6650.0, None, "fallback (B200_PROFILING.md)"
 
 
 class ClockSampler:
@@ -73,14 +101,18 @@ class ClockSampler:
         except Exception:
             self.proc = None
 
+    def mark(self):
+        """Samples before this point are warm-up / idle, not the timed region."""
+        self.skip = len(self.lines)
+
     def stop(self):
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         self.thread.join(timeout=2)
         sm, mx, reasons = [], None, set()
-        for ln in self.lines:
+        for ln in self.lines[getattr(self, "skip", 0):]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
                 continue
@@ -111,8 +143,9 @@ def build_model(cfg, device):
     from raindrop_b200.models_rd import Raindrop_v2
     torch.manual_seed(1)   # code/Raindrop.py:58
     gs = torch.ones(cfg["d_inp"], cfg["d_inp"])
+    kw = {} if cfg["static"] else {"static": False}
     m = Raindrop_v2(cfg["d_inp"], cfg["d_model"], cfg["nhead"], cfg["nhid"], cfg["nlayers"], cfg["dropout"],
-                    cfg["max_len"], cfg["d_static"], cfg["MAX"], 0.5, "mean", cfg["n_classes"], gs)
+                    cfg["max_len"], cfg["d_static"], cfg["MAX"], 0.5, "mean", cfg["n_classes"], gs, **kw)
     synth_weights(m, cfg, seed=7)      # random-init weights of the named architecture, same on every rank
     return m.to(device).train()
 
@@ -136,12 +169,22 @@ def timed_steps(step_fn, steps, flush_buf):
     return [s.elapsed_time(e) for s, e in ev]
 
 
-def max_over_ranks(x, world, device):
-    if world == 1:
-        return x
-    t = torch.tensor([x], dtype=torch.float64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return float(t.item())
+def summarize(per_step, world, device):
+    """per_step: this rank's CUDA-event times (ms).  All ranks' lists are gathered; a step costs what its
+    slowest rank took; the headline is the MEDIAN over steps."""
+    t = torch.tensor(per_step, dtype=torch.float64, device=device)
+    if world > 1:
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        allt = torch.stack(allt)                      # [world, steps]
+    else:
+        allt = t[None]
+    step_max = allt.max(dim=0).values.cpu().tolist()
+    srt = sorted(step_max)
+    n = len(srt)
+    return {"median": statistics.median(srt), "mean": sum(srt) / n, "p90": srt[min(n - 1, int(0.9 * n))],
+            "max": srt[-1], "min": srt[0],
+            "per_rank_median": [round(statistics.median(r), 4) for r in allt.cpu().tolist()]}
 
 
 def _round_tf32(t):
@@ -150,16 +193,17 @@ def _round_tf32(t):
     return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
 
 
-def roofline_leg(cfg, device):
+def roofline_leg(cfg, batch, device):
     """Message-passing layer kernel alone (rd_obprop_fwd on TF32-exact operands, no rounding pre-pass):
-    algorithmic bytes = read x[rows,C] + write out[rows,C]."""
+    algorithmic bytes = read x[rows,C] + write out[rows,C]; algorithmic flops = 2*rows*C^2."""
     from raindrop_b200 import lib as L
     lib = L.load()
     N, C = cfg["d_inp"], cfg["max_len"] * cfg["d_ob"]
-    peak, how = peaks()
+    hbm_peak, bf16_peak, how = peaks()
+    tf32_peak = bf16_peak / 2 if bf16_peak else None       # TF32 issues at half the bf16 rate
+    big_rows = max(batch * N, ((1 << 30) // (C * 8) // N + 1) * N)     # >= 1 GiB of activation traffic
     out = {}
-    for tag, B in (("large", 16384), ("at_config", BATCH)):
-        rows = B * N
+    for tag, rows in (("large", big_rows), ("at_config", batch * N)):
         x = _round_tf32(torch.randn(rows, C, device=device))
         W = _round_tf32(torch.randn(C, C, device=device) / C ** 0.5)
         b = torch.zeros(C, device=device)
@@ -175,8 +219,6 @@ def roofline_leg(cfg, device):
         ts = timed_steps(fn, 20, flush)
         ms = sum(ts) / len(ts)
         gb = rows * C * 8 / 1e9
-        # the same launch back to back (how MEASURED_PEAKS.json's copy bandwidth was taken); at `large` the
-        # 1.07 GB working set cannot stay in the 126 MB L2 either way
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(10):
@@ -184,88 +226,109 @@ def roofline_leg(cfg, device):
         e1.record()
         torch.cuda.synchronize()
         ms_b2b = e0.elapsed_time(e1) / 10
-        out[tag] = dict(rows=rows, ms=ms, achieved=gb / (ms * 1e-3), frac=gb / (ms * 1e-3) / peak,
-                        tflops=2.0 * rows * C * C / (ms * 1e-3) / 1e12, ms_b2b=ms_b2b, frac_b2b=gb / (ms_b2b * 1e-3) / peak)
+        out[tag] = dict(rows=rows, ms=ms, achieved=gb / (ms * 1e-3), frac=gb / (ms * 1e-3) / hbm_peak,
+                        tflops=2.0 * rows * C * C / (ms * 1e-3) / 1e12, ms_b2b=ms_b2b, frac_b2b=gb / (ms_b2b * 1e-3) / hbm_peak)
+        del x, y
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "obprop_tc_traffic.json")
-    if os.path.isfile(tpath):
+    if os.path.isfile(tpath) and C == 240:
         traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
     big = out["large"]
-    return {"kernel": "obprop_tc_kernel (tcgen05 TF32 + TMA, one ob-prop layer)", "bound": "hbm",
-            "achieved": round(big["achieved"], 1), "peak": peak, "peak_source": how, "unit": "GB/s",
-            "frac": round(big["frac"], 4), "traffic": traffic, "rows": big["rows"],
-            "algorithmic_bytes_per_launch": big["rows"] * C * 8, "ms_per_launch": round(big["ms"], 5),
-            "tflops_tf32": round(big["tflops"], 1),
-            "back_to_back": {"ms_per_launch": round(big["ms_b2b"], 5), "frac": round(big["frac_b2b"], 4),
-                             "note": "no L2 flush between launches (same protocol as the measured copy peak)"},
-            "at_config": {"rows": out["at_config"]["rows"], "ms_per_launch": round(out["at_config"]["ms"], 5),
-                          "achieved": round(out["at_config"]["achieved"], 1), "frac": round(out["at_config"]["frac"], 4),
-                          "note": "4352 rows = 34 tiles on 148 SMs, 8 MB: launch/latency bound, L2-sized"}}
+    tensor_frac = (big["tflops"] / tf32_peak) if tf32_peak else None
+    # C/4 flop per byte against the TF32 ridge: HBM binds at C=240, both are close at 860/1024, tensor at 2400
+    bound = "tensor" if (tensor_frac is not None and tensor_frac > big["frac"]) else "hbm"
+    r = {"kernel": "obprop_tc_kernel (tcgen05 TF32 + TMA, one ob-prop layer, C=%d)" % C, "bound": bound,
+         "peak_source": how, "rows": big["rows"], "ms_per_launch": round(big["ms"], 5), "traffic": traffic,
+         "algorithmic_bytes_per_launch": big["rows"] * C * 8, "algorithmic_flops_per_launch": 2 * big["rows"] * C * C,
+         "hbm": {"achieved": round(big["achieved"], 1), "peak": hbm_peak, "unit": "GB/s", "frac": round(big["frac"], 4)},
+         "tensor": {"achieved": round(big["tflops"], 1), "peak": tf32_peak, "unit": "TFLOP/s (tf32 = measured bf16 peak / 2)",
+                    "frac": round(tensor_frac, 4) if tensor_frac is not None else None},
+         "back_to_back": {"ms_per_launch": round(big["ms_b2b"], 5), "frac": round(big["frac_b2b"], 4),
+                          "note": "no L2 flush between launches (same protocol as the measured copy peak)"},
+         "at_config": {"rows": out["at_config"]["rows"], "ms_per_launch": round(out["at_config"]["ms"], 5),
+                       "achieved": round(out["at_config"]["achieved"], 1), "frac": round(out["at_config"]["frac"], 4),
+                       "tflops": round(out["at_config"]["tflops"], 1),
+                       "note": "the configuration's own batch: %d rows" % out["at_config"]["rows"]}}
+    if bound == "hbm":
+        r.update(achieved=r["hbm"]["achieved"], peak=hbm_peak, unit="GB/s", frac=r["hbm"]["frac"])
+    else:
+        r.update(achieved=r["tensor"]["achieved"], peak=tf32_peak, unit="TFLOP/s", frac=r["tensor"]["frac"])
+    return r
 
 
-def cpu_reference_leg(cfg, steps, warmup, budget_s=25.0):
+def cpu_reference_leg(name, steps, warmup, budget_s=25.0):
     """The CPU restatement of the reference (oracle/): same per-sample Python loop with per-edge
     lin_value GEMMs and torch.nn.TransformerEncoder as code/models_rd.py:322-358, train mode
-    (dropout 0.2), CrossEntropy + backward + Adam(lr=1e-4) like code/Raindrop.py:319-324."""
+    (dropout 0.2), CrossEntropy + backward + Adam(lr=1e-4) like code/Raindrop.py:319-324.
+    A step is a BOUNDED sample of the workload: the first `b_cpu` samples of the per-GPU batch (all of it
+    for P12 / P19; per-sample cost is independent of B in the reference's per-sample loop)."""
     from oracle.raindrop_oracle import build_oracle_model       # the checker, timed as the baseline
+    cfg_name, batch, _, opts, _ = BENCH_CONFIGS[name]
+    cfg = model_config(cfg_name, dropout=0.2)
+    b_cpu = {"P12": 32, "P19": 128, "PAM": 16, "P19x4": 128, "LARGEx8": 4}[name]
+    b_cpu = min(b_cpu, batch)
     model = build_oracle_model(cfg).train()
     synth_weights(model, cfg, seed=7)
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
-    batch = make_batch(cfg, BATCH, seed=1000 * 2)
-    # the path is thousands of tiny ops: more threads is not faster.  Probe a few thread counts on a
-    # small forward and keep the best, so the baseline gets the host's best configuration.
-    ncpu = os.cpu_count() or 1
-    probe = make_batch(cfg, 8, seed=5)
-    best_t, threads = None, 1
-    for cand in sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu}):
-        torch.set_num_threads(cand)
-        with torch.no_grad():
-            model.forward(probe["src"], probe["static"], probe["times"], probe["lengths"])
-            t0 = time.perf_counter()
-            model.forward(probe["src"], probe["static"], probe["times"], probe["lengths"])
-            dt = time.perf_counter() - t0
-        if best_t is None or dt < best_t:
-            best_t, threads = dt, cand
-    torch.set_num_threads(threads)
+    full = make_batch(cfg, b_cpu, seed=1000 * 2, **opts)
 
-    def one():
-        logits, _, _ = model.forward(batch["src"], batch["static"], batch["times"], batch["lengths"])
-        loss = F.cross_entropy(logits, batch["y"])
+    def one(b):
+        logits, _, _ = model.forward(b["src"], b["static"], b["times"], b["lengths"])
+        loss = F.cross_entropy(logits, b["y"])
         opt.zero_grad()
         loss.backward()
         opt.step()
         return loss.item()
 
+    # the path is thousands of tiny ops: more threads is not always faster.  Probe thread counts on the SAME
+    # kind of step that is timed (train step on a slice of the batch) and keep the best.
+    ncpu = os.cpu_count() or 1
+    pb = max(1, min(8, b_cpu))
+    probe = {k: (v[:, :pb] if k in ("src", "times") else (v[:pb] if v is not None else None)) for k, v in full.items()}
+    best_t, threads = None, 1
+    for cand in sorted({c for c in (4, 8, 16, 32, 64, ncpu) if c <= ncpu}):
+        torch.set_num_threads(cand)
+        one(probe)
+        t0 = time.perf_counter()
+        one(probe)
+        dt = time.perf_counter() - t0
+        if best_t is None or dt < best_t:
+            best_t, threads = dt, cand
+    torch.set_num_threads(threads)
     for _ in range(max(1, warmup)):
-        one()
+        one(full)
     ts = []
     t_begin = time.perf_counter()
     for _ in range(steps):
         t0 = time.perf_counter()
-        one()
+        one(full)
         ts.append(time.perf_counter() - t0)
         if time.perf_counter() - t_begin > budget_s:
             break
-    sec = sum(ts) / len(ts)
-    return {"value": round(BATCH / sec, 2), "unit": "samples/s", "cores": threads, "kind": "port",
-            "sample": "%d train steps (fwd+CE+bwd+Adam, dropout 0.2) of P19 B=%d after %d warm-up, %.2f s/step; "
-                      "torch %s CPU, %d threads (best of a probe over thread counts; host has %d logical CPUs)"
-                      % (len(ts), BATCH, max(1, warmup), sec, torch.__version__, threads, ncpu),
-            "sec_per_step": sec, "steps": len(ts)}
+    sec = statistics.median(ts)
+    return {"value": round(b_cpu / sec, 2), "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": "%d train steps (fwd+CE+bwd+Adam, dropout 0.2) on %d of the %d samples of a %s batch after %d warm-up, "
+                      "median %.2f s/step; torch %s CPU, %d threads (best of a probe over thread counts on the same "
+                      "train step; host has %d logical CPUs)"
+                      % (len(ts), b_cpu, batch, name, max(1, warmup), sec, torch.__version__, threads, ncpu),
+            "sec_per_step": sec, "steps": len(ts), "samples_per_step": b_cpu}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cfg = model_config(CFG_NAME, dropout=0.2)
-    cb = cpu_reference_leg(cfg, steps=max(1, min(args.steps, 20)), warmup=min(args.warmup, 2), budget_s=120.0)
-    line = {"impl": "reference", "metric": "samples/sec (P19-shape synthetic) training step", "value": cb["value"],
-            "unit": "samples/s", "n_gpus": args.gpus, "steps": cb["steps"], "warmup": min(args.warmup, 2),
+    name = args.config
+    batch = BENCH_CONFIGS[name][1]
+    cb = cpu_reference_leg(name, steps=max(1, min(args.steps, 20)), warmup=max(1, min(args.warmup, 3)), budget_s=150.0)
+    line = {"impl": "reference", "metric": "samples/sec (%s-shape synthetic) training step" % BENCH_CONFIGS[name][0],
+            "value": cb["value"],
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(cb["sec_per_step"] * 1e3, 2), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "P19 synthetic (batch=128, 34 sensors, T_max=60) Raindrop_v2 training step",
-                       "global_batch": BATCH, "note": "reference is CPU-only here: single process, host cores"},
+            "config": {"workload": workload_string(name), "global_batch": batch * args.gpus, "per_gpu_batch": batch,
+                       "note": "reference is CPU-only here: single process on rank 0's host cores, %d timed steps of %d samples"
+                               % (cb["steps"], cb["samples_per_step"])},
             "cpu_baseline": {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": cb["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -277,7 +340,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="P19", choices=sorted(BENCH_CONFIGS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-roofline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -285,18 +350,25 @@ def main():
         args.warmup = 3
 
     from raindrop_b200 import lib as L
+    from raindrop_b200.optim import FlatAdam
     from raindrop_b200.train import TrainStep, allreduce_gradients
     world, rank, local = dist_setup(args.gpus)
     device = torch.device("cuda", local if world > 1 else 0)
     torch.cuda.set_device(device)
-    cfg = model_config(CFG_NAME, dropout=0.2)
+    cfg_name, BATCH, named_gpus, opts, _ = BENCH_CONFIGS[args.config]
+    cfg = model_config(cfg_name, dropout=0.2)
     lib = L.load()
     flush = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
+    # clock sampler runs on rank 0 from BEFORE the first barrier (so starting it never sits between a barrier and
+    # the timed loop); samples taken before `mark()` are discarded
+    sampler = ClockSampler(device.index or 0)
+    if rank == 0:
+        sampler.start()
 
     # ---- leg 1: device-resident TrainStep, one CUDA graph per step ------------------------------
     model = build_model(cfg, device)
     ts = TrainStep(model, BATCH, lr=1e-4, use_graph=True)
-    host_batches = [make_batch(cfg, BATCH, seed=1000 * 2 + 17 * rank + i, pin=True) for i in range(4)]
+    host_batches = [make_batch(cfg, BATCH, seed=1000 * 2 + 17 * rank + i, pin=True, **opts) for i in range(4)]
     ts.load_batch(host_batches[0])
     n0 = lib.rd_launch_count()
     ts._enqueue()                      # eager once: counts our launches per step
@@ -311,12 +383,10 @@ def main():
     for _ in range(args.warmup):
         ts.step()
     torch.cuda.synchronize()
-    sampler = ClockSampler(device.index or 0)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    if rank == 0:
-        sampler.start()
+    sampler.mark()
     t_wall = time.perf_counter()
     per_step = timed_steps(ts.step, args.steps, flush)
     torch.cuda.synchronize()
@@ -324,34 +394,46 @@ def main():
         dist.barrier()
     wall = time.perf_counter() - t_wall
     clocks = sampler.stop() if rank == 0 else None
-    dev_ms = max_over_ranks(sum(per_step), world, device)
-    ms_per_step = dev_ms / args.steps
-    value = world * BATCH * args.steps / (dev_ms * 1e-3)
+    dev = summarize(per_step, world, device)
+    ms_per_step = dev["median"]
+    value = world * BATCH / (ms_per_step * 1e-3)
     loss_graph = float(ts.loss.item())
 
     # ---- leg 2: end to end through the drop-in module API, host batches ---------------------------
     model2 = build_model(cfg, device)
-    opt = torch.optim.Adam(model2.parameters(), lr=1e-4)
+    opt = FlatAdam(model2, lr=1e-4)
     crit = torch.nn.CrossEntropyLoss()
-    h2d = sum(t.numel() * t.element_size() for k, t in host_batches[0].items() if t is not None)
+    keys = [k for k in ("src", "times", "static", "y") if host_batches[0][k] is not None]
+    h2d = sum(host_batches[0][k].numel() * host_batches[0][k].element_size() for k in keys)
+    copy_stream = torch.cuda.Stream(device=device)
+    slots = [{k: torch.empty_like(host_batches[0][k], device=device) for k in keys} for _ in range(2)]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
     state = {"i": 0, "loss": 0.0}
 
+    def upload(i):
+        """pinned host batch i -> device slot i % 2 on the copy stream (overlaps the step that is running)"""
+        hb, slot = host_batches[i % len(host_batches)], slots[i % 2]
+        with torch.cuda.stream(copy_stream):
+            for k in keys:
+                slot[k].copy_(hb[k], non_blocking=True)
+            ready[i % 2].record(copy_stream)
+
     def e2e_step():
-        hb = host_batches[state["i"] % len(host_batches)]
+        i = state["i"]
         state["i"] += 1
-        P = hb["src"].to(device, non_blocking=True)
-        Pt = hb["times"].to(device, non_blocking=True)
-        Ps = hb["static"].to(device, non_blocking=True)
-        y = hb["y"].to(device, non_blocking=True)
-        lengths = torch.sum(Pt > 0, dim=0)                         # code/Raindrop.py:317
-        outputs, _, _ = model2.forward(P, Ps, Pt, lengths)         # code/Raindrop.py:319
+        upload(i + 1)                                              # H2D of the NEXT batch, inside this timed step
+        torch.cuda.current_stream().wait_event(ready[i % 2])
+        d = slots[i % 2]
+        lengths = torch.sum(d["times"] > 0, dim=0)                 # code/Raindrop.py:317
+        outputs, _, _ = model2.forward(d["src"], d.get("static"), d["times"], lengths)   # code/Raindrop.py:319
         opt.zero_grad()
-        loss = crit(outputs, y)
+        loss = crit(outputs, d["y"])
         loss.backward()
         allreduce_gradients(model2)
         opt.step()
         state["loss"] = loss.item()                                # D2H read of the step's result
 
+    upload(0)
     for _ in range(args.warmup):
         e2e_step()
     torch.cuda.synchronize()
@@ -360,40 +442,45 @@ def main():
     e2e_times = timed_steps(e2e_step, args.steps, flush)
     if world > 1:
         dist.barrier()
-    e2e_ms = max_over_ranks(sum(e2e_times), world, device)
-    e2e_value = world * BATCH * args.steps / (e2e_ms * 1e-3)
+    e2e = summarize(e2e_times, world, device)
+    e2e_value = world * BATCH / (e2e["median"] * 1e-3)
 
     if rank != 0:
         _finish(world)
         return
-    roof = roofline_leg(cfg, device)
     line = {
-        "metric": "samples/sec (P19-shape synthetic) training step", "value": round(value, 1), "unit": "samples/s",
+        "metric": "samples/sec (%s-shape synthetic) training step" % cfg_name, "value": round(value, 1), "unit": "samples/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_per_step, 4),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 (tf32 operands in the ob-prop GEMMs, 3xTF32 error-compensated encoder GEMMs)",
         "data": "synthetic",
-        "config": {"workload": "P19 synthetic (batch=128 per GPU, 34 sensors, T_max=60) Raindrop_v2 training step: "
-                               "fwd + CrossEntropy + bwd + Adam, dropout 0.2", "global_batch": world * BATCH,
-                   "per_gpu_batch": BATCH,
+        "config": {"workload": workload_string(args.config), "global_batch": world * BATCH, "per_gpu_batch": BATCH,
+                   "bench_config": args.config, "baseline_config_gpus": named_gpus,
                    "precision": "fp32 storage and accumulation; ob-prop GEMM operands rounded to TF32 (forward error 3e-4), "
-                                "encoder GEMMs error-compensated 3xTF32 (fp32-level)", "parallelism": "sample-sharded dp%d, 1 NCCL all-reduce of the flat grad bucket" % world,
+                                "encoder GEMMs error-compensated 3xTF32 (fp32-level)",
+                   "parallelism": "sample-sharded dp%d, NCCL all-reduce of the flat grad bucket in 2 pieces (first overlaps the ob-prop backward)" % world,
                    "l2": "flushed between timed steps (256 MiB write + read-back, outside the per-step CUDA-event pairs)",
                    "step": graph_note, "wall_ms_per_step_incl_flush": round(wall / args.steps * 1e3, 4)},
+        "timing": {"statistic": "median over steps of (max over ranks of the per-step CUDA-event time)",
+                   "ms_median": round(dev["median"], 4), "ms_mean": round(dev["mean"], 4), "ms_p90": round(dev["p90"], 4),
+                   "ms_max": round(dev["max"], 4), "ms_min": round(dev["min"], 4), "per_rank_median_ms": dev["per_rank_median"]},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 1), "unit": "samples/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 4,
-                "ms_per_step": round(e2e_ms / args.steps, 4),
-                "path": "pinned host batch -> H2D -> models_rd.Raindrop_v2.forward -> CrossEntropyLoss -> backward -> "
-                        "torch.optim.Adam.step -> loss.item()"},
+                "ms_per_step": round(e2e["median"], 4), "ms_mean": round(e2e["mean"], 4), "ms_p90": round(e2e["p90"], 4),
+                "ms_max": round(e2e["max"], 4), "per_rank_median_ms": e2e["per_rank_median"],
+                "path": "pinned host batch -> H2D (copy stream, one batch ahead) -> models_rd.Raindrop_v2.forward -> "
+                        "CrossEntropyLoss -> backward -> raindrop_b200.optim.FlatAdam.step -> loss.item()"},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
-        "roofline": roof,
         "final_loss": {"graph": round(loss_graph, 5), "e2e": round(state["loss"], 5)},
     }
+    if not args.no_roofline:
+        line["roofline"] = roofline_leg(cfg, BATCH, device)
     if world == 1 and not args.no_cpu_baseline:
         # separate process (own thread pool, hard time limit) so a slow host cannot stall the bench
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", "5",
-                                "--warmup", "1"], capture_output=True, text=True, timeout=240)
+                                "--warmup", "1", "--config", args.config], capture_output=True, text=True, timeout=300)
             ref = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
             line["cpu_baseline"] = ref["cpu_baseline"]
         except Exception as exc:  # noqa: BLE001

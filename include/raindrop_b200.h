@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define RD_ABI_VERSION 1
+#define RD_ABI_VERSION 2
 #define RD_MAX_LAYERS 8
 #define RD_D_PE 16 /* d_pe, code/models_rd.py:215 */
 
@@ -156,7 +156,11 @@ int rd_obprop_beta_fwd(const float* x, const float* p_t, const int64_t* edge_src
  *   rng_state  2 x uint64 on the device: {seed, counter}; the forward copies it into the
  *              workspace and increments the counter (only when training && dropout_p > 0)
  *   workspace  rd_workspace_bytes(dims) bytes, kept by the caller until backward is done
- *   logits  [B, n_classes]                                                                */
+ *   logits  [B, n_classes]
+ *   y       optional int64 labels [B]: when given, the head kernel also evaluates
+ *           torch.nn.CrossEntropyLoss (mean) -- code/Raindrop.py:322 -- writing the scalar `loss` and
+ *           `d_logits` [B, n_classes] = d(loss)/d(logits), ready for rd_raindrop_v2_bwd.  NULL: plain forward
+ *           (loss / d_logits ignored).                                                            */
 size_t rd_workspace_bytes(const rd_dims* dims);
 size_t rd_backward_scratch_bytes(const rd_dims* dims);
 /* offset (bytes) and element count of a named buffer inside the workspace; -1 if unknown */
@@ -165,11 +169,22 @@ int64_t rd_workspace_offset(const rd_dims* dims, int32_t which, int64_t* n_float
 int rd_raindrop_v2_fwd(const rd_dims* dims, const rd_params* params, const float* src,
                        const float* statics, const float* times, const int64_t* lengths,
                        const float* node_scale, uint64_t* rng_state, void* workspace,
-                       float* logits, void* stream);
+                       float* logits, const int64_t* y, float* loss, float* d_logits, void* stream);
 
+/* Backward (autograd of the above, code/Raindrop.py:323).  `phases` selects what one call does so that a
+ * data-parallel caller can start reducing the first gradient bucket while the rest is still being computed
+ * (SURVEY.md 8e):
+ *   RD_BWD_ENCODER  head + temporal-attention encoder: every gradient except the two lin_value pairs is final
+ *                   when the call's work completes; d(loss)/d(encoder input) stays in `scratch`
+ *   RD_BWD_OBPROP   observation propagation: ob1/ob2 lin_value gradients (needs the same scratch, after ENCODER)
+ *   both (3)        whole backward, weight gradients in one grouped tensor-core launch                    */
+#define RD_BWD_ENCODER 1
+#define RD_BWD_OBPROP 2
+#define RD_BWD_ALL 3
 int rd_raindrop_v2_bwd(const rd_dims* dims, const rd_params* params, const float* statics,
                        const int64_t* lengths, const float* node_scale, const void* workspace,
-                       const float* d_logits, const rd_grads* grads, void* scratch, void* stream);
+                       const float* d_logits, const rd_grads* grads, void* scratch, int32_t phases,
+                       void* stream);
 
 /* ---- pieces exposed on their own (module-level drop-ins and tests) -------------------------
  * pe[t,b,:] = [sin(times/ts_k), cos(times/ts_k)]  -> out[(t*B+b)*ld + col0 + 0..15]
@@ -184,6 +199,18 @@ int rd_positional_encoding(const float* times, int64_t n_tokens, const float* ti
 size_t rd_linear_scratch_bytes(int32_t in_features, int32_t out_features);
 int rd_linear_fwd(const float* x, const float* weight, const float* bias, int64_t rows, int32_t in_features,
                   int32_t out_features, int32_t relu, float* out, void* scratch, void* stream);
+
+/* Weight/bias gradients of up to 12 torch.nn.Linear layers in ONE grouped tensor-core launch (+ one reduction
+ * launch): d_weight[out_f, in_f] = d_out[rows, out_f]^T . x[rows, in_f], d_bias[out_f] = column sums of d_out.
+ * This is what autograd computes for every Linear on the path (code/Raindrop.py:323); a training step has ten of
+ * them (8 encoder weights + the two lin_value).  Error-compensated TF32 (fp32-level accuracy), deterministic.
+ * `partial`: rd_linear_wgrad_partial_bytes(rows, out_f, in_f) bytes of scratch per problem, 16-byte aligned. */
+typedef struct rd_wgrad_item {
+  const float* d_out; const float* x; int64_t rows; int32_t out_features; int32_t in_features;
+  float* d_weight; float* d_bias; void* partial;
+} rd_wgrad_item;
+size_t rd_linear_wgrad_partial_bytes(int64_t rows, int32_t out_features, int32_t in_features);
+int rd_linear_wgrad_group(const rd_wgrad_item* items, int32_t n, void* stream);
 
 /* TransformerConv.forward (code/transformer_conv.py:139-207), concat=True, root_weight=True,
  * beta=False, no edge features.  x [n_nodes, in]; weights [H*F, in]; edge_w may be NULL (then the
@@ -209,11 +236,14 @@ int rd_gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_t
  * mean cross entropy + d(loss)/d(logits), torch.nn.CrossEntropyLoss semantics. */
 int rd_cross_entropy_fwd_bwd(const float* logits, const int64_t* y, int32_t B, int32_t n_classes,
                              float* loss, float* d_logits, void* stream);
-/* torch.optim.Adam (no weight decay, no amsgrad) on flat buffers; `step` is a device counter
- * incremented by the call; grad is multiplied by grad_scale first (1/world_size after a sum). */
+/* torch.optim.Adam (no weight decay, no amsgrad) on flat buffers, ONE launch.  `step` is int64[2] on the
+ * device: step[0] = number of updates so far (incremented by the call, by the last CTA to finish),
+ * step[1] = ticket word that must be 0 on entry (the call leaves it 0).  grad is multiplied by grad_scale
+ * first (1/world_size after a sum all-reduce).  lr_dev: optional device scalar that overrides `lr`, so a
+ * captured CUDA graph follows a scheduler (ReduceLROnPlateau, code/Raindrop.py:257-259) without re-capture. */
 int rd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n,
-                 float lr, float beta1, float beta2, float eps, float grad_scale, int64_t* step,
-                 void* stream);
+                 float lr, const float* lr_dev, float beta1, float beta2, float eps, float grad_scale,
+                 int64_t* step, void* stream);
 
 /* debug: materialise the dropout keep/scale mask (0 or 1/(1-p)) of one dropout site, so tests can
  * replay train-mode forward/backward in the oracle with identical masks.  `site` ids in DESIGN.md. */

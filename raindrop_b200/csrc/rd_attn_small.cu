@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include "rd_kernels.cuh"
+#include "rd_tc_common.cuh"
 
 namespace rd {
 namespace {
@@ -325,16 +326,8 @@ bool attn_small_supported(int T, int hd) {
 }
 
 static int ensure_smem_attrs() {
-  static bool attr = false;
-  if (!attr) {
-    cudaError_t e1 = cudaFuncSetAttribute(attn_small_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fwd_smem(HDM));
-    cudaError_t e2 = cudaFuncSetAttribute(attn_small_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bwd_smem(HDM));
-    if (e1 != cudaSuccess || e2 != cudaSuccess) {
-      set_error("attn_small: cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
-      return -1;
-    }
-    attr = true;
-  }
+  RD_TRY(tc::ensure_max_smem((const void*)attn_small_fwd_kernel, (int)fwd_smem(HDM)));
+  RD_TRY(tc::ensure_max_smem((const void*)attn_small_bwd_kernel, (int)bwd_smem(HDM)));
   return 0;
 }
 

@@ -79,34 +79,36 @@ __global__ void rng_capture_kernel(uint64_t* state, uint64_t* cap, int advance) 
   if (advance) state[1] = state[1] + 1;
 }
 
-__global__ void lift_kernel(const float* __restrict__ src, const float* __restrict__ R_u, int B, int T, int N,
-                            int d_ob, float drop_p, const uint64_t* __restrict__ rng, int round, float* __restrict__ X0) {
-  const long long C = (long long)T * d_ob;
-  const long long total = (long long)B * N * C;
-  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= total) return;
-  long long row = o / C;
-  int c = (int)(o - row * C);
-  int b = (int)(row / N), n = (int)(row - (long long)b * N);
-  int t = c / d_ob, k = c - t * d_ob;
-  float v = __ldg(src + ((long long)t * B + b) * (2 * N) + n) * __ldg(R_u + n * d_ob + k);
-  v = fmaxf(v, 0.f);
-  if (drop_p > 0.f) {
-    uint64_t idx = ((uint64_t)t * B + b) * (uint64_t)(N * d_ob) + (uint64_t)(n * d_ob + k);
-    v *= dropout_scale(rng, SITE_LIFT, idx, drop_p, 1.f / (1.f - drop_p));
-  }
-  X0[o] = round ? to_tf32(v) : v;
-}
-
 struct TS8 { float v[8]; };
-__global__ void posenc_kernel(const float* __restrict__ times, long long n_tokens, TS8 ts, float* __restrict__ out,
-                              long long ld, int col0) {
+// One launch for the two element-wise producers of the forward's inputs:
+//   o <  n_lift : X0[(b*N+n), t*d_ob+k] = dropout(relu(src[t,b,n] * R_u[n*d_ob+k]))     code/models_rd.py:285-296,323-327
+//   o >= n_lift : positional encoding of token (o - n_lift) / 16 into out[tok*ld + col0 + j]   code/models_rd.py:28-43
+__global__ void lift_posenc_kernel(const float* __restrict__ src, const float* __restrict__ R_u, int B, int T, int N,
+                                   int d_ob, float drop_p, const uint64_t* __restrict__ rng, int round,
+                                   float* __restrict__ X0, long long n_lift, const float* __restrict__ times,
+                                   long long n_tokens, TS8 ts, float* __restrict__ pe_out, long long ld, int col0) {
   long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o < n_lift) {
+    const long long C = (long long)T * d_ob;
+    long long row = o / C;
+    int c = (int)(o - row * C);
+    int b = (int)(row / N), n = (int)(row - (long long)b * N);
+    int t = c / d_ob, k = c - t * d_ob;
+    float v = __ldg(src + ((long long)t * B + b) * (2 * N) + n) * __ldg(R_u + n * d_ob + k);
+    v = fmaxf(v, 0.f);
+    if (drop_p > 0.f) {
+      uint64_t idx = ((uint64_t)t * B + b) * (uint64_t)(N * d_ob) + (uint64_t)(n * d_ob + k);
+      v *= dropout_scale(rng, SITE_LIFT, idx, drop_p, 1.f / (1.f - drop_p));
+    }
+    X0[o] = round ? to_tf32(v) : v;
+    return;
+  }
+  o -= n_lift;
   if (o >= n_tokens * 16) return;
   long long tok = o >> 4;
   int j = (int)(o & 15);
   float scaled = __ldg(times + tok) / ts.v[j & 7];
-  out[tok * ld + col0 + j] = (j < 8) ? sinf(scaled) : cosf(scaled);
+  pe_out[tok * ld + col0 + j] = (j < 8) ? sinf(scaled) : cosf(scaled);
 }
 
 // one warp per node: segment max, then sum of exp, then s = sum(exp / (sum + 1e-16))
@@ -163,8 +165,10 @@ constexpr int LNB_MAXIT = 5;    // D <= 640
 __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(
     const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ dy, long long rows, int D, float* __restrict__ dx, float* __restrict__ dx_drop,
-    float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial) {
+    float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial,
+    unsigned* __restrict__ counter, float* __restrict__ dgamma, float* __restrict__ dbeta) {
   extern __shared__ float lsm[];                     // [8 warps][2][D]
+  __shared__ int s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float4 ag[LNB_MAXIT], ab[LNB_MAXIT];
@@ -228,6 +232,40 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(
     for (int w = 0; w < 8; ++w) s += lsm[w * 2 * D + c];     // c < D: dgamma column, else dbeta column
     partial[(long long)blockIdx.x * 2 * D + c] = s;
   }
+  if (!counter) return;
+  // ---- the last CTA to finish sums the per-CTA partial rows in a fixed order (deterministic) -----
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  const int nq = (2 * D) >> 2;                         // float4 columns of a partial row
+  int groups = 256 / nq; if (groups > 8) groups = 8; if (groups < 1) groups = 1;
+  const int width = 256 / groups;                      // float4 columns handled per pass
+  const int nblk = (int)gridDim.x;
+  const int per = (nblk + groups - 1) / groups;
+  const int gq = threadIdx.x / width, cl = threadIdx.x % width;
+  for (int q0 = 0; q0 < nq; q0 += width) {
+    const int cq = q0 + cl;
+    if (gq < groups && cq < nq) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+      const int r0 = gq * per, r1 = min(nblk, r0 + per);
+#pragma unroll 8
+      for (int r = r0; r < r1; ++r) {
+        const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (long long)r * 2 * D) + cq);
+        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+      }
+      *reinterpret_cast<float4*>(lsm + gq * 2 * D + 4 * cq) = a;
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
+    float sacc = 0.f;
+    for (int k = 0; k < groups; ++k) sacc += lsm[k * 2 * D + c];
+    if (c < D) dgamma[c] = sacc; else dbeta[c - D] = sacc;
+  }
+  if (threadIdx.x == 0) *counter = 0u;
 }
 
 __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ stats,
@@ -365,39 +403,6 @@ __global__ void attn_softmax_bwd_kernel(const float* __restrict__ P, float* __re
   }
 }
 
-// block (32 channels, 8 time groups): coalesced along d, the T reads of one channel are spread over 8
-// threads and reduced through shared memory (fixed order -> deterministic)
-__global__ void masked_mean_fwd_kernel(const float* __restrict__ x, const int64_t* __restrict__ lengths, int T, int B,
-                                       int D, float* __restrict__ out, long long ld) {
-  __shared__ float red[8][33];
-  const int b = blockIdx.y;
-  const int d = blockIdx.x * 32 + threadIdx.x;
-  const long long len = lengths[b];
-  const int nv = (int)(len < T ? (len < 0 ? 0 : len) : T);
-  float s = 0.f;
-  if (d < D)
-    for (int t = threadIdx.y; t < nv; t += 8) s += x[((long long)t * B + b) * D + d];
-  red[threadIdx.y][threadIdx.x] = s;
-  __syncthreads();
-  if (threadIdx.y == 0 && d < D) {
-#pragma unroll
-    for (int g = 1; g < 8; ++g) s += red[g][threadIdx.x];
-    out[(long long)b * ld + d] = s / (float)(len + 1);
-  }
-}
-
-__global__ void masked_mean_bwd_kernel(const float* __restrict__ dout, long long ld,
-                                       const int64_t* __restrict__ lengths, int T, int B, int D,
-                                       float* __restrict__ dx) {
-  long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (o >= (long long)T * B * D) return;
-  int d = (int)(o % D);
-  long long tb = o / D;
-  int b = (int)(tb % B), t = (int)(tb / B);
-  long long len = lengths[b];
-  dx[o] = (t < len) ? dout[(long long)b * ld + d] / (float)(len + 1) : 0.f;
-}
-
 __global__ void obprop_out_grad_kernel(const float* __restrict__ dZ, const float* __restrict__ Z,
                                        const float* __restrict__ s, int B, int T, int N, int d_ob, int D,
                                        int round, float* __restrict__ dZ2) {
@@ -459,27 +464,37 @@ __global__ void cross_entropy_kernel(const float* __restrict__ logits, const int
   }
 }
 
-__global__ void adam_tick_kernel(int64_t* step) { *step = *step + 1; }
-
+// One launch: every CTA reads the step count t (before anyone changes it), updates its slice with bias
+// corrections for t + 1, and the LAST CTA to finish stores t + 1 (ticket in step[1], self-resetting).
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, float lr, float b1, float b2, float eps, float gscale,
-                            const int64_t* __restrict__ step) {
-  __shared__ float bc[2];
+                            float* __restrict__ v, long long n, float lr, const float* __restrict__ lr_dev, float b1,
+                            float b2, float eps, float gscale, int64_t* __restrict__ step) {
+  __shared__ float bc[3];
   if (threadIdx.x == 0) {
-    double t = (double)(*step);
+    double t = (double)(*reinterpret_cast<volatile int64_t*>(step) + 1);
     bc[0] = (float)(1.0 - pow((double)b1, t));
     bc[1] = (float)sqrt(1.0 - pow((double)b2, t));
+    bc[2] = lr_dev ? *lr_dev : lr;
   }
   __syncthreads();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float gi = g[i] * gscale;
-  float mi = b1 * m[i] + (1.f - b1) * gi;
-  float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-  m[i] = mi;
-  v[i] = vi;
-  float denom = sqrtf(vi) / bc[1] + eps;
-  p[i] -= (lr / bc[0]) * (mi / denom);
+  if (i < n) {
+    float gi = g[i] * gscale;
+    float mi = b1 * m[i] + (1.f - b1) * gi;
+    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    float denom = sqrtf(vi) / bc[1] + eps;
+    p[i] -= (bc[2] / bc[0]) * (mi / denom);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long* ticket = reinterpret_cast<unsigned long long*>(step + 1);
+    if (atomicAdd(ticket, 1ull) == (unsigned long long)(gridDim.x - 1)) {
+      *ticket = 0ull;
+      step[0] = step[0] + 1;
+    }
+  }
 }
 
 }  // namespace
@@ -511,21 +526,23 @@ int gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_tota
   return 0;
 }
 
-int lift(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p, const uint64_t* rng,
-         int round, float* X0, cudaStream_t st) {
-  int64_t total = (int64_t)B * N * T * d_ob;
-  lift_kernel<<<blocks_for(total), TPB, 0, st>>>(src, R_u, B, T, N, d_ob, drop_p, rng, round, X0);
-  RD_CHECK_LAUNCH("lift_kernel");
+int lift_posenc(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p, const uint64_t* rng,
+                int round, float* X0, const float* times, int64_t n_tokens, const float* ts8_host, float* pe_out, int64_t ld,
+                int col0, cudaStream_t st) {
+  const int64_t n_lift = src ? (int64_t)B * N * T * d_ob : 0;
+  const int64_t n_pe = times ? n_tokens * 16 : 0;
+  TS8 ts;
+  if (times) memcpy(ts.v, ts8_host, sizeof(ts.v)); else memset(ts.v, 0, sizeof(ts.v));
+  if (n_lift + n_pe <= 0) return 0;
+  lift_posenc_kernel<<<blocks_for(n_lift + n_pe), TPB, 0, st>>>(src, R_u, B, T, N, d_ob, drop_p, rng, round, X0, n_lift, times,
+                                                               times ? n_tokens : 0, ts, pe_out, ld, col0);
+  RD_CHECK_LAUNCH("lift_posenc_kernel");
   return 0;
 }
 
 int posenc(const float* times, int64_t n_tokens, const float* ts8_host, float* out, int64_t ld, int col0,
            cudaStream_t st) {
-  TS8 ts;
-  memcpy(ts.v, ts8_host, sizeof(ts.v));
-  posenc_kernel<<<blocks_for(n_tokens * 16), TPB, 0, st>>>(times, n_tokens, ts, out, ld, col0);
-  RD_CHECK_LAUNCH("posenc_kernel");
-  return 0;
+  return lift_posenc(nullptr, nullptr, 0, 0, 0, 0, 0.f, nullptr, 0, nullptr, times, n_tokens, ts8_host, out, ld, col0, st);
 }
 
 int node_scale(const int64_t* edge_tgt, const float* edge_w, int E, int N, float* s, cudaStream_t st) {
@@ -548,14 +565,15 @@ int64_t ln_bwd_scratch_floats(int64_t rows, int D) {
 
 int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows, int D,
                   float* dx, float* dgamma, float* dbeta, float* scratch, float* dx_drop, float drop_p,
-                  const uint64_t* rng, uint32_t site, cudaStream_t st) {
+                  const uint64_t* rng, uint32_t site, unsigned* counter, cudaStream_t st) {
   const uintptr_t bits = reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
                          reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_drop);
   if ((D & 3) == 0 && D <= 128 * LNB_MAXIT && (bits & 15) == 0) {     // fused single pass
     const int chunks = (int)ceil_div(rows, LNB_ROWS);
     layernorm_bwd_fused_kernel<<<chunks, 256, 8 * 2 * D * sizeof(float), st>>>(
-        x, stats, gamma, dy, rows, D, dx, drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site, scratch);
+        x, stats, gamma, dy, rows, D, dx, drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site, scratch, counter, dgamma, dbeta);
     RD_CHECK_LAUNCH("layernorm_bwd_fused_kernel");
+    if (counter) return 0;          // reduced by the last CTA of the launch above
     return reduce_partials2(scratch, chunks, D, dgamma, D, dbeta, st);
   }
   layernorm_bwd_dx_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, stats, gamma, dy, rows, D, dx,
@@ -583,21 +601,6 @@ int attn_softmax_bwd(const float* P, float* dP, int B, int H, int T, float drop_
   int64_t rows = (int64_t)B * H * T;
   attn_softmax_bwd_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(P, dP, rows, T, drop_p, rng, site);
   RD_CHECK_LAUNCH("attn_softmax_bwd_kernel");
-  return 0;
-}
-
-int masked_mean_fwd(const float* x, const int64_t* lengths, int T, int B, int D, float* out, int64_t ld,
-                    cudaStream_t st) {
-  if (B > 65535) { set_error("masked_mean_fwd: batch too large for one launch"); return -2; }
-  masked_mean_fwd_kernel<<<dim3((unsigned)ceil_div(D, 32), (unsigned)B), dim3(32, 8), 0, st>>>(x, lengths, T, B, D, out, ld);
-  RD_CHECK_LAUNCH("masked_mean_fwd_kernel");
-  return 0;
-}
-
-int masked_mean_bwd(const float* dout, int64_t ld, const int64_t* lengths, int T, int B, int D, float* dx,
-                    cudaStream_t st) {
-  masked_mean_bwd_kernel<<<blocks_for((int64_t)T * B * D), TPB, 0, st>>>(dout, ld, lengths, T, B, D, dx);
-  RD_CHECK_LAUNCH("masked_mean_bwd_kernel");
   return 0;
 }
 
@@ -630,11 +633,9 @@ int cross_entropy(const float* logits, const int64_t* y, int B, int ncls, float*
   return 0;
 }
 
-int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
-         float gscale, int64_t* step, cudaStream_t st) {
-  adam_tick_kernel<<<1, 1, 0, st>>>(step);
-  RD_CHECK_LAUNCH("adam_tick_kernel");
-  adam_kernel<<<blocks_for(n), TPB, 0, st>>>(p, g, m, v, n, lr, b1, b2, eps, gscale, step);
+int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float b1, float b2,
+         float eps, float gscale, int64_t* step, cudaStream_t st) {
+  adam_kernel<<<blocks_for(n), TPB, 0, st>>>(p, g, m, v, n, lr, lr_dev, b1, b2, eps, gscale, step);
   RD_CHECK_LAUNCH("adam_kernel");
   return 0;
 }

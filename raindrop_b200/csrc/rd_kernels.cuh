@@ -11,9 +11,12 @@ int gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_tota
 int rng_capture(uint64_t* rng_state, uint64_t* captured, int advance, cudaStream_t st);
 
 // X0[(b*N+n), t*d_ob+k] = dropout(relu(src[t,b,n] * R_u[n*d_ob+k]))    code/models_rd.py:285-296,323-327
-// round != 0: values are rounded (RN) to TF32 so the tensor-core layer reads them exactly
-int lift(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p,
-         const uint64_t* rng, int round, float* X0, cudaStream_t st);
+// round != 0: values are rounded (RN) to TF32 so the tensor-core layer reads them exactly.
+// The same launch writes the positional encoding of `times` into pe_out[tok*ld + col0 ..+16] (src == nullptr
+// or times == nullptr skips that half).
+int lift_posenc(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p, const uint64_t* rng,
+                int round, float* X0, const float* times, int64_t n_tokens, const float* ts8_host, float* pe_out, int64_t ld,
+                int col0, cudaStream_t st);
 
 // y [cols, rows] = RN_tf32(x [rows, cols])^T
 int transpose_round(const float* x, int rows, int cols, float* y, cudaStream_t st);
@@ -30,9 +33,11 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t
 int64_t ln_bwd_scratch_floats(int64_t rows, int D);
 // dx_drop (optional, used when drop_p > 0): dx with the dropout mask of `site` re-applied, i.e. the
 // gradient w.r.t. the sub-layer output that was dropped before the residual add
+// counter != nullptr: the per-CTA partial rows are summed by the last CTA of the same launch (ticket in *counter,
+// which must be 0 on entry and is reset to 0); otherwise a second launch reduces them
 int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows,
                   int D, float* dx, float* dgamma, float* dbeta, float* scratch, float* dx_drop, float drop_p,
-                  const uint64_t* rng, uint32_t site, cudaStream_t st);
+                  const uint64_t* rng, uint32_t site, unsigned* counter, cudaStream_t st);
 
 // in-place masked softmax over rows of S [B,H,T,T]; key j masked when j >= lengths[b].
 // If Pd != nullptr also writes the dropped probabilities (training).
@@ -42,13 +47,18 @@ int attn_softmax_fwd(float* S, const int64_t* lengths, int B, int H, int T, floa
 int attn_softmax_bwd(const float* P, float* dP, int B, int H, int T, float drop_p, const uint64_t* rng,
                      uint32_t site, cudaStream_t st);
 
-// fused classification head (rd_head.cu): feat[:, :D] must hold the pooled encoder output
-int head_fwd(int B, int D, int N, int ds, int ncls, const float* statics, const float* emb_w, const float* emb_b,
-             const float* w0, const float* b0, const float* w2, const float* b2, float* feat, float* hpre, float* logits,
-             cudaStream_t st);
-int head_bwd(int B, int D, int N, int ds, int ncls, const float* statics, const float* w0, const float* w2,
-             const float* feat, const float* hpre, const float* dlogits, float* dh, float* dfeat, float* g_w0, float* g_b0,
-             float* g_w2, float* g_b2, float* g_emb_w, float* g_emb_b, cudaStream_t st);
+// fused pooling + classification head (rd_head.cu).  x = encoder output [T, B, D]; writes feat [B, Df], hpre [B, Df],
+// logits [B, ncls]; with labels y also the per-sample losses, d(loss)/d(logits) of the batch-mean CrossEntropy and
+// the scalar loss (summed by the last CTA, ticket in *counter which must be 0 on entry).
+int head_fwd(int B, int T, int D, int N, int ds, int ncls, const float* x, const int64_t* lengths, const float* statics,
+             const float* emb_w, const float* emb_b, const float* w0, const float* b0, const float* w2, const float* b2,
+             float* feat, float* hpre, float* logits, const int64_t* y, float* loss_ps, float* dlogits, float* loss,
+             unsigned* counter, cudaStream_t st);
+// dx = d(loss)/d(encoder output) [T, B, D] (masked-mean backward); also zeroes `counters[0..n_counters)`
+int head_bwd(int B, int T, int D, int N, int ds, int ncls, const int64_t* lengths, const float* statics, const float* w0,
+             const float* w2, const float* feat, const float* hpre, const float* dlogits, float* dh, float* dfeat, float* dx,
+             float* g_w0, float* g_b0, float* g_w2, float* g_b2, float* g_emb_w, float* g_emb_b, unsigned* counters,
+             int n_counters, cudaStream_t st);
 
 // fused attention for short sequences (rd_attn_small.cu): ctx from qkv in one launch, dqkv in one launch
 bool attn_small_supported(int T, int hd);
@@ -56,12 +66,6 @@ int attn_small_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T
                    const uint64_t* rng, uint32_t site, float* ctx, cudaStream_t st);
 int attn_small_bwd(const float* qkv, const float* dctx, const int64_t* lengths, int B, int H, int T, int hd,
                    float drop_p, const uint64_t* rng, uint32_t site, float* dqkv, cudaStream_t st);
-
-// pooled[b, d] = sum_{t < len_b} x[t,b,d] / (len_b + 1) -> out[b*ld + d]     code/models_rd.py:366-379
-int masked_mean_fwd(const float* x, const int64_t* lengths, int T, int B, int D, float* out, int64_t ld,
-                    cudaStream_t st);
-int masked_mean_bwd(const float* dout, int64_t ld, const int64_t* lengths, int T, int B, int D, float* dx,
-                    cudaStream_t st);
 
 // dZ2[(b*N+n), t*d_ob+k] = dZ[t,b,n*d_ob+k] * s[n] * (Z[t,b,n*d_ob+k] > 0)
 int obprop_out_grad(const float* dZ, const float* Z, const float* s, int B, int T, int N, int d_ob, int D,
@@ -77,7 +81,9 @@ int relu_scale_bwd(const float* d_out, const float* out, const float* scale, int
 
 int cross_entropy(const float* logits, const int64_t* y, int B, int ncls, float* loss, float* dlogits,
                   cudaStream_t st);
-int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, float b1, float b2, float eps,
-         float gscale, int64_t* step, cudaStream_t st);
+// step: int64[2] = {count, ticket}; the ticket word must be 0 on entry (it is reset by the launch).  The count is
+// incremented by the last CTA of the launch, so one launch does tick + update.  lr_dev (optional, device) overrides lr.
+int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float b1, float b2,
+         float eps, float gscale, int64_t* step, cudaStream_t st);
 
 }  // namespace rd

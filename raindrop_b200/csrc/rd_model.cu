@@ -49,7 +49,7 @@ struct Arena {
 };
 
 struct WsLayout {
-  int64_t rng, X0, H1, W1r, W2r, W2t, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
+  int64_t rng, cnt, loss_ps, X0, H1, W1r, W2r, W2t, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
   struct { int64_t qkv, P, Pd, ctx, r1, st1, x1, f, r2, st2; } l[RD_MAX_LAYERS];
   // error-compensation remainders and transposes of the encoder weights (rd_tc_gemm.cuh)
   struct { int64_t in_lo, in_t, in_tlo, out_lo, out_t, out_tlo, l1_lo, l1_t, l1_tlo, l2_lo, l2_t, l2_tlo; } wsp[RD_MAX_LAYERS];
@@ -59,17 +59,21 @@ WsLayout ws_layout(const Shape& s) {
   WsLayout w;
   Arena a;
   w.rng = a.take(4);
+  w.cnt = a.take(64);                   // ticket word of the fused loss reduction (zeroed by the step prologue)
+  w.loss_ps = a.take(s.B);              // per-sample cross-entropy terms
   w.X0 = a.take(s.M1 * s.C);
   w.H1 = a.take(s.M1 * s.C);
   w.W1r = a.take((int64_t)s.C * s.C);   // TF32-rounded copies of the two lin_value weights
   w.W2r = a.take((int64_t)s.C * s.C);
   w.W2t = a.take((int64_t)s.C * s.C);   // rounded W2^T for the backward d(input) GEMM
   for (int i = 0; i <= s.L; ++i) w.Z[i] = a.take(s.M2 * s.D);
-  int64_t pp = (int64_t)s.B * s.H * s.T * s.T;
+  // the T x T probabilities only reach HBM on the long-sequence path (the fused short-sequence kernels
+  // keep them in shared memory and recompute them in backward)
+  const int64_t pp = attn_small_supported(s.T, s.hd) ? 0 : (int64_t)s.B * s.H * s.T * s.T;
   for (int i = 0; i < s.L; ++i) {
     w.l[i].qkv = a.take(s.M2 * 3 * s.D);
     w.l[i].P = a.take(pp);
-    w.l[i].Pd = a.take(pp);
+    w.l[i].Pd = a.take(s.p > 0.f ? pp : 0);
     w.l[i].ctx = a.take(s.M2 * s.D);
     w.l[i].r1 = a.take(s.M2 * s.D);
     w.l[i].st1 = a.take(s.M2 * 2);
@@ -89,48 +93,55 @@ WsLayout ws_layout(const Shape& s) {
   return w;
 }
 
+// Backward scratch.  The weight gradients are DEFERRED: every linear layer's (dY, X) operand pair stays alive in
+// its own buffer until one grouped tensor-core launch (tc_wgrad_group) reduces them all, so dY buffers and the
+// split-K partial buffers are per layer / per problem instead of ping-pong.
 struct BwLayout {
-  int64_t dfeat, dhpre, gA, gB, gC, gF, gD, dqkv, dP, gO2, gO1, W2t, partial, aux, total;
+  int64_t cnt, dfeat, dhpre, gA, gB, gD, dP, gO2, gO1, partial, aux, total;
+  struct { int64_t K2, gF, K1, dqkv, wp[4]; } l[RD_MAX_LAYERS];   // wp: linear2, linear1, out_proj, in_proj partials
+  int64_t wp_ob[2];
   int64_t partial_floats, aux_floats;
 };
 
-int64_t tn_partial_floats(int Nout, int Kin, int64_t rows) {
+constexpr int N_COUNTERS = 64;
+
+int64_t splitk_partial_floats(int Nout, int Kin, int64_t rows) {
   int ns;
-  int64_t a = gemm_splitk_plan(Nout, Kin, (int)rows, &ns);
-  int64_t b = tc_wgrad_partial_floats(Nout, Kin, rows);     // tensor-core path (shape permitting)
-  return a > b ? a : b;
+  return gemm_splitk_plan(Nout, Kin, (int)rows, &ns);
 }
 
 BwLayout bw_layout(const Shape& s) {
   BwLayout b;
   Arena a;
+  b.cnt = a.take(N_COUNTERS);
   b.dfeat = a.take((int64_t)s.B * s.Df);
   b.dhpre = a.take((int64_t)s.B * s.Df);
   b.gA = a.take(s.M2 * s.D);
   b.gB = a.take(s.M2 * s.D);
-  b.gC = a.take(s.M2 * s.D);
-  b.gF = a.take(s.M2 * s.nhid);
   b.gD = a.take(s.M2 * s.D);
-  b.dqkv = a.take(s.M2 * 3 * s.D);
-  b.dP = a.take((int64_t)s.B * s.H * s.T * s.T);
+  b.dP = a.take(attn_small_supported(s.T, s.hd) ? 0 : (int64_t)s.B * s.H * s.T * s.T);
+  for (int l = 0; l < s.L; ++l) {
+    b.l[l].K2 = a.take(s.M2 * s.D);
+    b.l[l].gF = a.take(s.M2 * s.nhid);
+    b.l[l].K1 = a.take(s.M2 * s.D);
+    b.l[l].dqkv = a.take(s.M2 * 3 * s.D);
+    b.l[l].wp[0] = a.take(tc_wgrad_partial_floats(s.D, s.nhid, s.M2));
+    b.l[l].wp[1] = a.take(tc_wgrad_partial_floats(s.nhid, s.D, s.M2));
+    b.l[l].wp[2] = a.take(tc_wgrad_partial_floats(s.D, s.D, s.M2));
+    b.l[l].wp[3] = a.take(tc_wgrad_partial_floats(3 * s.D, s.D, s.M2));
+  }
   b.gO2 = a.take(s.M1 * s.C);
   b.gO1 = a.take(s.M1 * s.C);
-  b.W2t = a.take((int64_t)s.C * s.C);
+  b.wp_ob[0] = a.take(tc_wgrad_partial_floats(s.C, s.C, s.M1));
+  b.wp_ob[1] = a.take(tc_wgrad_partial_floats(s.C, s.C, s.M1));
+  // shared split-K scratch of the CUDA-core fallback (shapes the tensor-core kernel does not take)
   int64_t pf = 0;
-  auto upd = [&](int no, int ki, int64_t rows) { int64_t v = tn_partial_floats(no, ki, rows); if (v > pf) pf = v; };
+  auto upd = [&](int no, int ki, int64_t rows) { int64_t v = splitk_partial_floats(no, ki, rows); if (v > pf) pf = v; };
   upd(s.C, s.C, s.M1);
   upd(3 * s.D, s.D, s.M2); upd(s.D, s.D, s.M2); upd(s.nhid, s.D, s.M2); upd(s.D, s.nhid, s.M2);
-  upd(s.Df, s.Df, s.B); upd(s.ncls, s.Df, s.B);
-  if (s.ds > 0) upd(s.N, s.ds, s.B);
   b.partial_floats = pf;
   b.partial = a.take(pf);
-  int64_t af = 0;
-  auto upa = [&](int64_t v) { if (v > af) af = v; };
-  upa(colsum_scratch_floats(s.M1, s.C));
-  upa(colsum_scratch_floats(s.M2, 3 * s.D));
-  upa(colsum_scratch_floats(s.M2, s.nhid));
-  upa(colsum_scratch_floats(s.B, s.Df));
-  upa(ln_bwd_scratch_floats(s.M2, s.D));
+  int64_t af = ln_bwd_scratch_floats(s.M2, s.D);
   b.aux_floats = af;
   b.aux = a.take(af);
   b.total = a.off;
@@ -155,11 +166,29 @@ GemmP nn(const float* dY, int64_t ldy, const float* W, int64_t ldw, float* dX, i
   g.M = (int)M; g.N = Kin; g.K = Nout;
   return g;
 }
-// dW[Nout,Kin] = sum_r dY[r,Nout]^T X[r,Kin]   (split over rows, deterministic two-stage reduce)
-int tn(const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db, int Nout, int Kin, int64_t rows,
-       float* partial, cudaStream_t st) {
-  if (rows >= 256 && tc_wgrad_supported(Nout, Kin, ldy, ldx, dY, X))
-    return tc_wgrad(dY, ldy, X, ldx, rows, Nout, Kin, dW, db, partial, st);
+// dW[Nout,Kin] = sum_r dY[r,Nout]^T X[r,Kin], db = sum_r dY[r,:]: queued for the next grouped tensor-core launch when
+// the shape fits, else done right away on the CUDA cores (split over rows, deterministic two-stage reduce).
+struct WgradQueue {
+  WgradItem it[WG_MAX];
+  int n = 0;
+  int flush(cudaStream_t st) {
+    if (n == 0) return 0;
+    int rc = tc_wgrad_group(it, n, st);
+    n = 0;
+    return rc;
+  }
+};
+
+int tn(WgradQueue* q, const float* dY, int64_t ldy, const float* X, int64_t ldx, float* dW, float* db, int Nout, int Kin,
+       int64_t rows, float* tc_partial, float* partial, cudaStream_t st) {
+  if (rows >= 256 && tc_partial && tc_wgrad_supported(Nout, Kin, ldy, ldx, dY, X)) {
+    if (q) {
+      if (q->n == WG_MAX) RD_TRY(q->flush(st));
+      q->it[q->n++] = WgradItem{dY, ldy, X, ldx, rows, Nout, Kin, dW, db, tc_partial};
+      return 0;
+    }
+    return tc_wgrad(dY, ldy, X, ldx, rows, Nout, Kin, dW, db, tc_partial, st);
+  }
   GemmP g;
   g.A = dY; g.ta = 1; g.sAk = ldy; g.sAi = 1;
   g.B = X; g.tb = 0; g.sBk = ldx; g.sBj = 1;
@@ -200,16 +229,18 @@ static int obprop_forward(const ObpropTcArgs& a, cudaStream_t st) {
 
 static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* src, const float* statics,
                         const float* times, const int64_t* lengths, const float* nscale, uint64_t* rng_state,
-                        float* ws, float* logits, cudaStream_t st) {
+                        float* ws, float* logits, const int64_t* y, float* loss, float* d_logits, cudaStream_t st) {
   Shape s;
   RD_TRY(make_shape(dims, &s));
   if (s.ds > 0 && (!statics || !P->emb_weight || !P->emb_bias)) { set_error("static branch needs statics/emb"); return -2; }
   WsLayout w = ws_layout(s);
   uint64_t* rng = reinterpret_cast<uint64_t*>(ws + w.rng);
-  if (s.p > 0.f) {
-    if (!rng_state) { set_error("training with dropout needs rng_state"); return -2; }
-    RD_TRY(rng_capture(rng_state, rng, 1, st));
-  }
+  if (s.p > 0.f && !rng_state) { set_error("training with dropout needs rng_state"); return -2; }
+  if (y && (!loss || !d_logits)) { set_error("labels given without loss / d_logits outputs"); return -2; }
+  // rides along with the first weight-prep launch: dropout-stream capture (+ advance) and the loss ticket reset
+  StepPrologue pro;
+  if (s.p > 0.f) { pro.rng_state = rng_state; pro.rng_captured = rng; pro.advance = 1; }
+  pro.zero_counter = reinterpret_cast<unsigned*>(ws + w.cnt);
   float* X0 = ws + w.X0; float* H1 = ws + w.H1;
   // Tensor-core operands are kept exactly TF32-representable by their producers (lift, layer-1
   // epilogue, rounded weight copies) so the MMA's operand truncation is exact.
@@ -230,10 +261,11 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
       items[n++] = {E.linear1_weight, s.nhid, s.D, ws + w.wsp[l].l1_lo, ws + w.wsp[l].l1_t, ws + w.wsp[l].l1_tlo};
       items[n++] = {E.linear2_weight, s.D, s.nhid, ws + w.wsp[l].l2_lo, ws + w.wsp[l].l2_t, ws + w.wsp[l].l2_tlo};
     }
-    RD_TRY(split_weights(items, n, st));
+    RD_TRY(split_weights(items, n, st, l0 == 0 ? &pro : nullptr));
   }
-  RD_TRY(lift(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, tc, X0, st));
   float* Z0 = ws + w.Z[0];
+  // lift of the raw observations and the positional encoding (written into Z0[..., 4N:]) in one launch
+  RD_TRY(lift_posenc(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, tc, X0, times, s.M2, dims->pe_timescales, Z0, s.D, s.Dm, st));
   {
     ObpropTcArgs a;
     a.x = X0; a.W = W1; a.bias = P->ob1_value_bias; a.scale = nscale; a.scale_mod = s.N;
@@ -243,7 +275,6 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
     a.perm = 1; a.pB = s.B; a.pN = s.N; a.pdob = s.dob; a.pD = s.D;
     RD_TRY(obprop_forward(a, st));
   }
-  RD_TRY(posenc(times, s.M2, dims->pe_timescales, Z0, s.D, s.Dm, st));
 
   const float scale = 1.f / sqrtf((float)s.hd);
   const int64_t row3 = (int64_t)s.B * 3 * s.D;
@@ -304,31 +335,34 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
     RD_TRY(layernorm_fwd(r2, E.norm2_weight, E.norm2_bias, s.M2, s.D, dims->ln_eps, ws + w.Z[l + 1], ws + w.l[l].st2, st));
   }
   float* feat = ws + w.feat; float* hpre = ws + w.hpre;
-  RD_TRY(masked_mean_fwd(ws + w.Z[s.L], lengths, s.T, s.B, s.D, feat, s.Df, st));
-  RD_TRY(head_fwd(s.B, s.D, s.N, s.ds, s.ncls, statics, P->emb_weight, P->emb_bias, P->mlp0_weight, P->mlp0_bias,
-                  P->mlp2_weight, P->mlp2_bias, feat, hpre, logits, st));
+  RD_TRY(head_fwd(s.B, s.T, s.D, s.N, s.ds, s.ncls, ws + w.Z[s.L], lengths, statics, P->emb_weight, P->emb_bias,
+                  P->mlp0_weight, P->mlp0_bias, P->mlp2_weight, P->mlp2_bias, feat, hpre, logits, y, ws + w.loss_ps, d_logits,
+                  loss, reinterpret_cast<unsigned*>(ws + w.cnt), st));
   return 0;
 }
 
 static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* statics, const int64_t* lengths,
                         const float* nscale, const float* ws, const float* dlogits, const rd_grads* G, float* sc,
-                        cudaStream_t st) {
+                        int phases, cudaStream_t st) {
   Shape s;
   RD_TRY(make_shape(dims, &s));
+  if ((phases & ~3) || phases == 0) { set_error("rd_raindrop_v2_bwd: phases must be 1, 2 or 3"); return -2; }
   WsLayout w = ws_layout(s);
   BwLayout b = bw_layout(s);
   const uint64_t* rng = reinterpret_cast<const uint64_t*>(ws + w.rng);
   float* partial = sc + b.partial; float* aux = sc + b.aux;
+  unsigned* counters = reinterpret_cast<unsigned*>(sc + b.cnt);
   const float ik = s.p > 0.f ? 1.f / (1.f - s.p) : 1.f;
+  float* gA = sc + b.gA; float* gB = sc + b.gB; float* gD = sc + b.gD; float* dP = sc + b.dP;
+  WgradQueue wq;     // weight gradients wait here for ONE grouped tensor-core launch per phase
 
-  // ---- head: logits = mlp2(relu(mlp0(feat)))                      code/models_rd.py:383-385
+  if (phases & RD_BWD_ENCODER) {
+  // ---- head: logits = mlp2(relu(mlp0(feat))), pooled = masked mean          code/models_rd.py:366-385
   const float* feat = ws + w.feat; const float* hpre = ws + w.hpre;
   float* dfeat = sc + b.dfeat; float* dhpre = sc + b.dhpre;
-  RD_TRY(head_bwd(s.B, s.D, s.N, s.ds, s.ncls, statics, P->mlp0_weight, P->mlp2_weight, feat, hpre, dlogits, dhpre, dfeat,
-                  G->mlp0_weight, G->mlp0_bias, G->mlp2_weight, G->mlp2_bias, G->emb_weight, G->emb_bias, st));
-  float* gA = sc + b.gA; float* gB = sc + b.gB; float* gC = sc + b.gC; float* gF = sc + b.gF; float* gD = sc + b.gD;
-  float* dqkv = sc + b.dqkv; float* dP = sc + b.dP;
-  RD_TRY(masked_mean_bwd(dfeat, s.Df, lengths, s.T, s.B, s.D, gA, st));
+  RD_TRY(head_bwd(s.B, s.T, s.D, s.N, s.ds, s.ncls, lengths, statics, P->mlp0_weight, P->mlp2_weight, feat, hpre, dlogits,
+                  dhpre, dfeat, gA, G->mlp0_weight, G->mlp0_bias, G->mlp2_weight, G->mlp2_bias, G->emb_weight, G->emb_bias,
+                  counters, N_COUNTERS, st));
 
   const float scale = 1.f / sqrtf((float)s.hd);
   const int64_t row3 = (int64_t)s.B * 3 * s.D;
@@ -341,32 +375,34 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     const float* Pd = s.p > 0.f ? ws + w.l[l].Pd : Pm;
     const float* ctx = ws + w.l[l].ctx; const float* r1 = ws + w.l[l].r1; const float* x1 = ws + w.l[l].x1;
     const float* f = ws + w.l[l].f; const float* r2 = ws + w.l[l].r2;
-    // norm2 + feed-forward block
-    RD_TRY(layernorm_bwd(r2, ws + w.l[l].st2, E.norm2_weight, gA, s.M2, s.D, gB, GE.norm2_weight, GE.norm2_bias, aux,
-                         gC, s.p, rng, SITE_RESID2 + l, st));
-    const float* dg = s.p > 0.f ? gC : gB;
-    RD_TRY(tn(dg, s.D, f, s.nhid, GE.linear2_weight, GE.linear2_bias, s.D, s.nhid, s.M2, partial, st));
-    {   // gF = (dg . W2) * [f > 0] / (1-p)   ("NT" against W2^T so that the tensor-core kernel applies)
-      GemmP g = nt(dg, s.D, ws + w.wsp[l].l2_t, s.D, gF, s.nhid, s.M2, s.nhid, s.D);
+    float* K2 = sc + b.l[l].K2; float* gF = sc + b.l[l].gF; float* K1 = sc + b.l[l].K1; float* dqkv = sc + b.l[l].dqkv;
+    // norm2 + feed-forward block.  K2 = gradient w.r.t. the (dropped) linear2 output: operand of its weight
+    // gradient, kept until the grouped launch; res = the undropped residual-path gradient
+    float* res = s.p > 0.f ? gB : K2;
+    RD_TRY(layernorm_bwd(r2, ws + w.l[l].st2, E.norm2_weight, gA, s.M2, s.D, res, GE.norm2_weight, GE.norm2_bias, aux,
+                         K2, s.p, rng, SITE_RESID2 + l, counters + 2 * l, st));
+    RD_TRY(tn(&wq, K2, s.D, f, s.nhid, GE.linear2_weight, GE.linear2_bias, s.D, s.nhid, s.M2, sc + b.l[l].wp[0], partial, st));
+    {   // gF = (K2 . W2) * [f > 0] / (1-p)   ("NT" against W2^T so that the tensor-core kernel applies)
+      GemmP g = nt(K2, s.D, ws + w.wsp[l].l2_t, s.D, gF, s.nhid, s.M2, s.nhid, s.D);
       g.gate = f; g.gate_ld = s.nhid; g.gate_scale = ik;  // relu' and the FFN dropout mask in one
       RD_TRY(linear_nt(g, ws + w.wsp[l].l2_tlo, st));
     }
-    RD_TRY(tn(gF, s.nhid, x1, s.D, GE.linear1_weight, GE.linear1_bias, s.nhid, s.D, s.M2, partial, st));
+    RD_TRY(tn(&wq, gF, s.nhid, x1, s.D, GE.linear1_weight, GE.linear1_bias, s.nhid, s.D, s.M2, sc + b.l[l].wp[1], partial, st));
     {
       GemmP g = nt(gF, s.nhid, ws + w.wsp[l].l1_t, s.nhid, gA, s.D, s.M2, s.D, s.nhid);
-      g.resid = gB; g.resid_ld = s.D;
+      g.resid = res; g.resid_ld = s.D;
       RD_TRY(linear_nt(g, ws + w.wsp[l].l1_tlo, st));
     }
     // norm1 + self-attention block
-    RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, gB, GE.norm1_weight, GE.norm1_bias, aux,
-                         gC, s.p, rng, SITE_RESID1 + l, st));
-    const float* dy = s.p > 0.f ? gC : gB;
-    RD_TRY(tn(dy, s.D, ctx, s.D, GE.out_proj_weight, GE.out_proj_bias, s.D, s.D, s.M2, partial, st));
-    RD_TRY(linear_nt(nt(dy, s.D, ws + w.wsp[l].out_t, s.D, gD, s.D, s.M2, s.D, s.D), ws + w.wsp[l].out_tlo, st));
+    res = s.p > 0.f ? gB : K1;
+    RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, res, GE.norm1_weight, GE.norm1_bias, aux,
+                         K1, s.p, rng, SITE_RESID1 + l, counters + 2 * l + 1, st));
+    RD_TRY(tn(&wq, K1, s.D, ctx, s.D, GE.out_proj_weight, GE.out_proj_bias, s.D, s.D, s.M2, sc + b.l[l].wp[2], partial, st));
+    RD_TRY(linear_nt(nt(K1, s.D, ws + w.wsp[l].out_t, s.D, gD, s.D, s.M2, s.D, s.D), ws + w.wsp[l].out_tlo, st));
     if (attn_small_supported(s.T, s.hd)) {
       RD_TRY(attn_small_bwd(qkv, gD, lengths, s.B, s.H, s.T, s.hd, s.p, rng, SITE_ATTN + l, dqkv, st));
     } else {
-          {  // dPd[b,h] = dctx V^T
+      {  // dPd[b,h] = dctx V^T
         GemmP g;
         g.A = gD; g.ta = 0; g.sAi = (int64_t)s.B * s.D; g.sAk = 1; g.sAzo = s.D; g.sAzi = s.hd;
         g.B = qkv + 2 * s.D; g.tb = 1; g.sBj = row3; g.sBk = 1; g.sBzo = 3 * s.D; g.sBzi = s.hd;
@@ -400,19 +436,23 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
         RD_TRY(gemm(g, st));
       }
     }
-    RD_TRY(tn(dqkv, 3 * s.D, x, s.D, GE.in_proj_weight, GE.in_proj_bias, 3 * s.D, s.D, s.M2, partial, st));
+    RD_TRY(tn(&wq, dqkv, 3 * s.D, x, s.D, GE.in_proj_weight, GE.in_proj_bias, 3 * s.D, s.D, s.M2, sc + b.l[l].wp[3], partial, st));
     {
       GemmP g = nt(dqkv, 3 * s.D, ws + w.wsp[l].in_t, 3 * s.D, gA, s.D, s.M2, s.D, 3 * s.D);
-      g.resid = gB; g.resid_ld = s.D;
+      g.resid = res; g.resid_ld = s.D;
       RD_TRY(linear_nt(g, ws + w.wsp[l].in_tlo, st));
     }
   }
+  if (!(phases & RD_BWD_OBPROP)) RD_TRY(wq.flush(st));   // encoder + head gradients complete: the caller may reduce them now
+  }
+
+  if (phases & RD_BWD_OBPROP) {
   // ---- observation propagation: gA = d(loss)/d(Z0) [T,B,D]          code/models_rd.py:322-343
   float* gO2 = sc + b.gO2; float* gO1 = sc + b.gO1;
   const float* X0 = ws + w.X0; const float* H1 = ws + w.H1;
   const int tc = obprop_tc_supported(s.C) ? 1 : 0;
   RD_TRY(obprop_out_grad(gA, ws + w.Z[0], nscale, s.B, s.T, s.N, s.dob, s.D, tc, gO2, st));
-  RD_TRY(tn(gO2, s.C, H1, s.C, G->ob2_value_weight, G->ob2_value_bias, s.C, s.C, s.M1, partial, st));
+  RD_TRY(tn(&wq, gO2, s.C, H1, s.C, G->ob2_value_weight, G->ob2_value_bias, s.C, s.C, s.M1, sc + b.wp_ob[0], partial, st));
   if (tc) {
     // dZ1 = (dZ2 . W2) * s * [H1 > 0] on the tensor cores: "NT" form against a transposed, TF32-rounded W2
     const float* W2t = ws + w.W2t;      // written by the forward's weight-prep launch
@@ -425,7 +465,9 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     g.rowscale = nscale; g.rowscale_mod = s.N; g.gate = H1; g.gate_ld = s.C;
     RD_TRY(gemm(g, st));
   }
-  RD_TRY(tn(gO1, s.C, X0, s.C, G->ob1_value_weight, G->ob1_value_bias, s.C, s.C, s.M1, partial, st));
+  RD_TRY(tn(&wq, gO1, s.C, X0, s.C, G->ob1_value_weight, G->ob1_value_bias, s.C, s.C, s.M1, sc + b.wp_ob[1], partial, st));
+  RD_TRY(wq.flush(st));
+  }
   return 0;
 }
 
@@ -472,7 +514,8 @@ int rd_obprop_fwd(const float* x, const float* weight, const float* bias, const 
 }
 
 size_t rd_obprop_bwd_scratch_bytes(int64_t rows, int32_t C) {
-  int64_t a = round_up(rows * C, 64) + round_up(tn_partial_floats(C, C, rows), 64) + round_up(colsum_scratch_floats(rows, C), 64);
+  int64_t tcp = tc_wgrad_partial_floats(C, C, rows), skp = splitk_partial_floats(C, C, rows);
+  int64_t a = round_up(rows * C, 64) + round_up(tcp > skp ? tcp : skp, 64);
   return (size_t)a * sizeof(float);
 }
 
@@ -486,10 +529,8 @@ int rd_obprop_bwd(const float* x, const float* out, const float* d_out, const fl
   cudaStream_t st = (cudaStream_t)stream;
   float* dpre = (float*)scratch;
   float* partial = dpre + round_up(rows * C, 64);
-  float* aux = partial + round_up(tn_partial_floats(C, C, rows), 64);
   RD_TRY(relu_scale_bwd(d_out, out, nscale, mod, rows, C, dpre, st));
-  (void)aux;
-  RD_TRY(tn(dpre, C, x, C, d_weight, d_bias, C, C, rows, partial, st));
+  RD_TRY(tn(nullptr, dpre, C, x, C, d_weight, d_bias, C, C, rows, partial, partial, st));
   if (d_x) RD_TRY(gemm(nn(dpre, C, weight, C, d_x, C, rows, C, C), st));
   return 0;
 }
@@ -511,6 +552,28 @@ int rd_linear_fwd(const float* x, const float* weight, const float* bias, int64_
   GemmP g = nt(x, in_features, weight, in_features, out, out_features, rows, out_features, in_features);
   g.bias = bias; g.relu = relu;
   return linear_nt(g, (const float*)scratch, st);
+}
+
+size_t rd_linear_wgrad_partial_bytes(int64_t rows, int32_t out_features, int32_t in_features) {
+  if (rows < 1 || out_features < 1 || in_features < 1) return 0;
+  int64_t a = tc_wgrad_partial_floats(out_features, in_features, rows), b = splitk_partial_floats(out_features, in_features, rows);
+  return (size_t)round_up(a > b ? a : b, 64) * sizeof(float);
+}
+
+int rd_linear_wgrad_group(const rd_wgrad_item* items, int32_t n, void* stream) {
+  if (!items || n < 0) { set_error("rd_linear_wgrad_group: bad arguments"); return -2; }
+  cudaStream_t st = (cudaStream_t)stream;
+  WgradQueue wq;
+  for (int i = 0; i < n; ++i) {
+    const rd_wgrad_item& it = items[i];
+    if (!it.d_out || !it.x || !it.d_weight || !it.d_bias || !it.partial || it.rows < 1 || it.out_features < 1 || it.in_features < 1) {
+      set_error("rd_linear_wgrad_group: problem %d has a NULL pointer or an empty shape", i);
+      return -2;
+    }
+    RD_TRY(tn(&wq, it.d_out, it.out_features, it.x, it.in_features, it.d_weight, it.d_bias, it.out_features, it.in_features,
+              it.rows, (float*)it.partial, (float*)it.partial, st));
+  }
+  return wq.flush(st);
 }
 
 size_t rd_workspace_bytes(const rd_dims* dims) {
@@ -545,24 +608,24 @@ int64_t rd_workspace_offset(const rd_dims* dims, int32_t which, int64_t* n_float
 
 int rd_raindrop_v2_fwd(const rd_dims* dims, const rd_params* params, const float* src, const float* statics,
                        const float* times, const int64_t* lengths, const float* node_scale, uint64_t* rng_state,
-                       void* workspace, float* logits, void* stream) {
+                       void* workspace, float* logits, const int64_t* y, float* loss, float* d_logits, void* stream) {
   if (!dims || !params || !src || !times || !lengths || !node_scale || !workspace || !logits) {
     set_error("rd_raindrop_v2_fwd: NULL argument");
     return -2;
   }
   return raindrop_fwd(dims, params, src, statics, times, lengths, node_scale, rng_state, (float*)workspace, logits,
-                      (cudaStream_t)stream);
+                      y, loss, d_logits, (cudaStream_t)stream);
 }
 
 int rd_raindrop_v2_bwd(const rd_dims* dims, const rd_params* params, const float* statics, const int64_t* lengths,
                        const float* node_scale, const void* workspace, const float* d_logits, const rd_grads* grads,
-                       void* scratch, void* stream) {
+                       void* scratch, int32_t phases, void* stream) {
   if (!dims || !params || !lengths || !node_scale || !workspace || !d_logits || !grads || !scratch) {
     set_error("rd_raindrop_v2_bwd: NULL argument");
     return -2;
   }
   return raindrop_bwd(dims, params, statics, lengths, node_scale, (const float*)workspace, d_logits, grads,
-                      (float*)scratch, (cudaStream_t)stream);
+                      (float*)scratch, phases, (cudaStream_t)stream);
 }
 
 int rd_positional_encoding(const float* times, int64_t n_tokens, const float* timescales_host, float* out,
@@ -584,11 +647,11 @@ int rd_cross_entropy_fwd_bwd(const float* logits, const int64_t* y, int32_t B, i
   return cross_entropy(logits, y, B, ncls, loss, d_logits, (cudaStream_t)stream);
 }
 
-int rd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr, float beta1,
-                 float beta2, float eps, float grad_scale, int64_t* step, void* stream) {
+int rd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float lr,
+                 const float* lr_dev, float beta1, float beta2, float eps, float grad_scale, int64_t* step, void* stream) {
   if (!param || !grad || !exp_avg || !exp_avg_sq || !step || n < 0) { set_error("rd_adam_step: bad arguments"); return -2; }
   if (n == 0) return 0;
-  return adam(param, grad, exp_avg, exp_avg_sq, n, lr, beta1, beta2, eps, grad_scale, step, (cudaStream_t)stream);
+  return adam(param, grad, exp_avg, exp_avg_sq, n, lr, lr_dev, beta1, beta2, eps, grad_scale, step, (cudaStream_t)stream);
 }
 
 int rd_debug_dropout_mask(const uint64_t* rng_captured, uint32_t site, int64_t n, float p, float* out, void* stream) {

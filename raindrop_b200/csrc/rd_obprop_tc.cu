@@ -309,13 +309,8 @@ int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st) {
   }
   int total = p.m_tiles * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
-  static bool attr_done[4] = {false, false, false, false};
-  auto launch = [&](auto kern, int id) -> int {
-    if (!attr_done[id]) {   // once per instantiation (and never inside a stream capture after warm-up)
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
-      attr_done[id] = true;
-    }
+  auto launch = [&](auto kern, int) -> int {
+    RD_TRY(ensure_max_smem((const void*)kern, SMEM_LIMIT));   // once per (instantiation, device)
     kern<<<grid, NTHREADS, smem_bytes, st>>>(tmA, tmW, tmOut, p);
     return 0;
   };

@@ -4,6 +4,8 @@
 #include <cuda.h>
 #include <stdint.h>
 
+#include <mutex>
+
 #include "rd_common.cuh"
 
 namespace rd {
@@ -143,17 +145,34 @@ inline int encode(CUtensorMap* m, const void* addr, int rank, const cuuint64_t* 
   return 0;
 }
 
-inline int num_sms() {
+// cudaFuncSetAttribute(max dynamic shared memory) once per (kernel, device): a process that touches a second
+// GPU has to opt in there as well (the attribute is per device).
+inline int ensure_max_smem(const void* fn, int bytes) {
+  struct Slot { const void* fn; int dev; };
+  static Slot done[256];
   static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
+  static std::mutex mu;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  for (int i = 0; i < n; ++i) if (done[i].fn == fn && done[i].dev == dev) return 0;
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
+  if (n < 256) { done[n].fn = fn; done[n].dev = dev; ++n; }
+  return 0;
 }
 
+inline int num_sms() {
+  static int n[16] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int slot = (dev >= 0 && dev < 16) ? dev : 0;
+  if (n[slot] == 0) {
+    cudaDeviceGetAttribute(&n[slot], cudaDevAttrMultiProcessorCount, dev);
+    if (n[slot] <= 0) n[slot] = 148;
+  }
+  return n[slot];
+}
 
 }  // namespace tc
 }  // namespace rd

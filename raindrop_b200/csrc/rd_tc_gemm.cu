@@ -252,28 +252,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
 }
 
 // =================================================================================================
-// weight-gradient kernel ("TN"): D[m, n] = sum_r A[r, m] * B[r, n] over this CTA's row range
+// weight-gradient kernel ("TN"), GROUPED: one launch serves up to WG_MAX independent problems
+//   D_k[m, n] = sum_r A_k[r, m] * B_k[r, n]   over this CTA's row range of problem k
+// A training step has ten of these (8 encoder weights + 2 lin_value); launched one by one each was a
+// ~20 us latency chain (2 k-blocks per CTA).  Grouped, every CTA owns >= 8 k-blocks, the loader warps
+// prefetch the next k-block's global loads before they transpose/store the current one, and the
+// launch + prologue latency is paid once.
 // =================================================================================================
 struct WP {
   const float* A; long long lda;     // dY [rows, M]
   const float* B; long long ldb;     // X  [rows, N]  (+ implicit ones column at n == N)
-  long long rows; int M, N, BN, n_tiles, m_tiles, nsplit, rows_per_split, nstages, Mpad;
+  float* partial;                    // [nsplit][Mpad][Nld]
+  float* dW; float* db;              // final outputs (wgrad_reduce_group)
+  long long rows; int M, N, BN, n_tiles, m_tiles, nsplit, rows_per_split, nstages, Mpad, Nld;
+  int cta0;                          // first CTA of this problem inside the grouped grid
 };
+struct WGroup { WP it[WG_MAX]; int n; };
 
 __device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-// loads a 4(r) x 4(col) block, returns it transposed: out[e] = 4 consecutive r values of column e
-__device__ __forceinline__ void load_block_t(const float* __restrict__ src, long long ld, long long r0, long long r_end,
-                                             int col, bool col_ok, float4 (&out)[4]) {
-  float4 in[4];
+// loads a 4(r) x 4(col) block (not yet transposed)
+__device__ __forceinline__ void load_block(const float* __restrict__ src, long long ld, long long r0, long long r_end,
+                                           int col, bool col_ok, float4 (&in)[4]) {
 #pragma unroll
   for (int j = 0; j < 4; ++j)
     in[j] = (col_ok && r0 + j < r_end) ? __ldg(reinterpret_cast<const float4*>(src + (r0 + j) * ld + col))
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
-  out[0] = make_float4(in[0].x, in[1].x, in[2].x, in[3].x);
-  out[1] = make_float4(in[0].y, in[1].y, in[2].y, in[3].y);
-  out[2] = make_float4(in[0].z, in[1].z, in[2].z, in[3].z);
-  out[3] = make_float4(in[0].w, in[1].w, in[2].w, in[3].w);
 }
 
 __device__ __forceinline__ void store_hi_lo(uint32_t hi_base, uint32_t lo_base, int row, int c, const float4& v) {
@@ -284,14 +288,17 @@ __device__ __forceinline__ void store_hi_lo(uint32_t hi_base, uint32_t lo_base, 
 }
 
 __global__ void __launch_bounds__(448, 1)
-tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const WP p) {
+tc_wgrad_kernel(const __grid_constant__ WGroup g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  int pi = 0;
+#pragma unroll 1
+  for (int k = 1; k < g.n; ++k) if ((int)blockIdx.x >= g.it[k].cta0) pi = k;
+  const WP& p = g.it[pi];
   const uint32_t b_tile = (uint32_t)p.BN * 128u;
   const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
-  const uint32_t stg_base = base + (uint32_t)p.nstages * stage_bytes;
-  const uint32_t bar_base = stg_base + 8 * STG_BYTES;
+  const uint32_t bar_base = base + (uint32_t)p.nstages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
   const uint32_t tfull_bar = bar_base + 8u * (2 * MAX_STAGES);
@@ -299,13 +306,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const WP p) {
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   // work item of this CTA: (split, m tile, n tile)
-  const int item = blockIdx.x;
+  const int item = (int)blockIdx.x - p.cta0;
   const int n_t = item % p.n_tiles, m_t = (item / p.n_tiles) % p.m_tiles, split = item / (p.n_tiles * p.m_tiles);
   const long long r_begin = (long long)split * p.rows_per_split;
   const long long r_end = min(p.rows, r_begin + p.rows_per_split);
   const int k_blocks = (int)((r_end - r_begin + BK - 1) / BK);
+  const int nstages = p.nstages;
 
-  if (warp == 0 && lane == 0) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmP) : "memory");
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 8); mbar_init(empty_bar(s), 1); }   // 8 loader warps
@@ -340,17 +347,15 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const WP p) {
           umma_tf32(tmem_base, a_hi + o, b_hi + o, idesc, 1u);
         }
         umma_commit(empty_bar(stage));
-        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
       umma_commit(tfull_bar);
     }
   } else if (warp >= 2 && warp < 6) {
-    // ===== epilogue: accumulator tile -> partial buffer ==============================================
+    // ===== epilogue: accumulator tile -> partial buffer (each lane owns one row: 128-byte runs) =======
     const int q = warp & 3;
-    const uint32_t my_stg = stg_base + (uint32_t)(warp - 2) * 2u * STG_BYTES;
     const int n_chunks = (p.BN + 31) / 32;
-    const int row0 = split * p.Mpad + m_t * BM + q * 32;
-    int buf = 0;
+    float* prow = p.partial + ((long long)split * p.Mpad + m_t * BM + q * 32 + lane) * p.Nld + n_t * p.BN;
     mbar_wait(tfull_bar, 0);
     tc_fence_after();
     for (int ch = 0; ch < n_chunks; ++ch) {
@@ -361,24 +366,13 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const WP p) {
 #pragma unroll
         for (int e = 0; e < 32; ++e) v[e] = 0u;
       }
-      if (lane == 0) bulk_wait_read<1>();
-      __syncwarp();
-      const uint32_t stg = my_stg + (uint32_t)buf * STG_BYTES;
 #pragma unroll
       for (int j4 = 0; j4 < 8; ++j4) {
-        const uint32_t off = (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) << 4));
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "r"(v[4 * j4]), "r"(v[4 * j4 + 1]),
-                     "r"(v[4 * j4 + 2]), "r"(v[4 * j4 + 3]) : "memory");
+        const int c = ch * 32 + 4 * j4;
+        if (c < p.BN)
+          *reinterpret_cast<uint4*>(prow + c) = make_uint4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
       }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) {
-        tma_store_2d(&tmP, stg, n_t * p.BN + ch * 32, row0);
-        bulk_commit();
-      }
-      buf ^= 1;
     }
-    if (lane == 0) bulk_wait_read<0>();
   }
   // ===== loaders: warps 6..9 handle the A (dY^T) tile, warps 10..13 the B (X^T) tile
   if (warp >= 6) {
@@ -393,22 +387,23 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const WP p) {
     const int tile_cols = isA ? BM : p.BN;
     const int nblk = (tile_cols / 4 + 15) / 16;          // 4-column blocks per thread (2 for A, <= 3 for B)
     int stage = 0; uint32_t phase = 0;
-    for (int kb = 0; kb < k_blocks; ++kb) {
+    float4 cur[3][4], nxt[3][4];
+    auto issue = [&](int kb, float4 (&blk)[3][4]) {
       const long long r0 = r_begin + (long long)kb * BK + 4 * c;
-      float4 blk[3][4];
 #pragma unroll
       for (int it = 0; it < 3; ++it) {
         if (it < nblk) {
-          const int g = g0 + 16 * it;
-          const int col = col_base + 4 * g;
-          load_block_t(src, ld, r0, r_end, col, 4 * g < tile_cols && col < col_lim, blk[it]);
-          if (!isA && col == p.N && 4 * g < tile_cols) {   // the ones column: db = sum_r dY[r, :] * 1
-            const float o0 = r0 + 0 < r_end ? 1.f : 0.f, o1 = r0 + 1 < r_end ? 1.f : 0.f;
-            const float o2 = r0 + 2 < r_end ? 1.f : 0.f, o3 = r0 + 3 < r_end ? 1.f : 0.f;
-            blk[it][0] = make_float4(o0, o1, o2, o3);
+          const int gq = g0 + 16 * it;
+          const int col = col_base + 4 * gq;
+          load_block(src, ld, r0, r_end, col, 4 * gq < tile_cols && col < col_lim, blk[it]);
+          if (!isA && col == p.N && 4 * gq < tile_cols) {   // the ones column: db = sum_r dY[r, :] * 1
+#pragma unroll
+            for (int j = 0; j < 4; ++j) blk[it][j] = make_float4(r0 + j < r_end ? 1.f : 0.f, 0.f, 0.f, 0.f);
           }
         }
       }
+    };
+    auto store = [&](const float4 (&blk)[3][4]) {
       mbar_wait(empty_bar(stage), phase ^ 1u);
       const uint32_t sa = base + (uint32_t)stage * stage_bytes;
       const uint32_t hi = isA ? sa : sa + 2u * A_TILE;
@@ -416,17 +411,27 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const WP p) {
 #pragma unroll
       for (int it = 0; it < 3; ++it) {
         if (it < nblk) {
-          const int g = g0 + 16 * it;
-          if (4 * g < tile_cols) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) store_hi_lo(hi, lo, 4 * g + e, c, blk[it][e]);
+          const int gq = g0 + 16 * it;
+          if (4 * gq < tile_cols) {   // transpose the 4x4 block in registers: column e of 4 consecutive rows
+            store_hi_lo(hi, lo, 4 * gq + 0, c, make_float4(blk[it][0].x, blk[it][1].x, blk[it][2].x, blk[it][3].x));
+            store_hi_lo(hi, lo, 4 * gq + 1, c, make_float4(blk[it][0].y, blk[it][1].y, blk[it][2].y, blk[it][3].y));
+            store_hi_lo(hi, lo, 4 * gq + 2, c, make_float4(blk[it][0].z, blk[it][1].z, blk[it][2].z, blk[it][3].z));
+            store_hi_lo(hi, lo, 4 * gq + 3, c, make_float4(blk[it][0].w, blk[it][1].w, blk[it][2].w, blk[it][3].w));
           }
         }
       }
       fence_async_smem();
       __syncwarp();
       if (lane == 0) mbar_arrive(full_bar(stage));
-      if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+      if (++stage == nstages) { stage = 0; phase ^= 1u; }
+    };
+    if (k_blocks > 0) issue(0, cur);
+    for (int kb = 0; kb < k_blocks; kb += 2) {     // the next k-block's loads are in flight while this one is stored
+      if (kb + 1 < k_blocks) issue(kb + 1, nxt);
+      store(cur);
+      if (kb + 1 >= k_blocks) break;
+      if (kb + 2 < k_blocks) issue(kb + 2, cur);
+      store(nxt);
     }
   }
   tc_fence_before();
@@ -437,15 +442,25 @@ tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmP, const WP p) {
   }
 }
 
-// dW[m, n] = sum_s partial[s][m][n] (n < N), db[m] = sum_s partial[s][m][N]; fixed order -> deterministic
-__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, int nsplit, int M, int N, int Mpad, int Nld,
-                                    float* __restrict__ dW, float* __restrict__ db) {
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= (long long)M * (N + 1)) return;
-  int m = (int)(i / (N + 1)), n = (int)(i - (long long)m * (N + 1));
+// dW[m, n] = sum_s partial[s][m][n] (n < N), db[m] = sum_s partial[s][m][N]; fixed order -> deterministic.
+// One launch for every problem of a group.
+struct RItem { const float* partial; float* dW; float* db; int nsplit, M, N, Mpad, Nld; long long start; };
+struct RGroup { RItem it[WG_MAX]; long long total; int n; };
+__global__ void wgrad_reduce_kernel(const __grid_constant__ RGroup g) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.total) return;
+  int k = 0;
+#pragma unroll 1
+  for (int j = 1; j < g.n; ++j) if (i >= g.it[j].start) k = j;
+  const RItem& r = g.it[k];
+  const long long e = i - r.start;
+  const int m = (int)(e / (r.N + 1)), n = (int)(e - (long long)m * (r.N + 1));
+  const float* src = r.partial + (long long)m * r.Nld + n;
+  const long long stride = (long long)r.Mpad * r.Nld;
   float s = 0.f;
-  for (int k = 0; k < nsplit; ++k) s += partial[((long long)k * Mpad + m) * Nld + n];
-  if (n < N) dW[(long long)m * N + n] = s; else if (db) db[m] = s;
+#pragma unroll 4
+  for (int sp = 0; sp < r.nsplit; ++sp) s += __ldg(src + sp * stride);
+  if (n < r.N) r.dW[(long long)m * r.N + n] = s; else if (r.db) r.db[m] = s;
 }
 
 struct WPlan { int BN, n_tiles, m_tiles, nsplit, rows_per_split, Mpad, Nld; };
@@ -457,20 +472,30 @@ WPlan wgrad_plan(int M, int N, long long rows) {
   w.n_tiles = (int)ceil_div(Ncols, MAX_BN);
   w.BN = w.n_tiles == 1 ? (int)round_up(Ncols, 16) : (int)round_up(ceil_div(Ncols, w.n_tiles), 32);
   w.Nld = (int)round_up(w.n_tiles * w.BN, 4);
+  // row splits: ~512 rows (16 k-blocks) per CTA so the pipeline amortises its fill, but never more than
+  // ~2 waves of CTAs per problem (bounds the partial buffer for the big configurations)
   const int mn = w.m_tiles * w.n_tiles;
-  int ns = num_sms() / mn;
+  long long ns = ceil_div(rows, 512);
+  const long long cap = (2 * num_sms()) / mn > 1 ? (2 * num_sms()) / mn : 1;
+  if (ns > cap) ns = cap;
   if (ns < 1) ns = 1;
-  const long long max_ns = ceil_div(rows, 64);
-  if (ns > max_ns) ns = (int)max_ns;
   w.rows_per_split = (int)round_up(ceil_div(rows, ns), BK);
   w.nsplit = (int)ceil_div(rows, w.rows_per_split);
   return w;
 }
 
-struct SplitItems { WeightSplit it[16]; long long start[17]; int n; };
+struct SplitItems { WeightSplit it[16]; long long start[17]; int n; StepPrologue pro; };
 
-__global__ void split_weights_kernel(SplitItems s) {
+__global__ void split_weights_kernel(const __grid_constant__ SplitItems s) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {     // step prologue riding along: dropout counter capture (+ advance) and ticket reset
+    if (s.pro.rng_state) {
+      s.pro.rng_captured[0] = s.pro.rng_state[0];
+      s.pro.rng_captured[1] = s.pro.rng_state[1];
+      if (s.pro.advance) s.pro.rng_state[1] = s.pro.rng_state[1] + 1;
+    }
+    if (s.pro.zero_counter) *s.pro.zero_counter = 0u;
+  }
   if (i >= s.start[s.n]) return;
   int t = 0;
   while (t + 1 < s.n && i >= s.start[t + 1]) ++t;
@@ -495,6 +520,9 @@ void plan(long long M, int N, int* BN, int* n_tiles) {
   *n_tiles = nt;
   *BN = nt == 1 ? (int)round_up(N, 16) : (int)round_up(ceil_div(N, nt), 32);
 }
+
+
+int ensure_attr(const void* fn, int) { return ensure_max_smem(fn, SMEM_LIMIT); }
 
 }  // namespace
 
@@ -539,13 +567,8 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
   RD_TRY(encode(&tmC, a.C, 2, cd, cs, cb, CU_TENSOR_MAP_SWIZZLE_128B, "C"));
   const int total = p.m_tiles * p.n_tiles;
   const int grid = total < num_sms() ? total : num_sms();
-  static bool attr_done[16] = {};
   auto launch = [&](auto kern, int id) -> int {
-    if (!attr_done[id]) {
-      cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-      if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
-      attr_done[id] = true;
-    }
+    RD_TRY(ensure_attr((const void*)kern, id));
     kern<<<grid, NTHREADS, smem_bytes, st>>>(tmB, tmBlo, tmC, p);
     return 0;
   };
@@ -576,50 +599,68 @@ bool tc_wgrad_supported(int Nout, int Kin, long long ldy, long long ldx, const v
 
 long long tc_wgrad_partial_floats(int Nout, int Kin, long long rows) {
   WPlan w = wgrad_plan(Nout, Kin, rows);
-  return (long long)w.nsplit * w.Mpad * w.Nld;
+  return round_up((long long)w.nsplit * w.Mpad * w.Nld, 64);
 }
 
-int tc_wgrad(const float* dY, long long ldy, const float* X, long long ldx, long long rows, int Nout, int Kin,
-             float* dW, float* db, float* partial, cudaStream_t st) {
-  if (!tc_wgrad_supported(Nout, Kin, ldy, ldx, dY, X) || !partial) { set_error("tc_wgrad: unsupported shape/alignment"); return -2; }
-  WPlan w = wgrad_plan(Nout, Kin, rows);
-  WP p;
-  p.A = dY; p.lda = ldy; p.B = X; p.ldb = ldx; p.rows = rows; p.M = Nout; p.N = Kin;
-  p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = w.m_tiles; p.nsplit = w.nsplit; p.rows_per_split = w.rows_per_split;
-  p.Mpad = w.Mpad;
-  const int stage_bytes = 2 * A_TILE + 2 * p.BN * 128;
-  const int fixed = 1024 + 8 * STG_BYTES + 256;
-  p.nstages = (SMEM_LIMIT - fixed) / stage_bytes;
-  if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
-  if (p.nstages < 2) { set_error("tc_wgrad: not enough shared memory"); return -2; }
-  const int smem_bytes = fixed + p.nstages * stage_bytes;
-  CUtensorMap tmP;
-  cuuint64_t pd[2] = {(cuuint64_t)w.Nld, (cuuint64_t)w.nsplit * w.Mpad};
-  cuuint64_t ps[1] = {(cuuint64_t)w.Nld * 4};
-  cuuint32_t pb[2] = {32, 32};
-  RD_TRY(encode(&tmP, partial, 2, pd, ps, pb, CU_TENSOR_MAP_SWIZZLE_128B, "wgrad partial"));
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(tc_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT);
-    if (e != cudaSuccess) { set_error("cudaFuncSetAttribute(smem): %s", cudaGetErrorString(e)); return -1; }
-    attr_set = true;
+int tc_wgrad_group(const WgradItem* items, int n, cudaStream_t st) {
+  if (n <= 0) return 0;
+  if (n > WG_MAX) { set_error("tc_wgrad_group: at most %d problems per launch", WG_MAX); return -2; }
+  WGroup g;
+  RGroup r;
+  g.n = n; r.n = n;
+  int cta = 0, smem_bytes = 0;
+  long long tot = 0;
+  for (int i = 0; i < n; ++i) {
+    const WgradItem& a = items[i];
+    if (!tc_wgrad_supported(a.Nout, a.Kin, a.ldy, a.ldx, a.dY, a.X) || !a.partial || a.rows < 1 ||
+        (reinterpret_cast<uintptr_t>(a.partial) & 15)) {
+      set_error("tc_wgrad_group: problem %d has an unsupported shape/alignment", i);
+      return -2;
+    }
+    const WPlan w = wgrad_plan(a.Nout, a.Kin, a.rows);
+    WP& p = g.it[i];
+    p.A = a.dY; p.lda = a.ldy; p.B = a.X; p.ldb = a.ldx; p.partial = a.partial; p.dW = a.dW; p.db = a.db;
+    p.rows = a.rows; p.M = a.Nout; p.N = a.Kin;
+    p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = w.m_tiles; p.nsplit = w.nsplit; p.rows_per_split = w.rows_per_split;
+    p.Mpad = w.Mpad; p.Nld = w.Nld;
+    const int stage_bytes = 2 * A_TILE + 2 * p.BN * 128;
+    const int fixed = 1024 + 256;
+    p.nstages = (SMEM_LIMIT - fixed) / stage_bytes;
+    if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
+    if (p.nstages < 2) { set_error("tc_wgrad_group: not enough shared memory"); return -2; }
+    const int sb = fixed + p.nstages * stage_bytes;
+    if (sb > smem_bytes) smem_bytes = sb;
+    p.cta0 = cta;
+    cta += w.nsplit * w.m_tiles * w.n_tiles;
+    RItem& q = r.it[i];
+    q.partial = a.partial; q.dW = a.dW; q.db = a.db; q.nsplit = w.nsplit; q.M = a.Nout; q.N = a.Kin; q.Mpad = w.Mpad; q.Nld = w.Nld;
+    q.start = tot;
+    tot += (long long)a.Nout * (a.Kin + 1);
   }
-  const int grid = w.nsplit * w.m_tiles * w.n_tiles;
-  tc_wgrad_kernel<<<grid, 448, smem_bytes, st>>>(tmP, p);
+  r.total = tot;
+  RD_TRY(ensure_attr((const void*)tc_wgrad_kernel, 15));
+  tc_wgrad_kernel<<<cta, 448, smem_bytes, st>>>(g);
   RD_CHECK_LAUNCH("tc_wgrad_kernel");
-  const long long n = (long long)Nout * (Kin + 1);
-  wgrad_reduce_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, st>>>(partial, w.nsplit, Nout, Kin, w.Mpad, w.Nld, dW, db);
+  wgrad_reduce_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(r);
   RD_CHECK_LAUNCH("wgrad_reduce_kernel");
   return 0;
 }
 
-int split_weights(const WeightSplit* items, int n, cudaStream_t st) {
-  if (n <= 0) return 0;
+int tc_wgrad(const float* dY, long long ldy, const float* X, long long ldx, long long rows, int Nout, int Kin,
+             float* dW, float* db, float* partial, cudaStream_t st) {
+  WgradItem it{dY, ldy, X, ldx, rows, Nout, Kin, dW, db, partial};
+  return tc_wgrad_group(&it, 1, st);
+}
+
+int split_weights(const WeightSplit* items, int n, cudaStream_t st, const StepPrologue* pro) {
+  if (n <= 0 && !pro) return 0;
   if (n > 16) { set_error("split_weights: at most 16 tensors per launch"); return -2; }
   SplitItems s;
   s.n = n; s.start[0] = 0;
   for (int i = 0; i < n; ++i) { s.it[i] = items[i]; s.start[i + 1] = s.start[i] + (long long)items[i].rows * items[i].cols; }
-  split_weights_kernel<<<(unsigned)ceil_div(s.start[n], 256), 256, 0, st>>>(s);
+  s.pro = pro ? *pro : StepPrologue{};
+  const long long total = s.start[n] > 0 ? s.start[n] : 1;
+  split_weights_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(s);
   RD_CHECK_LAUNCH("split_weights_kernel");
   return 0;
 }

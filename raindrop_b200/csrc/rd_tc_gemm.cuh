@@ -31,10 +31,19 @@ bool tc_wgrad_supported(int Nout, int Kin, long long ldy, long long ldx, const v
 long long tc_wgrad_partial_floats(int Nout, int Kin, long long rows);
 int tc_wgrad(const float* dY, long long ldy, const float* X, long long ldx, long long rows, int Nout, int Kin,
              float* dW, float* db, float* partial, cudaStream_t st);
+// Grouped form: ONE tensor-core launch + ONE reduction launch for up to WG_MAX independent problems
+// (each with its own `partial` buffer of tc_wgrad_partial_floats(...) floats, 16-byte aligned).
+constexpr int WG_MAX = 12;
+struct WgradItem { const float* dY; long long ldy; const float* X; long long ldx; long long rows; int Nout, Kin;
+                   float* dW; float* db; float* partial; };
+int tc_wgrad_group(const WgradItem* items, int n, cudaStream_t st);
 
 // One launch for all weights of a step: lo = W - trunc19(W); t = W^T; t_lo = W^T - trunc19(W^T).
 // optional extras for the single-pass-TF32 layers: rn = RN_tf32(W), rn_t = RN_tf32(W)^T
 struct WeightSplit { const float* w; int rows, cols; float* lo; float* t; float* t_lo; float* rn = nullptr; float* rn_t = nullptr; };
-int split_weights(const WeightSplit* items, int n, cudaStream_t st);   // n <= 16
+// Optional step prologue done by thread 0 of the same launch: capture {seed, counter} of the dropout stream into
+// rng_captured (advance != 0: counter += 1 afterwards) and zero one ticket word.
+struct StepPrologue { uint64_t* rng_state = nullptr; uint64_t* rng_captured = nullptr; int advance = 0; unsigned* zero_counter = nullptr; };
+int split_weights(const WeightSplit* items, int n, cudaStream_t st, const StepPrologue* pro = nullptr);   // n <= 16
 
 }  // namespace rd

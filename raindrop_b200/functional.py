@@ -13,16 +13,19 @@ _LAYER_KEYS = ["self_attn.in_proj_weight", "self_attn.in_proj_bias", "self_attn.
                "self_attn.out_proj.bias", "linear1.weight", "linear1.bias", "linear2.weight",
                "linear2.bias", "norm1.weight", "norm1.bias", "norm2.weight", "norm2.bias"]
 _HEAD_FIELDS = [("emb.weight", "emb_weight"), ("emb.bias", "emb_bias"),
-                ("ob_propagation.lin_value.weight", "ob1_value_weight"),
-                ("ob_propagation.lin_value.bias", "ob1_value_bias"),
-                ("ob_propagation_layer2.lin_value.weight", "ob2_value_weight"),
-                ("ob_propagation_layer2.lin_value.bias", "ob2_value_bias"),
                 ("mlp_static.0.weight", "mlp0_weight"), ("mlp_static.0.bias", "mlp0_bias"),
                 ("mlp_static.2.weight", "mlp2_weight"), ("mlp_static.2.bias", "mlp2_bias")]
+_OBPROP_FIELDS = [("ob_propagation.lin_value.weight", "ob1_value_weight"),
+                  ("ob_propagation.lin_value.bias", "ob1_value_bias"),
+                  ("ob_propagation_layer2.lin_value.weight", "ob2_value_weight"),
+                  ("ob_propagation_layer2.lin_value.bias", "ob2_value_bias")]
 
 
 def used_param_fields(nlayers, static):
-    """[(state-dict key, struct field path)] in Function-argument order."""
+    """[(state-dict key, struct field path)] in Function-argument = flat-bucket order.  The order is the order
+    in which the backward FINISHES gradients (head, encoder, then the two lin_value pairs), so that the bucket
+    splits into a front part that can be all-reduced while the observation-propagation backward still runs
+     and a tail part (`n_obprop_fields` entries)."""
     out = []
     for key, field in _HEAD_FIELDS:
         if not static and key.startswith("emb."):
@@ -31,7 +34,12 @@ def used_param_fields(nlayers, static):
     for l in range(nlayers):
         for k, f in zip(_LAYER_KEYS, L._LAYER_FIELDS):
             out.append(("transformer_encoder.layers.%d.%s" % (l, k), ("layer", l, f)))
+    for key, field in _OBPROP_FIELDS:
+        out.append((key, (field,)))
     return out
+
+
+N_OBPROP_FIELDS = len(_OBPROP_FIELDS)
 
 
 def _set_field(struct, path, value):
@@ -60,6 +68,9 @@ class Plan:
         self.R_u = None             # [1, N*d_ob] device tensor
         self.rng_state = None       # int64[2] device tensor {seed, counter}
         self.owner = None           # weakref to the module (receives the flat gradient bucket)
+        self.debug_keep_workspace = False   # tests: keep the last forward's workspace for workspace_view()
+        self.last_workspace = None
+        self.last_dims = None
 
     def dims(self, B, training):
         key = (B, bool(training))
@@ -121,24 +132,34 @@ class RaindropV2Function(torch.autograd.Function):
         ws_bytes, sc_bytes = ws_bytes
         if ws_bytes == 0:
             L.check(-2, "rd_workspace_bytes")
-        ws = torch.empty(ws_bytes // 4, dtype=torch.float32, device=src.device)
+        # activation workspace: recycled through a small per-(B, mode) pool (a forward whose backward has not run
+        # yet keeps its workspace; everything else reuses the last one instead of a fresh multi-MB allocation)
+        pool = plan.__dict__.setdefault("_ws_pool", {}).setdefault((B, bool(training), src.device.index), [])
+        ws = pool.pop() if pool else torch.empty(ws_bytes // 4, dtype=torch.float32, device=src.device)
         logits = torch.empty(B, plan.n_classes, dtype=torch.float32, device=src.device)
         rng = plan.rng_state
         rc = lib.rd_raindrop_v2_fwd(C.byref(dims), C.byref(P), src.data_ptr(), L.ptr(static), times.data_ptr(),
                                     lengths.data_ptr(), plan.node_scale.data_ptr(), L.ptr(rng), ws.data_ptr(),
-                                    logits.data_ptr(), L.stream_ptr())
+                                    logits.data_ptr(), None, None, None, L.stream_ptr(src.device))
         L.check(rc, "rd_raindrop_v2_fwd")
-        ctx.plan, ctx.dims, ctx.P, ctx.ws = plan, dims, P, ws
+        ctx.plan, ctx.dims, ctx.P, ctx.ws, ctx.pool = plan, dims, P, ws, pool
         ctx.keep = (keep, static, lengths, plan.node_scale, plan.R_u)
         ctx.sc_bytes = sc_bytes
-        plan.last_workspace = ws
-        plan.last_dims = dims
+        if plan.debug_keep_workspace:      # parity tests read named activation buffers (workspace_view)
+            plan.last_workspace = ws
+            plan.last_dims = dims
+        elif not any(ctx.needs_input_grad):
+            pool.append(ws)                # no backward will come: hand the workspace straight back
+            ctx.ws = None
         return logits
 
     @staticmethod
     def backward(ctx, d_logits):
         lib = L.load()
         plan, dims = ctx.plan, ctx.dims
+        if ctx.ws is None:
+            raise L.RaindropB200Error("backward called twice (or after a no-grad forward): the activation workspace of "
+                                      "this forward has been released; retain_graph is not supported")
         keep, static, lengths, node_scale, _ = ctx.keep
         d_logits = _as_f32(d_logits)
         dev = d_logits.device
@@ -151,7 +172,15 @@ class RaindropV2Function(torch.autograd.Function):
                 total += t.numel()
             layout = plan.__dict__["_grad_layout"] = (offs, total)
         offs, total = layout
-        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        owner = plan.owner() if plan.owner is not None else None
+        flat = None
+        # (a parameter that still holds a .grad would make autograd ACCUMULATE into it; if that .grad aliases the
+        # static bucket the kernel has just overwritten it, so only use the bucket when every .grad is None)
+        if owner is not None and owner._flat_grad_static is not None and owner._flat_grad_static.numel() == total \
+                and owner._flat_grad_static.device == dev and all(t.grad is None for t in params):
+            flat = owner._flat_grad_static          # raindrop_b200.optim.FlatAdam: gradients land in its bucket
+        if flat is None:
+            flat = torch.empty(total, dtype=torch.float32, device=dev)
         base = flat.data_ptr()
         cachedG = plan.__dict__.get("_grad_struct")
         if cachedG is not None and cachedG[0] == base:
@@ -161,15 +190,20 @@ class RaindropV2Function(torch.autograd.Function):
             for (key, path), off in zip(plan.fields, offs):
                 _set_field(G, path, base + 4 * off)
             plan.__dict__["_grad_struct"] = (base, G)
-        scratch = torch.empty(ctx.sc_bytes // 4, dtype=torch.float32, device=dev)
+        scs = plan.__dict__.setdefault("_scratch", {})
+        skey = (ctx.sc_bytes, dev.index)
+        scratch = scs.get(skey)
+        if scratch is None:                  # backward scratch holds nothing across calls: one buffer per size
+            scratch = scs[skey] = torch.empty(ctx.sc_bytes // 4, dtype=torch.float32, device=dev)
         rc = lib.rd_raindrop_v2_bwd(C.byref(dims), C.byref(ctx.P), L.ptr(static), lengths.data_ptr(),
                                     node_scale.data_ptr(), ctx.ws.data_ptr(), d_logits.data_ptr(), C.byref(G),
-                                    scratch.data_ptr(), L.stream_ptr())
+                                    scratch.data_ptr(), L.BWD_ALL, L.stream_ptr(dev))
         L.check(rc, "rd_raindrop_v2_bwd")
         grads = torch._utils._unflatten_dense_tensors(flat, params)      # views, one C++ call
-        owner = plan.owner() if plan.owner is not None else None
         if owner is not None:
             owner._flat_grad = flat          # the DDP bucket: one all-reduce covers every gradient
+        if not plan.debug_keep_workspace:
+            ctx.pool.append(ctx.ws)
         ctx.ws = None
         return (None, None, None, None, None, None) + tuple(grads)
 

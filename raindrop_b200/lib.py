@@ -10,6 +10,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "librd_b200.so")
 
 RD_MAX_LAYERS = 8
+ABI_VERSION = 2
+BWD_ENCODER, BWD_OBPROP, BWD_ALL = 1, 2, 3
 RD_D_PE = 16
 
 # enum rd_ws_buffer
@@ -56,6 +58,11 @@ class RdGrads(C.Structure):
                 ("layer", RdLayer * RD_MAX_LAYERS)]
 
 
+class RdWgradItem(C.Structure):
+    _fields_ = [("d_out", C.c_void_p), ("x", C.c_void_p), ("rows", C.c_int64), ("out_features", C.c_int32),
+                ("in_features", C.c_int32), ("d_weight", C.c_void_p), ("d_bias", C.c_void_p), ("partial", C.c_void_p)]
+
+
 # name -> (restype, argtypes); every symbol include/raindrop_b200.h declares
 SIGNATURES = {
     "rd_abi_version": (C.c_int, []),
@@ -76,15 +83,17 @@ SIGNATURES = {
     "rd_workspace_offset": (C.c_int64, [C.POINTER(RdDims), C.c_int32, C.POINTER(C.c_int64)]),
     "rd_raindrop_v2_fwd": (C.c_int, [C.POINTER(RdDims), C.POINTER(RdParams), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                     C.c_void_p, C.c_void_p]),
+                                     C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "rd_raindrop_v2_bwd": (C.c_int, [C.POINTER(RdDims), C.POINTER(RdParams), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RdGrads), C.c_void_p,
-                                     C.c_void_p]),
+                                     C.c_int32, C.c_void_p]),
     "rd_positional_encoding": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p,
                                          C.c_int64, C.c_int32, C.c_void_p]),
     "rd_linear_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rd_linear_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rd_linear_wgrad_partial_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
+    "rd_linear_wgrad_group": (C.c_int, [C.POINTER(RdWgradItem), C.c_int32, C.c_void_p]),
     "rd_transformer_conv_scratch_bytes": (C.c_size_t, [C.c_int32] * 5),
     "rd_transformer_conv_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] +
@@ -93,7 +102,7 @@ SIGNATURES = {
                                   C.c_void_p]),
     "rd_cross_entropy_fwd_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p,
                                            C.c_void_p, C.c_void_p]),
-    "rd_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float,
+    "rd_adam_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_float, C.c_void_p,
                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     "rd_debug_dropout_mask": (C.c_int, [C.c_void_p, C.c_uint32, C.c_int64, C.c_float, C.c_void_p,
                                         C.c_void_p]),
@@ -120,7 +129,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the header and the library disagree
         fn.restype = res
         fn.argtypes = args
-    if lib.rd_abi_version() != 1:
+    if lib.rd_abi_version() != ABI_VERSION:
         raise RaindropB200Error("ABI version mismatch: %d" % lib.rd_abi_version())
     _lib = lib
     return lib
@@ -137,6 +146,7 @@ def ptr(t):
     return 0 if t is None else t.data_ptr()
 
 
-def stream_ptr():
+def stream_ptr(device=None):
+    """cudaStream_t of torch's current stream on `device` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

@@ -207,6 +207,7 @@ class Raindrop_v2(nn.Module):
         self._plan.owner = weakref.ref(self)
         self._graph_key = None
         self._flat_grad = None
+        self._flat_grad_static = None     # set by raindrop_b200.optim.FlatAdam
         self._seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
 
     def init_weights(self):

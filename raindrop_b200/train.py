@@ -105,7 +105,12 @@ def evaluate_sharded(model, P, Pstatic, Ptime, group=None):
 
 
 class TrainStep:
-    """fwd + loss + bwd + (all-reduce) + Adam for a fixed batch size on static device buffers."""
+    """fwd + loss + bwd + (all-reduce) + Adam for a fixed batch size on static device buffers.
+
+    Data parallel (world > 1): the flat gradient bucket is ordered head | encoder | lin_value pairs.  The front part
+    is complete when `rd_raindrop_v2_bwd(RD_BWD_ENCODER)` returns, so its NCCL all-reduce is issued on a side
+    stream and runs while the observation-propagation backward (`RD_BWD_OBPROP`) computes the tail part
+    (SURVEY.md section 8e); the tail is reduced afterwards and both join before the Adam launch."""
 
     def __init__(self, model, batch_size, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, group=None, use_graph=True,
                  distributed=True):
@@ -116,7 +121,7 @@ class TrainStep:
             raise L.RaindropB200Error("TrainStep needs the model on a CUDA device")
         self.device = dev
         self.plan = model._prepare(dev)
-        self.lr, self.betas, self.eps = float(lr), betas, float(eps)
+        self.betas, self.eps = betas, float(eps)
         self.group = group
         self.world = dist.get_world_size(group) if (distributed and dist.is_initialized()) else 1
         # ---- flatten the used parameters into one bucket (views keep the nn.Parameters alive) ----
@@ -125,6 +130,7 @@ class TrainStep:
         for p in params:
             self.offsets.append(total)
             total += (p.numel() + 3) // 4 * 4
+        self.split = self.offsets[len(params) - RF.N_OBPROP_FIELDS]     # [0, split): head + encoder, [split, total): ob-prop
         self.flat_p = torch.zeros(total, dtype=torch.float32, device=dev)
         for p, off in zip(params, self.offsets):
             view = self.flat_p[off:off + p.numel()].view(p.shape)
@@ -133,7 +139,9 @@ class TrainStep:
         self.flat_g = torch.zeros_like(self.flat_p)
         self.exp_avg = torch.zeros_like(self.flat_p)
         self.exp_avg_sq = torch.zeros_like(self.flat_p)
-        self.step_count = torch.zeros(1, dtype=torch.int64, device=dev)
+        self.step_count = torch.zeros(2, dtype=torch.int64, device=dev)          # {count, ticket}
+        self.lr_dev = torch.full((1,), float(lr), dtype=torch.float32, device=dev)   # read by the Adam kernel every step
+        self._lr = float(lr)
         # ---- static I/O buffers ------------------------------------------------------------------
         T, N = self.plan.T, self.plan.N
         self.src = torch.zeros(T, self.B, 2 * N, dtype=torch.float32, device=dev)
@@ -153,9 +161,23 @@ class TrainStep:
             RF._set_field(self.G, path, self.flat_g.data_ptr() + 4 * off)
         self.ws = torch.empty(lib.rd_workspace_bytes(C.byref(self.dims)) // 4, dtype=torch.float32, device=dev)
         self.scratch = torch.empty(lib.rd_backward_scratch_bytes(C.byref(self.dims)) // 4, dtype=torch.float32, device=dev)
+        self.side = torch.cuda.Stream(device=dev) if self.world > 1 else None
         self.graph = None
         self.use_graph = use_graph
         self.kernel_launches = None
+
+    # learning rate lives in a device scalar, so a scheduler can change it under a captured graph
+    @property
+    def lr(self):
+        return self._lr
+
+    @lr.setter
+    def lr(self, value):
+        self.set_lr(value)
+
+    def set_lr(self, value):
+        self._lr = float(value)
+        self.lr_dev.fill_(self._lr)
 
     def load_batch(self, batch, non_blocking=True):
         """Host (pinned) or device tensors -> the static device buffers."""
@@ -166,32 +188,58 @@ class TrainStep:
         if self.static is not None:
             self.static.copy_(batch["static"], non_blocking=non_blocking)
 
+    def _bwd(self, phases, st):
+        L.check(self.lib.rd_raindrop_v2_bwd(C.byref(self.dims), C.byref(self.P), L.ptr(self.static), self.lengths.data_ptr(),
+                                            self.plan.node_scale.data_ptr(), self.ws.data_ptr(), self.d_logits.data_ptr(),
+                                            C.byref(self.G), self.scratch.data_ptr(), phases, st), "rd_raindrop_v2_bwd")
+
     def _enqueue(self):
-        lib, st = self.lib, L.stream_ptr()
+        lib, st = self.lib, L.stream_ptr(self.device)
+        # forward incl. CrossEntropyLoss + d(loss)/d(logits) (fused into the head kernel)
         L.check(lib.rd_raindrop_v2_fwd(C.byref(self.dims), C.byref(self.P), self.src.data_ptr(), L.ptr(self.static),
                                        self.times.data_ptr(), self.lengths.data_ptr(), self.plan.node_scale.data_ptr(),
-                                       self.plan.rng_state.data_ptr(), self.ws.data_ptr(), self.logits.data_ptr(), st),
+                                       self.plan.rng_state.data_ptr(), self.ws.data_ptr(), self.logits.data_ptr(),
+                                       self.y.data_ptr(), self.loss.data_ptr(), self.d_logits.data_ptr(), st),
                 "rd_raindrop_v2_fwd")
-        L.check(lib.rd_cross_entropy_fwd_bwd(self.logits.data_ptr(), self.y.data_ptr(), self.B, self.plan.n_classes,
-                                             self.loss.data_ptr(), self.d_logits.data_ptr(), st), "rd_cross_entropy_fwd_bwd")
-        L.check(lib.rd_raindrop_v2_bwd(C.byref(self.dims), C.byref(self.P), L.ptr(self.static), self.lengths.data_ptr(),
-                                       self.plan.node_scale.data_ptr(), self.ws.data_ptr(), self.d_logits.data_ptr(),
-                                       C.byref(self.G), self.scratch.data_ptr(), st), "rd_raindrop_v2_bwd")
         if self.world > 1:
-            dist.all_reduce(self.flat_g, group=self.group)
+            cur = torch.cuda.current_stream(self.device)
+            self._bwd(L.BWD_ENCODER, st)
+            self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side):           # bucket 1 hides behind the ob-prop backward
+                dist.all_reduce(self.flat_g[:self.split], group=self.group)
+            self._bwd(L.BWD_OBPROP, st)
+            dist.all_reduce(self.flat_g[self.split:], group=self.group)
+            cur.wait_stream(self.side)
+        else:
+            self._bwd(L.BWD_ALL, st)
         L.check(lib.rd_adam_step(self.flat_p.data_ptr(), self.flat_g.data_ptr(), self.exp_avg.data_ptr(),
-                                 self.exp_avg_sq.data_ptr(), self.flat_p.numel(), self.lr, self.betas[0], self.betas[1],
-                                 self.eps, 1.0 / self.world, self.step_count.data_ptr(), st), "rd_adam_step")
+                                 self.exp_avg_sq.data_ptr(), self.flat_p.numel(), self._lr, self.lr_dev.data_ptr(),
+                                 self.betas[0], self.betas[1], self.eps, 1.0 / self.world, self.step_count.data_ptr(), st),
+                "rd_adam_step")
+
+    def _snapshot(self):
+        return [t.clone() for t in (self.flat_p, self.exp_avg, self.exp_avg_sq, self.step_count, self.plan.rng_state,
+                                    self.loss, self.logits)]
+
+    def _restore(self, snap):
+        for t, s_ in zip((self.flat_p, self.exp_avg, self.exp_avg_sq, self.step_count, self.plan.rng_state,
+                          self.loss, self.logits), snap):
+            t.copy_(s_)
 
     def capture(self, warmup=3):
-        """Warm up on a side stream, then capture one step into a CUDA graph."""
+        """Warm up on a side stream, then capture one step into a CUDA graph.  Warm-up iterations are real
+        steps (they load modules, size NCCL channels, ...), so parameters, Adam moments, the step counter and
+        the dropout stream are snapshotted before and restored after: capture() has no effect on training."""
         s = torch.cuda.Stream(device=self.device)
-        s.wait_stream(torch.cuda.current_stream())
+        snap = self._snapshot() if warmup > 0 else None
+        s.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(s):
             for _ in range(warmup):
                 self._enqueue()
-        torch.cuda.current_stream().wait_stream(s)
-        torch.cuda.synchronize()
+            if snap is not None:
+                self._restore(snap)
+        torch.cuda.current_stream(self.device).wait_stream(s)
+        torch.cuda.synchronize(self.device)
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._enqueue()

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol():
     lib = L.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.rd_abi_version() == 1
+    assert lib.rd_abi_version() == L.ABI_VERSION
 
 
 def test_struct_layout_matches_header_sizes():
@@ -156,3 +156,28 @@ def test_root_module_is_the_drop_in():
                                         "MAX", "perc", "aggreg", "n_classes", "global_structure", "sensor_wise_mask",
                                         "static"]          # code/models_rd.py:208-209
     assert list(inspect.signature(ns["Raindrop_v2"].forward).parameters)[1:] == ["src", "static", "times", "lengths"]
+
+
+def test_launcher_beats_a_competing_models_rd(tmp_path):
+    """`python -m raindrop_b200.launch code/Raindrop.py` must import THIS implementation even though the script's
+    own directory holds a competing models_rd.py (sys.path[0] precedes PYTHONPATH) -- ADVICE r1."""
+    import subprocess
+    import sys
+    code = tmp_path / "code"
+    code.mkdir()
+    (code / "models_rd.py").write_text("WHO = 'reference'\n")
+    (code / "utils_x.py").write_text("HELPER = 41\n")
+    (code / "script.py").write_text(
+        "import os, sys\nfrom models_rd import *\nimport models_rd, utils_x\n"
+        "print('MODULE', os.path.abspath(models_rd.__file__))\nprint('HAS', 'Raindrop_v2' in globals(), utils_x.HELPER + 1)\n"
+        "print('CWD', os.getcwd())\nprint('ARGV', sys.argv[1:])\n")
+    env = dict(os.environ, PYTHONPATH=ROOT)
+    r = subprocess.run([sys.executable, "-m", "raindrop_b200.launch", str(code / "script.py"), "--dataset", "P19"],
+                       capture_output=True, text=True, env=env, cwd=str(tmp_path), timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = dict(ln.split(" ", 1) for ln in r.stdout.strip().splitlines() if " " in ln)
+    assert out["MODULE"] == os.path.join(ROOT, "raindrop_b200", "models_rd.py"), out
+    assert out["HAS"] == "True 42" and out["CWD"] == str(code) and out["ARGV"] == "['--dataset', 'P19']", out
+    # and the naive recipe indeed picks the competing file (the bug the launcher exists for)
+    r2 = subprocess.run([sys.executable, str(code / "script.py")], capture_output=True, text=True, env=env, timeout=300)
+    assert "MODULE " + str(code / "models_rd.py") in r2.stdout or r2.returncode != 0

@@ -47,6 +47,7 @@ def _run_dropin(cfg, batch, weight_seed, train=False):
     from raindrop_b200 import lib as L
     model = build_dropin(cfg, weight_seed)
     model.train(train)
+    model._plan.debug_keep_workspace = True
     d = to_dev(batch)
     logits, distance, third = model.forward(d["src"], d["static"], d["times"], d["lengths"])
     assert third is None and distance.dim() == 0
@@ -393,13 +394,112 @@ def test_cross_entropy_and_adam():
     assert abs(loss.item() - ref.item()) < 1e-6 and normwise(dl, lt.grad) < 1e-5
     p = torch.randn(1000, generator=g).cuda(); p_ref = torch.nn.Parameter(p.clone())
     opt = torch.optim.Adam([p_ref], lr=1e-2)
-    m = torch.zeros_like(p); v = torch.zeros_like(p); step = torch.zeros(1, dtype=torch.int64, device="cuda")
+    m = torch.zeros_like(p); v = torch.zeros_like(p); step = torch.zeros(2, dtype=torch.int64, device="cuda")   # {count, ticket}
+    lr_dev = torch.full((1,), 1e-2, device="cuda")
     for it in range(5):
         grad = torch.randn(1000, generator=g).cuda()
         p_ref.grad = grad.clone(); opt.step()
-        L.check(lib.rd_adam_step(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), 1000, 1e-2, 0.9, 0.999, 1e-8,
-                                 1.0, step.data_ptr(), L.stream_ptr()), "adam")
-    assert step.item() == 5 and normwise(p, p_ref.detach()) < 1e-5
+        # odd iterations read the learning rate from the device scalar (what a captured graph does)
+        L.check(lib.rd_adam_step(p.data_ptr(), grad.data_ptr(), m.data_ptr(), v.data_ptr(), 1000, 1e-2 if it % 2 == 0 else 123.0,
+                                 None if it % 2 == 0 else lr_dev.data_ptr(), 0.9, 0.999, 1e-8, 1.0, step.data_ptr(),
+                                 L.stream_ptr()), "adam")
+    assert step.tolist() == [5, 0] and normwise(p, p_ref.detach()) < 1e-5
+
+
+def test_fused_head_loss_matches_torch_cross_entropy():
+    """rd_raindrop_v2_fwd with labels: loss and d(loss)/d(logits) come out of the head kernel (CrossEntropyLoss,
+    mean reduction, code/Raindrop.py:322) -- compared with torch on the kernel's own logits, 2 and 8 classes."""
+    from raindrop_b200.train import TrainStep
+    for name, B in (("P19", 37), ("TINY8", 5)):
+        cfg = model_config(name, dropout=0.0)
+        ts = TrainStep(build_dropin(cfg, 3).train(), B, use_graph=False)
+        ts.load_batch(to_dev(make_batch(cfg, B, seed=9)))
+        ts.step()
+        lt = ts.logits.clone().requires_grad_(True)
+        ref = F.cross_entropy(lt, ts.y); ref.backward()
+        assert abs(ts.loss.item() - ref.item()) < 1e-6 * max(1.0, abs(ref.item())), (name, ts.loss.item(), ref.item())
+        assert normwise(ts.d_logits, lt.grad) < 1e-5
+
+
+def test_flat_adam_matches_torch_adam():
+    """raindrop_b200.optim.FlatAdam (one launch on the flat bucket) == torch.optim.Adam on the module path."""
+    from raindrop_b200.optim import FlatAdam
+    cfg = model_config("P19", dropout=0.0)
+    B = 16
+    m1 = build_dropin(cfg, 8).train(); m2 = build_dropin(cfg, 8).train()
+    o1 = torch.optim.Adam(m1.parameters(), lr=1e-3); o2 = FlatAdam(m2, lr=1e-3)
+    sched = torch.optim.lr_scheduler.StepLR(o2, step_size=2, gamma=0.5)        # it is a torch Optimizer
+    sched1 = torch.optim.lr_scheduler.StepLR(o1, step_size=2, gamma=0.5)
+    for it in range(4):
+        d = to_dev(make_batch(cfg, B, seed=70 + it))
+        losses = []
+        for m, o in ((m1, o1), (m2, o2)):
+            logits, _, _ = m.forward(d["src"], d["static"], d["times"], d["lengths"])
+            loss = F.cross_entropy(logits, d["y"])
+            o.zero_grad(); loss.backward(); o.step()
+            losses.append(loss.item())
+        sched.step(); sched1.step()
+        assert abs(losses[0] - losses[1]) < 2e-4 * max(1.0, abs(losses[0])), (it, losses)
+    assert o2._grads_in_bucket()          # the backward wrote straight into the optimiser's bucket (no gather)
+    p1, p2 = dict(m1.named_parameters()), dict(m2.named_parameters())
+    for k in used_param_keys(cfg):
+        assert rel_l2(p2[k], p1[k]) < 5e-3, k
+    # in-place zero_grad keeps .grad tensors alive: the bucket must then NOT be reused (autograd accumulates)
+    d = to_dev(make_batch(cfg, B, seed=99))
+    o2.zero_grad(set_to_none=False)
+    logits, _, _ = m2.forward(d["src"], d["static"], d["times"], d["lengths"])
+    F.cross_entropy(logits, d["y"]).backward()
+    g_a = {k: p2[k].grad.clone() for k in used_param_keys(cfg)}
+    o2.zero_grad()
+    logits, _, _ = m2.forward(d["src"], d["static"], d["times"], d["lengths"])
+    F.cross_entropy(logits, d["y"]).backward()
+    for k in used_param_keys(cfg):
+        assert torch.equal(g_a[k], p2[k].grad), k
+
+
+def test_default_capture_has_no_side_effects():
+    """TrainStep.step() with the DEFAULT implicit capture (3 warm-up iterations) must give the same trajectory as
+    the eager loop: warm-up is snapshotted/restored (parameters, Adam moments, step count, dropout stream)."""
+    from raindrop_b200.train import TrainStep
+    cfg = model_config("P19", dropout=0.2)
+    B = 16
+    a = TrainStep(build_dropin(cfg, 4).train(), B, lr=1e-3, use_graph=True)
+    b = TrainStep(build_dropin(cfg, 4).train(), B, lr=1e-3, use_graph=False)
+    for it in range(3):
+        d = to_dev(make_batch(cfg, B, seed=30 + it))
+        a.load_batch(d); b.load_batch(d)
+        la, lb = a.step().item(), b.step().item()
+        assert la == lb, (it, la, lb)
+    assert torch.equal(a.flat_p, b.flat_p) and a.step_count.tolist() == [3, 0]
+    # learning rate lives on the device: changing it after capture takes effect
+    a.set_lr(0.0); b.set_lr(0.0)
+    before = a.flat_p.clone()
+    a.step(); b.step()
+    assert torch.equal(a.flat_p, before) and torch.equal(b.flat_p, before)
+
+
+@pytest.mark.parametrize("shapes", [[(7680, 456, 152), (7680, 152, 152), (7680, 272, 152), (7680, 152, 272), (4352, 240, 240)],
+                                    [(300, 16, 64)], [(1000, 288, 160), (5000, 64, 1024), (777, 860, 860)]])
+def test_grouped_weight_gradients(shapes):
+    """rd_linear_wgrad_group: several dW = dY^T X (+ db) problems in ONE tensor-core launch, fp32-accurate."""
+    import ctypes as C
+    from raindrop_b200 import lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(3)
+    items = (L.RdWgradItem * len(shapes))()
+    keep, outs = [], []
+    for i, (rows, nout, kin) in enumerate(shapes):
+        dY = torch.randn(rows, nout, generator=g).cuda(); X = torch.randn(rows, kin, generator=g).cuda()
+        dW = torch.empty(nout, kin, device="cuda"); db = torch.empty(nout, device="cuda")
+        part = torch.empty(lib.rd_linear_wgrad_partial_bytes(rows, nout, kin) // 4, device="cuda")
+        items[i].d_out, items[i].x, items[i].rows, items[i].out_features, items[i].in_features = dY.data_ptr(), X.data_ptr(), rows, nout, kin
+        items[i].d_weight, items[i].d_bias, items[i].partial = dW.data_ptr(), db.data_ptr(), part.data_ptr()
+        keep.append((dY, X, part)); outs.append((dW, db))
+    L.check(lib.rd_linear_wgrad_group(items, len(shapes), L.stream_ptr()), "rd_linear_wgrad_group")
+    for (dY, X, _), (dW, db) in zip(keep, outs):
+        ref = dY.double().T @ X.double()
+        assert normwise(dW, ref) < 2e-5, normwise(dW, ref)
+        assert normwise(db, dY.double().sum(0)) < 2e-5
 
 
 # ---- training mode --------------------------------------------------------------------------------
@@ -413,6 +513,7 @@ def test_train_mode_dropout_statistics_and_replay():
     cfg = model_config("P19", dropout=0.2)
     batch = make_batch(cfg, 16, seed=1)
     model = build_dropin(cfg, 2).train()
+    model._plan.debug_keep_workspace = True
     d = to_dev(batch)
     out1, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
     x0_train = RF.workspace_view(model._plan, L.WS_X0).clone()
