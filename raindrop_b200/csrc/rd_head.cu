@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadP p, const float* __re
                                                       float* __restrict__ dlogits, float* __restrict__ loss,
                                                       unsigned* __restrict__ counter) {
   extern __shared__ float sm[];
-  float* fs = sm; float* hs = fs + p.Df; float* red = hs + p.Df;     // red: [8][D] pooling partials, later logits
+  float* fs = sm; float* hs = fs + p.Df; float* red = sm + ((2 * p.Df + 3) & ~3);     // red (16-byte aligned): [8][D] pooling partials, later logits
   __shared__ int s_last;
   const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* fb = feat + (long long)b * p.Df;
@@ -137,14 +137,12 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadP p, const float* __re
 // grid = B: dh = (dlogits . W2) * [h > 0];  dfeat = dh . W0;  d(encoder output)[t, b, :] = dfeat[:D] / (len+1) for t < len
 __global__ void __launch_bounds__(HT) head_bwd_sample_kernel(HeadP p, const float* __restrict__ hpre,
                                                              const float* __restrict__ dlogits, float* __restrict__ dh,
-                                                             float* __restrict__ dfeat, float* __restrict__ dx,
-                                                             unsigned* __restrict__ counters, int n_counters) {
+                                                             float* __restrict__ dfeat, float* __restrict__ dx) {
   extern __shared__ float sm[];
   float* ds_ = sm;                 // dh of this sample [Df]
   float* part = sm + p.Df;         // [groups][Df] partial dfeat
   float* df = part;                // final dfeat (group 0's row after the combine)
   const int b = blockIdx.x, tid = threadIdx.x;
-  if (b == 0 && counters) for (int i = tid; i < n_counters; i += HT) counters[i] = 0u;   // last-block tickets of this backward
   for (int j = tid; j < p.Df; j += HT) {
     float a = 0.f;
     for (int c = 0; c < p.ncls; ++c) a = fmaf(__ldg(dlogits + (long long)b * p.ncls + c), __ldg(p.w2 + (long long)c * p.Df + j), a);
@@ -249,7 +247,7 @@ int head_fwd(int B, int T, int D, int N, int ds, int ncls, const float* x, const
              unsigned* counter, cudaStream_t st) {
   HeadP p = make(B, T, D, N, ds, ncls, statics, emb_w, emb_b, w0, b0, w2, b2, lengths);
   const int red = 8 * D > ncls ? 8 * D : ncls;
-  const size_t smem = (size_t)(2 * p.Df + red) * sizeof(float);
+  const size_t smem = (size_t)(((2 * p.Df + 3) & ~3) + red) * sizeof(float);
   if (smem > 48 * 1024 || (D & 3)) { set_error("head_fwd: feature width %d not supported", p.Df); return -2; }
   if (y && (!loss_ps || !dlogits || !loss || !counter)) { set_error("head_fwd: labels given without loss outputs"); return -2; }
   head_fwd_kernel<<<B, HT, smem, st>>>(p, x, feat, hpre, logits, y, loss_ps, dlogits, loss, counter);
@@ -259,14 +257,13 @@ int head_fwd(int B, int T, int D, int N, int ds, int ncls, const float* x, const
 
 int head_bwd(int B, int T, int D, int N, int ds, int ncls, const int64_t* lengths, const float* statics, const float* w0,
              const float* w2, const float* feat, const float* hpre, const float* dlogits, float* dh, float* dfeat, float* dx,
-             float* g_w0, float* g_b0, float* g_w2, float* g_b2, float* g_emb_w, float* g_emb_b, unsigned* counters,
-             int n_counters, cudaStream_t st) {
+             float* g_w0, float* g_b0, float* g_w2, float* g_b2, float* g_emb_w, float* g_emb_b, cudaStream_t st) {
   HeadP p = make(B, T, D, N, ds, ncls, statics, nullptr, nullptr, w0, nullptr, w2, nullptr, lengths);
   const int kpad = p.Df >= HT ? HT : ((p.Df + 31) / 32) * 32;
   const int groups = HT / kpad;
   const size_t smem = (size_t)(1 + groups) * p.Df * sizeof(float);
   if (smem > 48 * 1024) { set_error("head_bwd: feature width %d too large", p.Df); return -2; }
-  head_bwd_sample_kernel<<<B, HT, smem, st>>>(p, hpre, dlogits, dh, dfeat, dx, counters, n_counters);
+  head_bwd_sample_kernel<<<B, HT, smem, st>>>(p, hpre, dlogits, dh, dfeat, dx);
   RD_CHECK_LAUNCH("head_bwd_sample_kernel");
   OuterGroup g;
   g.B = B; g.n = 0;

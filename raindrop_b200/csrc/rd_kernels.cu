@@ -81,7 +81,8 @@ __global__ void rng_capture_kernel(uint64_t* state, uint64_t* cap, int advance) 
 
 struct TS8 { float v[8]; };
 // One launch for the two element-wise producers of the forward's inputs:
-//   o <  n_lift : X0[(b*N+n), t*d_ob+k] = dropout(relu(src[t,b,n] * R_u[n*d_ob+k]))     code/models_rd.py:285-296,323-327
+//   o <  n_lift : X0[(b*N+n), t*d_ob + 0..d_ob) = dropout(relu(src[t,b,n] * R_u[n*d_ob + k]))   code/models_rd.py:285-296,323-327
+//                 (one thread per (row, t); for d_ob == 4 one 128-bit store and ONE Philox block per thread)
 //   o >= n_lift : positional encoding of token (o - n_lift) / 16 into out[tok*ld + col0 + j]   code/models_rd.py:28-43
 __global__ void lift_posenc_kernel(const float* __restrict__ src, const float* __restrict__ R_u, int B, int T, int N,
                                    int d_ob, float drop_p, const uint64_t* __restrict__ rng, int round,
@@ -89,18 +90,29 @@ __global__ void lift_posenc_kernel(const float* __restrict__ src, const float* _
                                    long long n_tokens, TS8 ts, float* __restrict__ pe_out, long long ld, int col0) {
   long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (o < n_lift) {
-    const long long C = (long long)T * d_ob;
-    long long row = o / C;
-    int c = (int)(o - row * C);
-    int b = (int)(row / N), n = (int)(row - (long long)b * N);
-    int t = c / d_ob, k = c - t * d_ob;
-    float v = __ldg(src + ((long long)t * B + b) * (2 * N) + n) * __ldg(R_u + n * d_ob + k);
-    v = fmaxf(v, 0.f);
-    if (drop_p > 0.f) {
-      uint64_t idx = ((uint64_t)t * B + b) * (uint64_t)(N * d_ob) + (uint64_t)(n * d_ob + k);
-      v *= dropout_scale(rng, SITE_LIFT, idx, drop_p, 1.f / (1.f - drop_p));
+    const long long row = o / T;
+    const int t = (int)(o - row * T);
+    const int b = (int)(row / N), n = (int)(row - (long long)b * N);
+    const float sv = __ldg(src + ((long long)t * B + b) * (2 * N) + n);
+    const float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+    const uint64_t idx0 = ((uint64_t)t * B + b) * (uint64_t)(N * d_ob) + (uint64_t)(n * d_ob);
+    float* dst = X0 + row * ((long long)T * d_ob) + (long long)t * d_ob;
+    if (d_ob == 4) {       // idx0 % 4 == 0: the four channels share one Philox block
+      const float4 r = __ldg(reinterpret_cast<const float4*>(R_u) + n);
+      float4 v = make_float4(fmaxf(sv * r.x, 0.f), fmaxf(sv * r.y, 0.f), fmaxf(sv * r.z, 0.f), fmaxf(sv * r.w, 0.f));
+      if (drop_p > 0.f) {
+        const float4 m = dropout_scale4(rng, SITE_LIFT, idx0, drop_p, ik);
+        v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+      }
+      if (round) v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      *reinterpret_cast<float4*>(dst) = v;
+    } else {
+      for (int k = 0; k < d_ob; ++k) {
+        float v = fmaxf(sv * __ldg(R_u + n * d_ob + k), 0.f);
+        if (drop_p > 0.f) v *= dropout_scale(rng, SITE_LIFT, idx0 + k, drop_p, ik);
+        dst[k] = round ? to_tf32(v) : v;
+      }
     }
-    X0[o] = round ? to_tf32(v) : v;
     return;
   }
   o -= n_lift;
@@ -165,10 +177,8 @@ constexpr int LNB_MAXIT = 5;    // D <= 640
 __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(
     const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ dy, long long rows, int D, float* __restrict__ dx, float* __restrict__ dx_drop,
-    float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial,
-    unsigned* __restrict__ counter, float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial) {
   extern __shared__ float lsm[];                     // [8 warps][2][D]
-  __shared__ int s_last;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
   float4 ag[LNB_MAXIT], ab[LNB_MAXIT];
@@ -232,40 +242,6 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(
     for (int w = 0; w < 8; ++w) s += lsm[w * 2 * D + c];     // c < D: dgamma column, else dbeta column
     partial[(long long)blockIdx.x * 2 * D + c] = s;
   }
-  if (!counter) return;
-  // ---- the last CTA to finish sums the per-CTA partial rows in a fixed order (deterministic) -----
-  __threadfence();
-  __syncthreads();
-  if (threadIdx.x == 0) s_last = (atomicAdd(counter, 1u) == gridDim.x - 1);
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int nq = (2 * D) >> 2;                         // float4 columns of a partial row
-  int groups = 256 / nq; if (groups > 8) groups = 8; if (groups < 1) groups = 1;
-  const int width = 256 / groups;                      // float4 columns handled per pass
-  const int nblk = (int)gridDim.x;
-  const int per = (nblk + groups - 1) / groups;
-  const int gq = threadIdx.x / width, cl = threadIdx.x % width;
-  for (int q0 = 0; q0 < nq; q0 += width) {
-    const int cq = q0 + cl;
-    if (gq < groups && cq < nq) {
-      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-      const int r0 = gq * per, r1 = min(nblk, r0 + per);
-#pragma unroll 8
-      for (int r = r0; r < r1; ++r) {
-        const float4 v = __ldcg(reinterpret_cast<const float4*>(partial + (long long)r * 2 * D) + cq);
-        a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-      }
-      *reinterpret_cast<float4*>(lsm + gq * 2 * D + 4 * cq) = a;
-    }
-  }
-  __syncthreads();
-  for (int c = threadIdx.x; c < 2 * D; c += blockDim.x) {
-    float sacc = 0.f;
-    for (int k = 0; k < groups; ++k) sacc += lsm[k * 2 * D + c];
-    if (c < D) dgamma[c] = sacc; else dbeta[c - D] = sacc;
-  }
-  if (threadIdx.x == 0) *counter = 0u;
 }
 
 __global__ void layernorm_bwd_dx_kernel(const float* __restrict__ x, const float* __restrict__ stats,
@@ -529,7 +505,7 @@ int gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_tota
 int lift_posenc(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p, const uint64_t* rng,
                 int round, float* X0, const float* times, int64_t n_tokens, const float* ts8_host, float* pe_out, int64_t ld,
                 int col0, cudaStream_t st) {
-  const int64_t n_lift = src ? (int64_t)B * N * T * d_ob : 0;
+  const int64_t n_lift = src ? (int64_t)B * N * T : 0;      // one thread per (row, t)
   const int64_t n_pe = times ? n_tokens * 16 : 0;
   TS8 ts;
   if (times) memcpy(ts.v, ts8_host, sizeof(ts.v)); else memset(ts.v, 0, sizeof(ts.v));
@@ -565,26 +541,27 @@ int64_t ln_bwd_scratch_floats(int64_t rows, int D) {
 
 int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows, int D,
                   float* dx, float* dgamma, float* dbeta, float* scratch, float* dx_drop, float drop_p,
-                  const uint64_t* rng, uint32_t site, unsigned* counter, cudaStream_t st) {
+                  const uint64_t* rng, uint32_t site, int* deferred_chunks, cudaStream_t st) {
   const uintptr_t bits = reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
                          reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_drop);
+  int chunks;
   if ((D & 3) == 0 && D <= 128 * LNB_MAXIT && (bits & 15) == 0) {     // fused single pass
-    const int chunks = (int)ceil_div(rows, LNB_ROWS);
+    chunks = (int)ceil_div(rows, LNB_ROWS);
     layernorm_bwd_fused_kernel<<<chunks, 256, 8 * 2 * D * sizeof(float), st>>>(
-        x, stats, gamma, dy, rows, D, dx, drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site, scratch, counter, dgamma, dbeta);
+        x, stats, gamma, dy, rows, D, dx, drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site, scratch);
     RD_CHECK_LAUNCH("layernorm_bwd_fused_kernel");
-    if (counter) return 0;          // reduced by the last CTA of the launch above
-    return reduce_partials2(scratch, chunks, D, dgamma, D, dbeta, st);
+  } else {
+    layernorm_bwd_dx_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, stats, gamma, dy, rows, D, dx,
+                                                                drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site);
+    RD_CHECK_LAUNCH("layernorm_bwd_dx_kernel");
+    chunks = (int)ceil_div(rows, LN_ROWS);
+    if (chunks > 65535) { set_error("layernorm_bwd: too many row chunks"); return -2; }
+    dim3 grid((unsigned)ceil_div(D, 32), (unsigned)chunks);
+    layernorm_bwd_param_kernel<<<grid, dim3(32, 8), 0, st>>>(x, stats, dy, rows, D, scratch);
+    RD_CHECK_LAUNCH("layernorm_bwd_param_kernel");
   }
-  layernorm_bwd_dx_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, stats, gamma, dy, rows, D, dx,
-                                                              drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site);
-  RD_CHECK_LAUNCH("layernorm_bwd_dx_kernel");
-  int chunks = (int)ceil_div(rows, LN_ROWS);
-  if (chunks > 65535) { set_error("layernorm_bwd: too many row chunks"); return -2; }
-  dim3 grid((unsigned)ceil_div(D, 32), (unsigned)chunks);
-  layernorm_bwd_param_kernel<<<grid, dim3(32, 8), 0, st>>>(x, stats, dy, rows, D, scratch);
-  RD_CHECK_LAUNCH("layernorm_bwd_param_kernel");
-  // [chunk][2][D] -> dgamma, dbeta in one deterministic pass
+  // scratch = [chunks][2][D] partial column sums -> dgamma, dbeta (fixed order, deterministic)
+  if (deferred_chunks) { *deferred_chunks = chunks; return 0; }     // the caller folds this into a later reduction launch
   return reduce_partials2(scratch, chunks, D, dgamma, D, dbeta, st);
 }
 

@@ -33,11 +33,11 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t
 int64_t ln_bwd_scratch_floats(int64_t rows, int D);
 // dx_drop (optional, used when drop_p > 0): dx with the dropout mask of `site` re-applied, i.e. the
 // gradient w.r.t. the sub-layer output that was dropped before the residual add
-// counter != nullptr: the per-CTA partial rows are summed by the last CTA of the same launch (ticket in *counter,
-// which must be 0 on entry and is reset to 0); otherwise a second launch reduces them
+// deferred_chunks != nullptr: the reduction of the per-CTA partial rows scratch[chunks][2][D] is left to the caller
+// (*deferred_chunks = chunks), who folds it into a later grouped reduction launch (tc_wgrad_group)
 int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows,
                   int D, float* dx, float* dgamma, float* dbeta, float* scratch, float* dx_drop, float drop_p,
-                  const uint64_t* rng, uint32_t site, unsigned* counter, cudaStream_t st);
+                  const uint64_t* rng, uint32_t site, int* deferred_chunks, cudaStream_t st);
 
 // in-place masked softmax over rows of S [B,H,T,T]; key j masked when j >= lengths[b].
 // If Pd != nullptr also writes the dropped probabilities (training).
@@ -54,11 +54,10 @@ int head_fwd(int B, int T, int D, int N, int ds, int ncls, const float* x, const
              const float* emb_w, const float* emb_b, const float* w0, const float* b0, const float* w2, const float* b2,
              float* feat, float* hpre, float* logits, const int64_t* y, float* loss_ps, float* dlogits, float* loss,
              unsigned* counter, cudaStream_t st);
-// dx = d(loss)/d(encoder output) [T, B, D] (masked-mean backward); also zeroes `counters[0..n_counters)`
+// dx = d(loss)/d(encoder output) [T, B, D] (masked-mean backward)
 int head_bwd(int B, int T, int D, int N, int ds, int ncls, const int64_t* lengths, const float* statics, const float* w0,
              const float* w2, const float* feat, const float* hpre, const float* dlogits, float* dh, float* dfeat, float* dx,
-             float* g_w0, float* g_b0, float* g_w2, float* g_b2, float* g_emb_w, float* g_emb_b, unsigned* counters,
-             int n_counters, cudaStream_t st);
+             float* g_w0, float* g_b0, float* g_w2, float* g_b2, float* g_emb_w, float* g_emb_b, cudaStream_t st);
 
 // fused attention for short sequences (rd_attn_small.cu): ctx from qkv in one launch, dqkv in one launch
 bool attn_small_supported(int T, int hd);

@@ -97,13 +97,11 @@ WsLayout ws_layout(const Shape& s) {
 // its own buffer until one grouped tensor-core launch (tc_wgrad_group) reduces them all, so dY buffers and the
 // split-K partial buffers are per layer / per problem instead of ping-pong.
 struct BwLayout {
-  int64_t cnt, dfeat, dhpre, gA, gB, gD, dP, gO2, gO1, partial, aux, total;
-  struct { int64_t K2, gF, K1, dqkv, wp[4]; } l[RD_MAX_LAYERS];   // wp: linear2, linear1, out_proj, in_proj partials
+  int64_t dfeat, dhpre, gA, gB, gD, dP, gO2, gO1, partial, total;
+  struct { int64_t K2, gF, K1, dqkv, wp[4], ln[2]; } l[RD_MAX_LAYERS];   // wp: linear2, linear1, out_proj, in_proj partials; ln: norm2, norm1
   int64_t wp_ob[2];
-  int64_t partial_floats, aux_floats;
+  int64_t partial_floats;
 };
-
-constexpr int N_COUNTERS = 64;
 
 int64_t splitk_partial_floats(int Nout, int Kin, int64_t rows) {
   int ns;
@@ -113,7 +111,6 @@ int64_t splitk_partial_floats(int Nout, int Kin, int64_t rows) {
 BwLayout bw_layout(const Shape& s) {
   BwLayout b;
   Arena a;
-  b.cnt = a.take(N_COUNTERS);
   b.dfeat = a.take((int64_t)s.B * s.Df);
   b.dhpre = a.take((int64_t)s.B * s.Df);
   b.gA = a.take(s.M2 * s.D);
@@ -129,6 +126,8 @@ BwLayout bw_layout(const Shape& s) {
     b.l[l].wp[1] = a.take(tc_wgrad_partial_floats(s.nhid, s.D, s.M2));
     b.l[l].wp[2] = a.take(tc_wgrad_partial_floats(s.D, s.D, s.M2));
     b.l[l].wp[3] = a.take(tc_wgrad_partial_floats(3 * s.D, s.D, s.M2));
+    b.l[l].ln[0] = a.take(ln_bwd_scratch_floats(s.M2, s.D));      // per-CTA dgamma/dbeta partial rows, reduced with the group
+    b.l[l].ln[1] = a.take(ln_bwd_scratch_floats(s.M2, s.D));
   }
   b.gO2 = a.take(s.M1 * s.C);
   b.gO1 = a.take(s.M1 * s.C);
@@ -141,9 +140,6 @@ BwLayout bw_layout(const Shape& s) {
   upd(3 * s.D, s.D, s.M2); upd(s.D, s.D, s.M2); upd(s.nhid, s.D, s.M2); upd(s.D, s.nhid, s.M2);
   b.partial_floats = pf;
   b.partial = a.take(pf);
-  int64_t af = ln_bwd_scratch_floats(s.M2, s.D);
-  b.aux_floats = af;
-  b.aux = a.take(af);
   b.total = a.off;
   return b;
 }
@@ -170,12 +166,19 @@ GemmP nn(const float* dY, int64_t ldy, const float* W, int64_t ldw, float* dX, i
 // the shape fits, else done right away on the CUDA cores (split over rows, deterministic two-stage reduce).
 struct WgradQueue {
   WgradItem it[WG_MAX];
-  int n = 0;
+  ColsumItem cs[CS_MAX];
+  int n = 0, ncs = 0;
   int flush(cudaStream_t st) {
-    if (n == 0) return 0;
-    int rc = tc_wgrad_group(it, n, st);
-    n = 0;
+    if (n == 0 && ncs == 0) return 0;
+    int rc = tc_wgrad_group(it, n, cs, ncs, st);
+    n = 0; ncs = 0;
     return rc;
+  }
+  // out[c] = sum over the chunks of partial[chunk*stride + c]: reduced by the group's reduction launch
+  int colsum(const float* partial, long long stride, int nsplit, int ncols, float* out, cudaStream_t st) {
+    if (ncs == CS_MAX) RD_TRY(flush(st));
+    cs[ncs++] = ColsumItem{partial, stride, nsplit, ncols, out};
+    return 0;
   }
 };
 
@@ -350,8 +353,7 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
   WsLayout w = ws_layout(s);
   BwLayout b = bw_layout(s);
   const uint64_t* rng = reinterpret_cast<const uint64_t*>(ws + w.rng);
-  float* partial = sc + b.partial; float* aux = sc + b.aux;
-  unsigned* counters = reinterpret_cast<unsigned*>(sc + b.cnt);
+  float* partial = sc + b.partial;
   const float ik = s.p > 0.f ? 1.f / (1.f - s.p) : 1.f;
   float* gA = sc + b.gA; float* gB = sc + b.gB; float* gD = sc + b.gD; float* dP = sc + b.dP;
   WgradQueue wq;     // weight gradients wait here for ONE grouped tensor-core launch per phase
@@ -361,8 +363,7 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
   const float* feat = ws + w.feat; const float* hpre = ws + w.hpre;
   float* dfeat = sc + b.dfeat; float* dhpre = sc + b.dhpre;
   RD_TRY(head_bwd(s.B, s.T, s.D, s.N, s.ds, s.ncls, lengths, statics, P->mlp0_weight, P->mlp2_weight, feat, hpre, dlogits,
-                  dhpre, dfeat, gA, G->mlp0_weight, G->mlp0_bias, G->mlp2_weight, G->mlp2_bias, G->emb_weight, G->emb_bias,
-                  counters, N_COUNTERS, st));
+                  dhpre, dfeat, gA, G->mlp0_weight, G->mlp0_bias, G->mlp2_weight, G->mlp2_bias, G->emb_weight, G->emb_bias, st));
 
   const float scale = 1.f / sqrtf((float)s.hd);
   const int64_t row3 = (int64_t)s.B * 3 * s.D;
@@ -379,8 +380,11 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     // norm2 + feed-forward block.  K2 = gradient w.r.t. the (dropped) linear2 output: operand of its weight
     // gradient, kept until the grouped launch; res = the undropped residual-path gradient
     float* res = s.p > 0.f ? gB : K2;
-    RD_TRY(layernorm_bwd(r2, ws + w.l[l].st2, E.norm2_weight, gA, s.M2, s.D, res, GE.norm2_weight, GE.norm2_bias, aux,
-                         K2, s.p, rng, SITE_RESID2 + l, counters + 2 * l, st));
+    int chunks = 0;
+    RD_TRY(layernorm_bwd(r2, ws + w.l[l].st2, E.norm2_weight, gA, s.M2, s.D, res, GE.norm2_weight, GE.norm2_bias,
+                         sc + b.l[l].ln[0], K2, s.p, rng, SITE_RESID2 + l, &chunks, st));
+    RD_TRY(wq.colsum(sc + b.l[l].ln[0], 2 * s.D, chunks, s.D, GE.norm2_weight, st));
+    RD_TRY(wq.colsum(sc + b.l[l].ln[0] + s.D, 2 * s.D, chunks, s.D, GE.norm2_bias, st));
     RD_TRY(tn(&wq, K2, s.D, f, s.nhid, GE.linear2_weight, GE.linear2_bias, s.D, s.nhid, s.M2, sc + b.l[l].wp[0], partial, st));
     {   // gF = (K2 . W2) * [f > 0] / (1-p)   ("NT" against W2^T so that the tensor-core kernel applies)
       GemmP g = nt(K2, s.D, ws + w.wsp[l].l2_t, s.D, gF, s.nhid, s.M2, s.nhid, s.D);
@@ -395,8 +399,10 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     }
     // norm1 + self-attention block
     res = s.p > 0.f ? gB : K1;
-    RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, res, GE.norm1_weight, GE.norm1_bias, aux,
-                         K1, s.p, rng, SITE_RESID1 + l, counters + 2 * l + 1, st));
+    RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, res, GE.norm1_weight, GE.norm1_bias,
+                         sc + b.l[l].ln[1], K1, s.p, rng, SITE_RESID1 + l, &chunks, st));
+    RD_TRY(wq.colsum(sc + b.l[l].ln[1], 2 * s.D, chunks, s.D, GE.norm1_weight, st));
+    RD_TRY(wq.colsum(sc + b.l[l].ln[1] + s.D, 2 * s.D, chunks, s.D, GE.norm1_bias, st));
     RD_TRY(tn(&wq, K1, s.D, ctx, s.D, GE.out_proj_weight, GE.out_proj_bias, s.D, s.D, s.M2, sc + b.l[l].wp[2], partial, st));
     RD_TRY(linear_nt(nt(K1, s.D, ws + w.wsp[l].out_t, s.D, gD, s.D, s.M2, s.D, s.D), ws + w.wsp[l].out_tlo, st));
     if (attn_small_supported(s.T, s.hd)) {

@@ -138,11 +138,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       const int row0 = m_t * BM + q * 32;
       const long long row = (long long)row0 + lane;
       const bool row_ok = row < p.M;
+      // gate / residual operands of chunk ch are fetched one chunk AHEAD (chunk 0 before the accumulator is even
+      // complete): their L2 round trips used to sit, one per chunk, on the critical path of the epilogue
+      float4 pg[8], pr[8];
+      auto prefetch = [&](int ch) {
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int c = col0 + ch * 32 + 4 * j4;
+          const bool ok = row_ok && c < p.N && ch * 32 + 4 * j4 < p.BN;
+          if (GATE) pg[j4] = ok ? __ldg(reinterpret_cast<const float4*>(p.gate + row * p.gate_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          if (RESID) pr[j4] = ok ? __ldg(reinterpret_cast<const float4*>(p.resid + row * p.resid_ld + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      };
+      if (GATE || RESID) prefetch(0);
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
       for (int ch = 0; ch < n_chunks; ++ch) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + ch * 32), v);
+        float4 cg[8], cr[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) { if (GATE) cg[j4] = pg[j4]; if (RESID) cr[j4] = pr[j4]; }
+        if ((GATE || RESID) && ch + 1 < n_chunks) prefetch(ch + 1);
         const float* bs = bias_s + acc * 256 + ch * 32;
         const int c0 = col0 + ch * 32;
         if (lane == 0) bulk_wait_read<1>();
@@ -159,7 +176,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             o[e] = RELU ? fmaxf(x, 0.f) : x;
           }
           if (GATE && ok) {
-            float4 g = __ldg(reinterpret_cast<const float4*>(p.gate + row * p.gate_ld + c));
+            const float4 g = cg[j4];
             o[0] = g.x > 0.f ? o[0] * p.gate_scale : 0.f; o[1] = g.y > 0.f ? o[1] * p.gate_scale : 0.f;
             o[2] = g.z > 0.f ? o[2] * p.gate_scale : 0.f; o[3] = g.w > 0.f ? o[3] * p.gate_scale : 0.f;
           }
@@ -168,7 +185,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
             o[0] *= m.x; o[1] *= m.y; o[2] *= m.z; o[3] *= m.w;
           }
           if (RESID && ok) {
-            float4 r = __ldg(reinterpret_cast<const float4*>(p.resid + row * p.resid_ld + c));
+            const float4 r = cr[j4];
             o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
           }
           const uint32_t off = (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) << 4));
@@ -259,35 +276,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
 // prefetch the next k-block's global loads before they transpose/store the current one, and the
 // launch + prologue latency is paid once.
 // =================================================================================================
+// Both operands are row-major activations [rows, cols] and the contraction runs over ROWS, i.e. they are
+// "MN-major" from the tensor core's point of view.  tcgen05 takes MN-major TF32 operands directly (instruction
+// descriptor bits 15/16), so the tiles go global -> shared memory by TMA exactly as they lie in memory:
+//   box {32 columns, 32 rows} with the 128B swizzle  ==  canonical MN-major SW128 atom ((4,8,m),(8,k)):((1,4,LBO),(32,SBO))
+//   (one 128-byte line = 32 consecutive columns of one row; 8 rows = one K group of 1024 B; the next 32 columns are
+//   the next box, LBO = 4096 B apart).  No register transposes; four warps only derive the error-compensation
+// remainders lo = x - trunc19(x) (same addresses, so the swizzle never has to be undone) and plant the "ones"
+// column that makes the bias gradient fall out of the same MMAs.
 struct WP {
-  const float* A; long long lda;     // dY [rows, M]
-  const float* B; long long ldb;     // X  [rows, N]  (+ implicit ones column at n == N)
   float* partial;                    // [nsplit][Mpad][Nld]
-  float* dW; float* db;              // final outputs (wgrad_reduce_group)
   long long rows; int M, N, BN, n_tiles, m_tiles, nsplit, rows_per_split, nstages, Mpad, Nld;
   int cta0;                          // first CTA of this problem inside the grouped grid
 };
-struct WGroup { WP it[WG_MAX]; int n; };
+struct WGroup { CUtensorMap tmA[WG_MAX]; CUtensorMap tmB[WG_MAX]; WP it[WG_MAX]; int n; };
+
+constexpr int W_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 remainder pass + epilogue
+constexpr int MN_BOX = 32 * 32 * 4;  // one {32 col, 32 row} fp32 box = 4096 bytes
 
 __device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
-// loads a 4(r) x 4(col) block (not yet transposed)
-__device__ __forceinline__ void load_block(const float* __restrict__ src, long long ld, long long r0, long long r_end,
-                                           int col, bool col_ok, float4 (&in)[4]) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-    in[j] = (col_ok && r0 + j < r_end) ? __ldg(reinterpret_cast<const float4*>(src + (r0 + j) * ld + col))
-                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
+  // start | LBO = 4096 B (next 32-column group) | SBO = 1024 B (next 8-row K group) | version 1 | SWIZZLE_128B
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(MN_BOX >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-__device__ __forceinline__ void store_hi_lo(uint32_t hi_base, uint32_t lo_base, int row, int c, const float4& v) {
-  const uint32_t off = (uint32_t)(row * 128 + ((c ^ (row & 7)) << 4));
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi_base + off), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
-  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(lo_base + off), "f"(lo_part(v.x)), "f"(lo_part(v.y)),
-               "f"(lo_part(v.z)), "f"(lo_part(v.w)) : "memory");
-}
-
-__global__ void __launch_bounds__(448, 1)
+__global__ void __launch_bounds__(W_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ WGroup g) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -297,12 +311,13 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
   for (int k = 1; k < g.n; ++k) if ((int)blockIdx.x >= g.it[k].cta0) pi = k;
   const WP& p = g.it[pi];
   const uint32_t b_tile = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
+  const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;      // A hi | A lo | B hi | B lo
   const uint32_t bar_base = base + (uint32_t)p.nstages * stage_bytes;
-  auto full_bar = [&](int s) { return bar_base + 8u * s; };
-  auto empty_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
-  const uint32_t tfull_bar = bar_base + 8u * (2 * MAX_STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 1);
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };                    // TMA bytes landed
+  auto ready_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };    // remainders written
+  auto empty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };// MMAs have read the stage
+  const uint32_t tfull_bar = bar_base + 8u * (3 * MAX_STAGES);
+  const uint32_t tmem_slot = bar_base + 8u * (3 * MAX_STAGES + 1);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   // work item of this CTA: (split, m tile, n tile)
@@ -312,10 +327,15 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
   const long long r_end = min(p.rows, r_begin + p.rows_per_split);
   const int k_blocks = (int)((r_end - r_begin + BK - 1) / BK);
   const int nstages = p.nstages;
+  const int b_groups = p.BN >> 5;                       // 32-column groups of the B tile
 
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmA[pi]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmB[pi]) : "memory");
+  }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 8); mbar_init(empty_bar(s), 1); }   // 8 loader warps
+      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 4); mbar_init(empty_bar(s), 1); }
       mbar_init(tfull_bar, 1);
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -328,20 +348,37 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  if (warp == 1) {
-    // ===== MMA issuer ================================================================================
+  if (warp == 0) {
+    // ===== TMA producer: raw row-major tiles, up to `nstages` k-blocks in flight ======================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(full_bar(stage), phase);
+        mbar_wait(empty_bar(stage), phase ^ 1u);
+        mbar_expect_tx(full_bar(stage), (uint32_t)(4 + b_groups) * MN_BOX);
+        const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+        const int r0 = (int)(r_begin + (long long)kb * BK);
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) tma_load_2d(&g.tmA[pi], full_bar(stage), sa + gq * MN_BOX, m_t * BM + gq * 32, r0);
+        for (int gq = 0; gq < b_groups; ++gq)
+          tma_load_2d(&g.tmB[pi], full_bar(stage), sa + 2u * A_TILE + gq * MN_BOX, n_t * p.BN + gq * 32, r0);
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer ================================================================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |     // MN-major A and B
+                             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(ready_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-        const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE);
-        const uint64_t b_hi = umma_desc_sw128(sa + 2u * A_TILE), b_lo = umma_desc_sw128(sa + 2u * A_TILE + b_tile);
+        const uint64_t a_hi = umma_desc_mn_sw128(sa), a_lo = umma_desc_mn_sw128(sa + A_TILE);
+        const uint64_t b_hi = umma_desc_mn_sw128(sa + 2u * A_TILE), b_lo = umma_desc_mn_sw128(sa + 2u * A_TILE + b_tile);
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint64_t o = (uint64_t)(kk * 2);
+          const uint64_t o = (uint64_t)(kk * 64);            // next 8-row K group: +1024 bytes
           umma_tf32(tmem_base, a_lo + o, b_hi + o, idesc, (kb | kk) ? 1u : 0u);
           umma_tf32(tmem_base, a_hi + o, b_lo + o, idesc, 1u);
           umma_tf32(tmem_base, a_hi + o, b_hi + o, idesc, 1u);
@@ -351,8 +388,38 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
       }
       umma_commit(tfull_bar);
     }
-  } else if (warp >= 2 && warp < 6) {
-    // ===== epilogue: accumulator tile -> partial buffer (each lane owns one row: 128-byte runs) =======
+  } else {
+    // ===== warps 2-5: remainder pass per k-block, then the epilogue ====================================
+    const int lt = threadIdx.x - 64;            // 0..127
+    {
+      int stage = 0; uint32_t phase = 0;
+      const int ones_col = p.N - n_t * p.BN;    // tile-local column of the implicit ones column (bias gradient)
+      const bool has_ones = ones_col >= 0 && ones_col < p.BN;
+      const uint32_t a_vec = A_TILE / 16, b_vec = b_tile / 16;
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+        if (has_ones && lt < BK) {             // X[r, N] := 1 for the valid rows of this k-block (OOB columns arrived as 0)
+          const long long r = r_begin + (long long)kb * BK + lt;
+          const uint32_t off = (uint32_t)((ones_col >> 5) * MN_BOX + lt * 128 + ((((ones_col & 31) >> 2) ^ (lt & 7)) << 4) + (ones_col & 3) * 4);
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 2u * A_TILE + off), "f"(r < r_end ? 1.f : 0.f) : "memory");
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (uint32_t v = lt; v < a_vec + b_vec; v += 128) {
+          const uint32_t src = v < a_vec ? sa + v * 16u : sa + 2u * A_TILE + (v - a_vec) * 16u;
+          const uint32_t dst = src + (v < a_vec ? (uint32_t)A_TILE : b_tile);
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(src));
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(lo_part(x.x)), "f"(lo_part(x.y)),
+                       "f"(lo_part(x.z)), "f"(lo_part(x.w)) : "memory");
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(stage));
+        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+      }
+    }
+    // ----- epilogue: accumulator tile -> partial buffer (each lane owns one row: 128-byte runs) -------
     const int q = warp & 3;
     const int n_chunks = (p.BN + 31) / 32;
     float* prow = p.partial + ((long long)split * p.Mpad + m_t * BM + q * 32 + lane) * p.Nld + n_t * p.BN;
@@ -374,66 +441,6 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
       }
     }
   }
-  // ===== loaders: warps 6..9 handle the A (dY^T) tile, warps 10..13 the B (X^T) tile
-  if (warp >= 6) {
-    const bool isA = warp < 10;
-    const int lt = (threadIdx.x - 192) & 127;          // 0..127 within the operand's loader group
-    const int c = lt & 7;                                 // which 4-row block of the 32-row k-block
-    const int g0 = lt >> 3;                               // first 4-column block
-    const float* __restrict__ src = isA ? p.A : p.B;
-    const long long ld = isA ? p.lda : p.ldb;
-    const int col_base = isA ? m_t * BM : n_t * p.BN;
-    const int col_lim = isA ? p.M : p.N;
-    const int tile_cols = isA ? BM : p.BN;
-    const int nblk = (tile_cols / 4 + 15) / 16;          // 4-column blocks per thread (2 for A, <= 3 for B)
-    int stage = 0; uint32_t phase = 0;
-    float4 cur[3][4], nxt[3][4];
-    auto issue = [&](int kb, float4 (&blk)[3][4]) {
-      const long long r0 = r_begin + (long long)kb * BK + 4 * c;
-#pragma unroll
-      for (int it = 0; it < 3; ++it) {
-        if (it < nblk) {
-          const int gq = g0 + 16 * it;
-          const int col = col_base + 4 * gq;
-          load_block(src, ld, r0, r_end, col, 4 * gq < tile_cols && col < col_lim, blk[it]);
-          if (!isA && col == p.N && 4 * gq < tile_cols) {   // the ones column: db = sum_r dY[r, :] * 1
-#pragma unroll
-            for (int j = 0; j < 4; ++j) blk[it][j] = make_float4(r0 + j < r_end ? 1.f : 0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      }
-    };
-    auto store = [&](const float4 (&blk)[3][4]) {
-      mbar_wait(empty_bar(stage), phase ^ 1u);
-      const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-      const uint32_t hi = isA ? sa : sa + 2u * A_TILE;
-      const uint32_t lo = isA ? sa + A_TILE : sa + 2u * A_TILE + b_tile;
-#pragma unroll
-      for (int it = 0; it < 3; ++it) {
-        if (it < nblk) {
-          const int gq = g0 + 16 * it;
-          if (4 * gq < tile_cols) {   // transpose the 4x4 block in registers: column e of 4 consecutive rows
-            store_hi_lo(hi, lo, 4 * gq + 0, c, make_float4(blk[it][0].x, blk[it][1].x, blk[it][2].x, blk[it][3].x));
-            store_hi_lo(hi, lo, 4 * gq + 1, c, make_float4(blk[it][0].y, blk[it][1].y, blk[it][2].y, blk[it][3].y));
-            store_hi_lo(hi, lo, 4 * gq + 2, c, make_float4(blk[it][0].z, blk[it][1].z, blk[it][2].z, blk[it][3].z));
-            store_hi_lo(hi, lo, 4 * gq + 3, c, make_float4(blk[it][0].w, blk[it][1].w, blk[it][2].w, blk[it][3].w));
-          }
-        }
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(stage));
-      if (++stage == nstages) { stage = 0; phase ^= 1u; }
-    };
-    if (k_blocks > 0) issue(0, cur);
-    for (int kb = 0; kb < k_blocks; kb += 2) {     // the next k-block's loads are in flight while this one is stored
-      if (kb + 1 < k_blocks) issue(kb + 1, nxt);
-      store(cur);
-      if (kb + 1 >= k_blocks) break;
-      if (kb + 2 < k_blocks) issue(kb + 2, cur);
-      store(nxt);
-    }
-  }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -444,8 +451,11 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
 
 // dW[m, n] = sum_s partial[s][m][n] (n < N), db[m] = sum_s partial[s][m][N]; fixed order -> deterministic.
 // One launch for every problem of a group.
-struct RItem { const float* partial; float* dW; float* db; int nsplit, M, N, Mpad, Nld; long long start; };
-struct RGroup { RItem it[WG_MAX]; long long total; int n; };
+// kind 0: a weight gradient (above).  kind 1: plain column sums out[c] = sum_s partial[s*stride + c], c < N
+// (the LayerNorm dgamma / dbeta partial rows ride along in the same launch).
+struct RItem { const float* partial; float* dW; float* db; int nsplit, M, N, Mpad, Nld, kind; long long stride; long long start; };
+constexpr int RG_MAX = WG_MAX + CS_MAX;
+struct RGroup { RItem it[RG_MAX]; long long total; int n; };
 __global__ void wgrad_reduce_kernel(const __grid_constant__ RGroup g) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.total) return;
@@ -454,6 +464,14 @@ __global__ void wgrad_reduce_kernel(const __grid_constant__ RGroup g) {
   for (int j = 1; j < g.n; ++j) if (i >= g.it[j].start) k = j;
   const RItem& r = g.it[k];
   const long long e = i - r.start;
+  if (r.kind == 1) {
+    const float* src = r.partial + e;
+    float s = 0.f;
+#pragma unroll 8
+    for (int sp = 0; sp < r.nsplit; ++sp) s += __ldg(src + sp * r.stride);
+    r.dW[e] = s;
+    return;
+  }
   const int m = (int)(e / (r.N + 1)), n = (int)(e - (long long)m * (r.N + 1));
   const float* src = r.partial + (long long)m * r.Nld + n;
   const long long stride = (long long)r.Mpad * r.Nld;
@@ -470,7 +488,7 @@ WPlan wgrad_plan(int M, int N, long long rows) {
   w.Mpad = w.m_tiles * BM;
   const int Ncols = N + 1;                                  // + the ones column
   w.n_tiles = (int)ceil_div(Ncols, MAX_BN);
-  w.BN = w.n_tiles == 1 ? (int)round_up(Ncols, 16) : (int)round_up(ceil_div(Ncols, w.n_tiles), 32);
+  w.BN = (int)round_up(ceil_div(Ncols, w.n_tiles), 32);     // whole 32-column TMA boxes
   w.Nld = (int)round_up(w.n_tiles * w.BN, 4);
   // row splits: ~512 rows (16 k-blocks) per CTA so the pipeline amortises its fill, but never more than
   // ~2 waves of CTAs per problem (bounds the partial buffer for the big configurations)
@@ -602,12 +620,12 @@ long long tc_wgrad_partial_floats(int Nout, int Kin, long long rows) {
   return round_up((long long)w.nsplit * w.Mpad * w.Nld, 64);
 }
 
-int tc_wgrad_group(const WgradItem* items, int n, cudaStream_t st) {
-  if (n <= 0) return 0;
-  if (n > WG_MAX) { set_error("tc_wgrad_group: at most %d problems per launch", WG_MAX); return -2; }
+int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs, cudaStream_t st) {
+  if (n <= 0 && ncs <= 0) return 0;
+  if (n > WG_MAX || ncs > CS_MAX) { set_error("tc_wgrad_group: at most %d problems (+ %d column sums) per launch", WG_MAX, CS_MAX); return -2; }
   WGroup g;
   RGroup r;
-  g.n = n; r.n = n;
+  g.n = n; r.n = n + (ncs > 0 ? ncs : 0);
   int cta = 0, smem_bytes = 0;
   long long tot = 0;
   for (int i = 0; i < n; ++i) {
@@ -619,8 +637,15 @@ int tc_wgrad_group(const WgradItem* items, int n, cudaStream_t st) {
     }
     const WPlan w = wgrad_plan(a.Nout, a.Kin, a.rows);
     WP& p = g.it[i];
-    p.A = a.dY; p.lda = a.ldy; p.B = a.X; p.ldb = a.ldx; p.partial = a.partial; p.dW = a.dW; p.db = a.db;
+    p.partial = a.partial;
     p.rows = a.rows; p.M = a.Nout; p.N = a.Kin;
+    {
+      cuuint32_t box[2] = {32, BK};
+      cuuint64_t da[2] = {(cuuint64_t)a.Nout, (cuuint64_t)a.rows}, sa_[1] = {(cuuint64_t)a.ldy * 4};
+      RD_TRY(encode(&g.tmA[i], a.dY, 2, da, sa_, box, CU_TENSOR_MAP_SWIZZLE_128B, "wgrad dY"));
+      cuuint64_t db_[2] = {(cuuint64_t)a.Kin, (cuuint64_t)a.rows}, sb_[1] = {(cuuint64_t)a.ldx * 4};
+      RD_TRY(encode(&g.tmB[i], a.X, 2, db_, sb_, box, CU_TENSOR_MAP_SWIZZLE_128B, "wgrad X"));
+    }
     p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = w.m_tiles; p.nsplit = w.nsplit; p.rows_per_split = w.rows_per_split;
     p.Mpad = w.Mpad; p.Nld = w.Nld;
     const int stage_bytes = 2 * A_TILE + 2 * p.BN * 128;
@@ -628,19 +653,30 @@ int tc_wgrad_group(const WgradItem* items, int n, cudaStream_t st) {
     p.nstages = (SMEM_LIMIT - fixed) / stage_bytes;
     if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
     if (p.nstages < 2) { set_error("tc_wgrad_group: not enough shared memory"); return -2; }
+    if (a.rows > 0x7fffffffLL) { set_error("tc_wgrad_group: too many rows"); return -2; }
     const int sb = fixed + p.nstages * stage_bytes;
     if (sb > smem_bytes) smem_bytes = sb;
     p.cta0 = cta;
     cta += w.nsplit * w.m_tiles * w.n_tiles;
     RItem& q = r.it[i];
     q.partial = a.partial; q.dW = a.dW; q.db = a.db; q.nsplit = w.nsplit; q.M = a.Nout; q.N = a.Kin; q.Mpad = w.Mpad; q.Nld = w.Nld;
+    q.kind = 0; q.stride = 0;
     q.start = tot;
     tot += (long long)a.Nout * (a.Kin + 1);
   }
+  for (int i = 0; i < ncs; ++i) {
+    RItem& q = r.it[n + i];
+    q.partial = cs[i].partial; q.dW = cs[i].out; q.db = nullptr; q.nsplit = cs[i].nsplit; q.M = 1; q.N = cs[i].ncols;
+    q.Mpad = 1; q.Nld = 0; q.kind = 1; q.stride = cs[i].stride;
+    q.start = tot;
+    tot += cs[i].ncols;
+  }
   r.total = tot;
-  RD_TRY(ensure_attr((const void*)tc_wgrad_kernel, 15));
-  tc_wgrad_kernel<<<cta, 448, smem_bytes, st>>>(g);
-  RD_CHECK_LAUNCH("tc_wgrad_kernel");
+  if (n > 0) {
+    RD_TRY(ensure_attr((const void*)tc_wgrad_kernel, 15));
+    tc_wgrad_kernel<<<cta, W_THREADS, smem_bytes, st>>>(g);
+    RD_CHECK_LAUNCH("tc_wgrad_kernel");
+  }
   wgrad_reduce_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(r);
   RD_CHECK_LAUNCH("wgrad_reduce_kernel");
   return 0;
@@ -649,7 +685,7 @@ int tc_wgrad_group(const WgradItem* items, int n, cudaStream_t st) {
 int tc_wgrad(const float* dY, long long ldy, const float* X, long long ldx, long long rows, int Nout, int Kin,
              float* dW, float* db, float* partial, cudaStream_t st) {
   WgradItem it{dY, ldy, X, ldx, rows, Nout, Kin, dW, db, partial};
-  return tc_wgrad_group(&it, 1, st);
+  return tc_wgrad_group(&it, 1, nullptr, 0, st);
 }
 
 int split_weights(const WeightSplit* items, int n, cudaStream_t st, const StepPrologue* pro) {

@@ -36,7 +36,10 @@ int tc_wgrad(const float* dY, long long ldy, const float* X, long long ldx, long
 constexpr int WG_MAX = 12;
 struct WgradItem { const float* dY; long long ldy; const float* X; long long ldx; long long rows; int Nout, Kin;
                    float* dW; float* db; float* partial; };
-int tc_wgrad_group(const WgradItem* items, int n, cudaStream_t st);
+// Column sums riding along in the group's reduction launch: out[c] = sum_{s < nsplit} partial[s*stride + c], c < ncols
+constexpr int CS_MAX = 36;
+struct ColsumItem { const float* partial; long long stride; int nsplit, ncols; float* out; };
+int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs, cudaStream_t st);
 
 // One launch for all weights of a step: lo = W - trunc19(W); t = W^T; t_lo = W^T - trunc19(W^T).
 // optional extras for the single-pass-TF32 layers: rn = RN_tf32(W), rn_t = RN_tf32(W)^T

@@ -173,14 +173,7 @@ class RaindropV2Function(torch.autograd.Function):
             layout = plan.__dict__["_grad_layout"] = (offs, total)
         offs, total = layout
         owner = plan.owner() if plan.owner is not None else None
-        flat = None
-        # (a parameter that still holds a .grad would make autograd ACCUMULATE into it; if that .grad aliases the
-        # static bucket the kernel has just overwritten it, so only use the bucket when every .grad is None)
-        if owner is not None and owner._flat_grad_static is not None and owner._flat_grad_static.numel() == total \
-                and owner._flat_grad_static.device == dev and all(t.grad is None for t in params):
-            flat = owner._flat_grad_static          # raindrop_b200.optim.FlatAdam: gradients land in its bucket
-        if flat is None:
-            flat = torch.empty(total, dtype=torch.float32, device=dev)
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
         base = flat.data_ptr()
         cachedG = plan.__dict__.get("_grad_struct")
         if cachedG is not None and cachedG[0] == base:
@@ -206,6 +199,133 @@ class RaindropV2Function(torch.autograd.Function):
             ctx.pool.append(ctx.ws)
         ctx.ws = None
         return (None, None, None, None, None, None) + tuple(grads)
+
+
+class _StepSlot:
+    """Static buffers + captured CUDA graphs of one (batch size, mode, device) for the flat-bucket fast path."""
+
+    def __init__(self, plan, B, training, dev, flat):
+        lib = L.load()
+        self.B, self.training, self.dev = B, training, dev
+        self.dims = plan.dims(B, training)
+        f32 = dict(dtype=torch.float32, device=dev)
+        self.src = torch.zeros(plan.T, B, 2 * plan.N, **f32)
+        self.times = torch.zeros(plan.T, B, **f32)
+        self.lengths = torch.ones(B, dtype=torch.int64, device=dev)
+        self.static = torch.zeros(B, plan.d_static, **f32) if plan.static else None
+        self.logits = torch.zeros(B, plan.n_classes, **f32)
+        self.d_logits = torch.zeros(B, plan.n_classes, **f32)
+        ws_bytes = lib.rd_workspace_bytes(C.byref(self.dims))
+        if ws_bytes == 0:
+            L.check(-2, "rd_workspace_bytes")
+        self.ws = torch.empty(ws_bytes // 4, **f32)
+        self.scratch = None
+        self.P, self.G = L.RdParams(), L.RdGrads()
+        self.P.R_u = plan.R_u.data_ptr()
+        for (key, path), off in zip(plan.fields, flat.offsets):
+            _set_field(self.P, path, flat.flat_p.data_ptr() + 4 * off)
+            _set_field(self.G, path, flat.flat_g.data_ptr() + 4 * off)
+        self.key = (flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), plan.R_u.data_ptr(), plan.node_scale.data_ptr(),
+                    plan.rng_state.data_ptr())
+        self.fwd_calls = self.bwd_calls = 0
+        self.fwd_graph = self.bwd_graph = None
+        self.pending = False          # a forward whose backward has not run yet owns the buffers
+
+
+def _run_or_capture(slot, which, fn):
+    """1st call eager (one-time kernel attribute setup must not happen inside a capture), 2nd call captured,
+    afterwards one graph launch per call."""
+    graph = getattr(slot, which + "_graph")
+    if graph is not None:
+        graph.replay()
+        return
+    calls = getattr(slot, which + "_calls")
+    setattr(slot, which + "_calls", calls + 1)
+    if calls == 0 or not GRAPHS_ENABLED or torch.cuda.is_current_stream_capturing():
+        fn()
+        return
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        fn()
+    setattr(slot, which + "_graph", g)
+    g.replay()
+
+
+GRAPHS_ENABLED = True
+
+
+class RaindropV2FlatFunction(torch.autograd.Function):
+    """Same arithmetic as RaindropV2Function for a model whose used parameters live in ONE flat leaf tensor
+    (raindrop_b200.optim.FlatAdam).  Inputs are staged into static buffers so that the forward and the backward are
+    each ONE CUDA-graph launch; the gradient bucket is written in place (flat_p.grad IS the bucket), so autograd
+    has a single leaf to visit and nothing to copy."""
+
+    @staticmethod
+    def forward(ctx, plan, training, slot, flat, src, static, times, lengths, flat_p):
+        lib = L.load()
+        slot.src.copy_(src); slot.times.copy_(times); slot.lengths.copy_(lengths)
+        if slot.static is not None:
+            slot.static.copy_(static)
+
+        def fwd():
+            rc = lib.rd_raindrop_v2_fwd(C.byref(slot.dims), C.byref(slot.P), slot.src.data_ptr(), L.ptr(slot.static),
+                                        slot.times.data_ptr(), slot.lengths.data_ptr(), plan.node_scale.data_ptr(),
+                                        L.ptr(plan.rng_state), slot.ws.data_ptr(), slot.logits.data_ptr(), None, None, None,
+                                        L.stream_ptr(slot.dev))
+            L.check(rc, "rd_raindrop_v2_fwd")
+        _run_or_capture(slot, "fwd", fwd)
+        ctx.plan, ctx.slot, ctx.flat = plan, slot, flat
+        slot.pending = bool(ctx.needs_input_grad[-1])
+        if plan.debug_keep_workspace:
+            plan.last_workspace, plan.last_dims = slot.ws, slot.dims
+        return slot.logits.clone()
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        lib = L.load()
+        plan, slot, flat = ctx.plan, ctx.slot, ctx.flat
+        if not slot.pending:
+            raise L.RaindropB200Error("backward called twice for one forward (retain_graph is not supported)")
+        slot.d_logits.copy_(d_logits)
+        if slot.scratch is None:
+            slot.scratch = torch.empty(lib.rd_backward_scratch_bytes(C.byref(slot.dims)) // 4, dtype=torch.float32,
+                                       device=slot.dev)
+
+        def bwd():
+            rc = lib.rd_raindrop_v2_bwd(C.byref(slot.dims), C.byref(slot.P), L.ptr(slot.static), slot.lengths.data_ptr(),
+                                        plan.node_scale.data_ptr(), slot.ws.data_ptr(), slot.d_logits.data_ptr(),
+                                        C.byref(slot.G), slot.scratch.data_ptr(), L.BWD_ALL, L.stream_ptr(slot.dev))
+            L.check(rc, "rd_raindrop_v2_bwd")
+        _run_or_capture(slot, "bwd", bwd)
+        slot.pending = False
+        flat.grads_ready = True
+        owner = plan.owner() if plan.owner is not None else None
+        if owner is not None:
+            owner._flat_grad = flat.flat_g
+        # flat_p.grad already IS flat_g (written in place by the kernels): nothing for autograd to accumulate
+        return (None,) * 9
+
+
+def flat_forward(plan, training, flat, src, static, times, lengths):
+    """Entry of the flat-bucket fast path (models_rd.Raindrop_v2.forward when a FlatAdam is bound)."""
+    dev = src.device
+    B = src.shape[1]
+    if src.shape[0] != plan.T or src.shape[2] != 2 * plan.N:
+        raise ValueError("src must be [max_len=%d, B, 2*d_inp=%d], got %s" % (plan.T, 2 * plan.N, tuple(src.shape)))
+    slots = plan.__dict__.setdefault("_slots", {})
+    k = (B, bool(training), dev.index)
+    slot = slots.get(k)
+    key = (flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), plan.R_u.data_ptr(), plan.node_scale.data_ptr(),
+           plan.rng_state.data_ptr())
+    if slot is None or slot.key != key:      # pointers changed (graph / R_u / optimiser re-created): rebuild
+        slot = slots[k] = _StepSlot(plan, B, bool(training), dev, flat)
+    if slot.pending:
+        if torch.is_grad_enabled():
+            raise L.RaindropB200Error("a FlatAdam-bound model keeps ONE forward in flight per batch size: call "
+                                      "loss.backward() before the next training forward (for gradient accumulation "
+                                      "use torch.optim.Adam)")
+        return None      # caller falls back to the general path (e.g. a no-grad probe between forward and backward)
+    return RaindropV2FlatFunction.apply(plan, training, slot, flat, src, static, times, lengths, flat.flat_p)
 
 
 class ObPropLayerFunction(torch.autograd.Function):

@@ -207,7 +207,7 @@ class Raindrop_v2(nn.Module):
         self._plan.owner = weakref.ref(self)
         self._graph_key = None
         self._flat_grad = None
-        self._flat_grad_static = None     # set by raindrop_b200.optim.FlatAdam
+        self._flat_optim = None           # weakref to a bound raindrop_b200.optim.FlatAdam
         self._seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
 
     def init_weights(self):
@@ -272,7 +272,13 @@ class Raindrop_v2(nn.Module):
         times = times.to(device=device, dtype=torch.float32).contiguous()
         lengths = lengths.to(device=device, dtype=torch.int64).contiguous()
         st = static.to(device=device, dtype=torch.float32).contiguous() if (self.static and static is not None) else None
-        logits = RF.RaindropV2Function.apply(plan, self.training, src, st, times, lengths, *self.used_parameters())
+        logits = None
+        flat = self._flat_optim() if self._flat_optim is not None else None
+        if flat is not None and flat.flat_p.device == device:
+            # parameters live in one flat leaf (raindrop_b200.optim.FlatAdam): graph-captured fast path
+            logits = RF.flat_forward(plan, self.training, flat, src, st, times, lengths)
+        if logits is None:
+            logits = RF.RaindropV2Function.apply(plan, self.training, src, st, times, lengths, *self.used_parameters())
         # alpha_all has identical columns on the live path, so mean(cdist) == 0 (code/models_rd.py:343-346)
         distance = torch.zeros((), dtype=torch.float32, device=device)
         return logits, distance, None
