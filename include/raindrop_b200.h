@@ -200,6 +200,21 @@ size_t rd_linear_scratch_bytes(int32_t in_features, int32_t out_features);
 int rd_linear_fwd(const float* x, const float* weight, const float* bias, int64_t rows, int32_t in_features,
                   int32_t out_features, int32_t relu, float* out, void* scratch, void* stream);
 
+/* Temporal self-attention core of nn.TransformerEncoderLayer.self_attn (code/models_rd.py:232-237,358) for one
+ * packed projection qkv [T, B, 3*H*hd] (seq-first, as F.multi_head_attention_forward lays it out):
+ *   ctx[t, b, h*hd:(h+1)*hd] = dropout(softmax_j(q_t . k_j / sqrt(hd), keys j >= lengths[b] masked)) . v
+ * and its backward d_qkv [T, B, 3*H*hd] from d_ctx [T, B, H*hd] (probabilities are recomputed, nothing T x T is
+ * stored).  rng_captured = 2 x uint64 {seed, counter} on the device (ignored when drop_p == 0); `site` selects the
+ * dropout stream (16 + layer inside the model).  impl: 0 = automatic, 1 = tcgen05 tensor-core kernels
+ * (T <= 64, hd <= 96, hd % 4 == 0), 2 = CUDA-core kernels (T <= 64, hd <= 96).  Longer sequences are handled inside
+ * rd_raindrop_v2_fwd/_bwd (they need workspace). */
+int rd_temporal_attention_fwd(const float* qkv, const int64_t* lengths, int32_t B, int32_t H, int32_t T, int32_t hd,
+                              float drop_p, const uint64_t* rng_captured, uint32_t site, int32_t impl, float* ctx,
+                              void* stream);
+int rd_temporal_attention_bwd(const float* qkv, const float* d_ctx, const int64_t* lengths, int32_t B, int32_t H,
+                              int32_t T, int32_t hd, float drop_p, const uint64_t* rng_captured, uint32_t site,
+                              int32_t impl, float* d_qkv, void* stream);
+
 /* Weight/bias gradients of up to 12 torch.nn.Linear layers in ONE grouped tensor-core launch (+ one reduction
  * launch): d_weight[out_f, in_f] = d_out[rows, out_f]^T . x[rows, in_f], d_bias[out_f] = column sums of d_out.
  * This is what autograd computes for every Linear on the path (code/Raindrop.py:323); a training step has ten of

@@ -66,6 +66,13 @@ int attn_small_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T
 int attn_small_bwd(const float* qkv, const float* dctx, const int64_t* lengths, int B, int H, int T, int hd,
                    float drop_p, const uint64_t* rng, uint32_t site, float* dqkv, cudaStream_t st);
 
+// the same on the tensor cores (rd_attn_tc.cu: tcgen05 3xTF32, TMA-staged head slices, T <= 64, hd <= 96, hd % 4 == 0)
+bool attn_tc_supported(int T, int hd);
+int attn_tc_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T, int hd, float drop_p,
+                const uint64_t* rng, uint32_t site, float* ctx, cudaStream_t st);
+int attn_tc_bwd(const float* qkv, const float* dctx, const int64_t* lengths, int B, int H, int T, int hd,
+                float drop_p, const uint64_t* rng, uint32_t site, float* dqkv, cudaStream_t st);
+
 // dZ2[(b*N+n), t*d_ob+k] = dZ[t,b,n*d_ob+k] * s[n] * (Z[t,b,n*d_ob+k] > 0)
 int obprop_out_grad(const float* dZ, const float* Z, const float* s, int B, int T, int N, int d_ob, int D,
                     int round, float* dZ2, cudaStream_t st);

@@ -294,7 +294,9 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
       RD_TRY(linear_nt(g, ws + w.wsp[l].in_lo, st));
     }
     float* ctx = ws + w.l[l].ctx;
-    if (attn_small_supported(s.T, s.hd)) {
+    if (attn_tc_supported(s.T, s.hd)) {
+      RD_TRY(attn_tc_fwd(qkv, lengths, s.B, s.H, s.T, s.hd, s.p, rng, SITE_ATTN + l, ctx, st));
+    } else if (attn_small_supported(s.T, s.hd)) {
       RD_TRY(attn_small_fwd(qkv, lengths, s.B, s.H, s.T, s.hd, s.p, rng, SITE_ATTN + l, ctx, st));
     } else {
       {  // S[b,h] = scale * Q K^T
@@ -405,7 +407,9 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     RD_TRY(wq.colsum(sc + b.l[l].ln[1] + s.D, 2 * s.D, chunks, s.D, GE.norm1_bias, st));
     RD_TRY(tn(&wq, K1, s.D, ctx, s.D, GE.out_proj_weight, GE.out_proj_bias, s.D, s.D, s.M2, sc + b.l[l].wp[2], partial, st));
     RD_TRY(linear_nt(nt(K1, s.D, ws + w.wsp[l].out_t, s.D, gD, s.D, s.M2, s.D, s.D), ws + w.wsp[l].out_tlo, st));
-    if (attn_small_supported(s.T, s.hd)) {
+    if (attn_tc_supported(s.T, s.hd)) {
+      RD_TRY(attn_tc_bwd(qkv, gD, lengths, s.B, s.H, s.T, s.hd, s.p, rng, SITE_ATTN + l, dqkv, st));
+    } else if (attn_small_supported(s.T, s.hd)) {
       RD_TRY(attn_small_bwd(qkv, gD, lengths, s.B, s.H, s.T, s.hd, s.p, rng, SITE_ATTN + l, dqkv, st));
     } else {
       {  // dPd[b,h] = dctx V^T
@@ -558,6 +562,35 @@ int rd_linear_fwd(const float* x, const float* weight, const float* bias, int64_
   GemmP g = nt(x, in_features, weight, in_features, out, out_features, rows, out_features, in_features);
   g.bias = bias; g.relu = relu;
   return linear_nt(g, (const float*)scratch, st);
+}
+
+int rd_temporal_attention_fwd(const float* qkv, const int64_t* lengths, int32_t B, int32_t H, int32_t T, int32_t hd,
+                              float drop_p, const uint64_t* rng_captured, uint32_t site, int32_t impl, float* ctx,
+                              void* stream) {
+  if (!qkv || !lengths || !ctx || B < 1 || H < 1 || T < 1 || hd < 1 || drop_p < 0.f || drop_p >= 1.f || (drop_p > 0.f && !rng_captured)) {
+    set_error("rd_temporal_attention_fwd: bad arguments");
+    return -2;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((impl == 0 || impl == 1) && attn_tc_supported(T, hd)) return attn_tc_fwd(qkv, lengths, B, H, T, hd, drop_p, rng_captured, site, ctx, st);
+  if ((impl == 0 || impl == 2) && attn_small_supported(T, hd)) return attn_small_fwd(qkv, lengths, B, H, T, hd, drop_p, rng_captured, site, ctx, st);
+  set_error("rd_temporal_attention_fwd: T=%d hd=%d not supported by implementation %d", T, hd, impl);
+  return -2;
+}
+
+int rd_temporal_attention_bwd(const float* qkv, const float* d_ctx, const int64_t* lengths, int32_t B, int32_t H,
+                              int32_t T, int32_t hd, float drop_p, const uint64_t* rng_captured, uint32_t site,
+                              int32_t impl, float* d_qkv, void* stream) {
+  if (!qkv || !d_ctx || !lengths || !d_qkv || B < 1 || H < 1 || T < 1 || hd < 1 || drop_p < 0.f || drop_p >= 1.f ||
+      (drop_p > 0.f && !rng_captured)) {
+    set_error("rd_temporal_attention_bwd: bad arguments");
+    return -2;
+  }
+  cudaStream_t st = (cudaStream_t)stream;
+  if ((impl == 0 || impl == 1) && attn_tc_supported(T, hd)) return attn_tc_bwd(qkv, d_ctx, lengths, B, H, T, hd, drop_p, rng_captured, site, d_qkv, st);
+  if ((impl == 0 || impl == 2) && attn_small_supported(T, hd)) return attn_small_bwd(qkv, d_ctx, lengths, B, H, T, hd, drop_p, rng_captured, site, d_qkv, st);
+  set_error("rd_temporal_attention_bwd: T=%d hd=%d not supported by implementation %d", T, hd, impl);
+  return -2;
 }
 
 size_t rd_linear_wgrad_partial_bytes(int64_t rows, int32_t out_features, int32_t in_features) {

@@ -47,6 +47,16 @@ __device__ __forceinline__ void tma_load_2d(const CUtensorMap* map, uint32_t bar
       "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(const CUtensorMap* map, uint32_t bar, uint32_t dst, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                ::"l"(map), "r"(src), "r"(c0), "r"(c1) : "memory");
@@ -90,6 +100,24 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
 }
 
 
+// MN-major TF32 operand tile (the contraction index runs over the ROWS of a row-major tile).  For 32-bit operands the
+// tensor core accepts exactly one MN-major shared-memory layout: 128-byte lines of 32 consecutive M/N elements whose
+// 32-BYTE chunks are XOR-swizzled with (line & 3) -- Swizzle<2,5,2>, descriptor layout type SWIZZLE_128B_BASE32B,
+// which is what TMA produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  K atoms are 4 lines (SBO = 512 bytes),
+// 32-element M/N groups are `lbo_bytes` apart (LBO).  One kind::tf32 MMA (K = 8) consumes 8 lines = 1024 bytes.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) | (32ull << 32) | (1ull << 46) | (1ull << 61);
+}
+// byte offset of the 16-byte piece holding columns 4*q4 .. 4*q4+3 (q4 < 8) of line `r` inside one 32-column group
+__device__ __forceinline__ uint32_t mn_sw_offset(int r, int q4) {
+  return (uint32_t)(r * 128 + ((((q4 >> 1) ^ (r & 3))) << 5) + ((q4 & 1) << 4));
+}
+// instruction descriptor, kind::tf32, fp32 accumulate; a_mn / b_mn: operand is MN-major
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N, bool a_mn, bool b_mn) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | (a_mn ? (1u << 15) : 0u) | (b_mn ? (1u << 16) : 0u) |
+         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -112,11 +140,11 @@ inline EncodeTiledFn get_encode() {
 // cuTensorMapEncodeTiled costs a few microseconds of host time; a training step re-encodes the same
 // ~90 maps every step (same buffers, same shapes), so keep them in a small direct-mapped cache.
 struct TmapKey {
-  const void* addr; int rank; int swizzle; cuuint64_t dims[4]; cuuint64_t strides[3]; cuuint32_t box[4];
+  const void* addr; int rank; int swizzle; cuuint64_t dims[5]; cuuint64_t strides[4]; cuuint32_t box[5];
   bool operator==(const TmapKey& o) const {
     if (addr != o.addr || rank != o.rank || swizzle != o.swizzle) return false;
-    for (int i = 0; i < 4; ++i) if (dims[i] != o.dims[i] || box[i] != o.box[i]) return false;
-    for (int i = 0; i < 3; ++i) if (strides[i] != o.strides[i]) return false;
+    for (int i = 0; i < 5; ++i) if (dims[i] != o.dims[i] || box[i] != o.box[i]) return false;
+    for (int i = 0; i < 4; ++i) if (strides[i] != o.strides[i]) return false;
     return true;
   }
 };

@@ -278,12 +278,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
 // =================================================================================================
 // Both operands are row-major activations [rows, cols] and the contraction runs over ROWS, i.e. they are
 // "MN-major" from the tensor core's point of view.  tcgen05 takes MN-major TF32 operands directly (instruction
-// descriptor bits 15/16), so the tiles go global -> shared memory by TMA exactly as they lie in memory:
-//   box {32 columns, 32 rows} with the 128B swizzle  ==  canonical MN-major SW128 atom ((4,8,m),(8,k)):((1,4,LBO),(32,SBO))
-//   (one 128-byte line = 32 consecutive columns of one row; 8 rows = one K group of 1024 B; the next 32 columns are
-//   the next box, LBO = 4096 B apart).  No register transposes; four warps only derive the error-compensation
-// remainders lo = x - trunc19(x) (same addresses, so the swizzle never has to be undone) and plant the "ones"
-// column that makes the bias gradient fall out of the same MMAs.
+// descriptor bits 15/16) in exactly one shared-memory layout, the 128B swizzle with 32-byte atoms (rd_tc_common.cuh),
+// which TMA produces with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  So the tiles go global -> shared memory exactly as
+// they lie in memory: box {32 columns, 32 rows}; one 128-byte line = 32 consecutive columns of one row; the next 32
+// columns are the next box, LBO = 4096 B apart.  No register transposes; four warps only derive the
+// error-compensation remainders lo = x - trunc19(x) (same addresses, so the swizzle never has to be undone) and
+// plant the "ones" column that makes the bias gradient fall out of the same MMAs.
 struct WP {
   float* partial;                    // [nsplit][Mpad][Nld]
   long long rows; int M, N, BN, n_tiles, m_tiles, nsplit, rows_per_split, nstages, Mpad, Nld;
@@ -295,11 +295,6 @@ constexpr int W_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 remain
 constexpr int MN_BOX = 32 * 32 * 4;  // one {32 col, 32 row} fp32 box = 4096 bytes
 
 __device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
-
-__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t saddr) {
-  // start | LBO = 4096 B (next 32-column group) | SBO = 1024 B (next 8-row K group) | version 1 | SWIZZLE_128B
-  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(MN_BOX >> 4) << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
-}
 
 __global__ void __launch_bounds__(W_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ WGroup g) {
@@ -374,8 +369,8 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
         mbar_wait(ready_bar(stage), phase);
         tc_fence_after();
         const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-        const uint64_t a_hi = umma_desc_mn_sw128(sa), a_lo = umma_desc_mn_sw128(sa + A_TILE);
-        const uint64_t b_hi = umma_desc_mn_sw128(sa + 2u * A_TILE), b_lo = umma_desc_mn_sw128(sa + 2u * A_TILE + b_tile);
+        const uint64_t a_hi = umma_desc_mn_sw128(sa, MN_BOX), a_lo = umma_desc_mn_sw128(sa + A_TILE, MN_BOX);
+        const uint64_t b_hi = umma_desc_mn_sw128(sa + 2u * A_TILE, MN_BOX), b_lo = umma_desc_mn_sw128(sa + 2u * A_TILE + b_tile, MN_BOX);
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk) {
           const uint64_t o = (uint64_t)(kk * 64);            // next 8-row K group: +1024 bytes
@@ -401,7 +396,7 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
         const uint32_t sa = base + (uint32_t)stage * stage_bytes;
         if (has_ones && lt < BK) {             // X[r, N] := 1 for the valid rows of this k-block (OOB columns arrived as 0)
           const long long r = r_begin + (long long)kb * BK + lt;
-          const uint32_t off = (uint32_t)((ones_col >> 5) * MN_BOX + lt * 128 + ((((ones_col & 31) >> 2) ^ (lt & 7)) << 4) + (ones_col & 3) * 4);
+          const uint32_t off = (uint32_t)((ones_col >> 5) * MN_BOX) + mn_sw_offset(lt, (ones_col & 31) >> 2) + (uint32_t)(ones_col & 3) * 4u;
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 2u * A_TILE + off), "f"(r < r_end ? 1.f : 0.f) : "memory");
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -464,15 +459,19 @@ __global__ void wgrad_reduce_kernel(const __grid_constant__ RGroup g) {
   for (int j = 1; j < g.n; ++j) if (i >= g.it[j].start) k = j;
   const RItem& r = g.it[k];
   const long long e = i - r.start;
-  if (r.kind == 1) {
-    const float* src = r.partial + e;
+  if (r.kind == 1) {      // one warp per output column (item starts are multiples of 32): lanes stride over the chunks
+    const long long col = e >> 5;
+    const int lane = (int)(e & 31);
+    const float* src = r.partial + col;
     float s = 0.f;
-#pragma unroll 8
-    for (int sp = 0; sp < r.nsplit; ++sp) s += __ldg(src + sp * r.stride);
-    r.dW[e] = s;
+#pragma unroll 4
+    for (int sp = lane; sp < r.nsplit; sp += 32) s += __ldg(src + sp * r.stride);
+    s = warp_sum(s);        // fixed butterfly order: deterministic
+    if (lane == 0) r.dW[col] = s;
     return;
   }
   const int m = (int)(e / (r.N + 1)), n = (int)(e - (long long)m * (r.N + 1));
+  if (m >= r.M) return;       // padding between this item and the next (warp-aligned) one
   const float* src = r.partial + (long long)m * r.Nld + n;
   const long long stride = (long long)r.Mpad * r.Nld;
   float s = 0.f;
@@ -642,9 +641,9 @@ int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs,
     {
       cuuint32_t box[2] = {32, BK};
       cuuint64_t da[2] = {(cuuint64_t)a.Nout, (cuuint64_t)a.rows}, sa_[1] = {(cuuint64_t)a.ldy * 4};
-      RD_TRY(encode(&g.tmA[i], a.dY, 2, da, sa_, box, CU_TENSOR_MAP_SWIZZLE_128B, "wgrad dY"));
+      RD_TRY(encode(&g.tmA[i], a.dY, 2, da, sa_, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, "wgrad dY"));
       cuuint64_t db_[2] = {(cuuint64_t)a.Kin, (cuuint64_t)a.rows}, sb_[1] = {(cuuint64_t)a.ldx * 4};
-      RD_TRY(encode(&g.tmB[i], a.X, 2, db_, sb_, box, CU_TENSOR_MAP_SWIZZLE_128B, "wgrad X"));
+      RD_TRY(encode(&g.tmB[i], a.X, 2, db_, sb_, box, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, "wgrad X"));
     }
     p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = w.m_tiles; p.nsplit = w.nsplit; p.rows_per_split = w.rows_per_split;
     p.Mpad = w.Mpad; p.Nld = w.Nld;
@@ -668,8 +667,9 @@ int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs,
     RItem& q = r.it[n + i];
     q.partial = cs[i].partial; q.dW = cs[i].out; q.db = nullptr; q.nsplit = cs[i].nsplit; q.M = 1; q.N = cs[i].ncols;
     q.Mpad = 1; q.Nld = 0; q.kind = 1; q.stride = cs[i].stride;
+    tot = round_up(tot, 32);                 // warp-aligned: 32 threads per output column
     q.start = tot;
-    tot += cs[i].ncols;
+    tot += 32LL * cs[i].ncols;
   }
   r.total = tot;
   if (n > 0) {

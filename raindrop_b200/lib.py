@@ -92,6 +92,10 @@ SIGNATURES = {
     "rd_linear_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rd_linear_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rd_temporal_attention_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_float,
+                                            C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]),
+    "rd_temporal_attention_bwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
+                                            C.c_float, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]),
     "rd_linear_wgrad_partial_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "rd_linear_wgrad_group": (C.c_int, [C.POINTER(RdWgradItem), C.c_int32, C.c_void_p]),
     "rd_transformer_conv_scratch_bytes": (C.c_size_t, [C.c_int32] * 5),

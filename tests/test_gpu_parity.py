@@ -509,6 +509,46 @@ def test_grouped_weight_gradients(shapes):
         assert normwise(db, dY.double().sum(0)) < 2e-5
 
 
+@pytest.mark.parametrize("B,H,T,hd", [(5, 2, 60, 76), (3, 2, 10, 20), (2, 4, 64, 96), (4, 1, 33, 8), (130, 2, 60, 76)])
+def test_temporal_attention_operator(B, H, T, hd):
+    """rd_temporal_attention_fwd/_bwd (tcgen05 kernels) vs an fp64 torch restatement of the masked softmax attention
+    of nn.TransformerEncoderLayer (code/models_rd.py:358), and vs the CUDA-core kernels under dropout (same
+    counter-based masks -> same result)."""
+    from raindrop_b200 import lib as L
+    lib = L.load()
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    D = H * hd
+    qkv = torch.randn(T, B, 3 * D, generator=g).cuda()
+    dctx = torch.randn(T, B, D, generator=g).cuda()
+    lengths = torch.randint(1, T + 1, (B,), generator=g).cuda()
+    lengths[0] = T
+    rng = torch.tensor([12345, 7], dtype=torch.int64, device="cuda")
+
+    def run(impl, p):
+        ctx = torch.full((T, B, D), float("nan"), device="cuda"); dq = torch.full((T, B, 3 * D), float("nan"), device="cuda")
+        L.check(lib.rd_temporal_attention_fwd(qkv.data_ptr(), lengths.data_ptr(), B, H, T, hd, p, rng.data_ptr(), 16, impl,
+                                              ctx.data_ptr(), L.stream_ptr()), "attn fwd")
+        L.check(lib.rd_temporal_attention_bwd(qkv.data_ptr(), dctx.data_ptr(), lengths.data_ptr(), B, H, T, hd, p,
+                                              rng.data_ptr(), 16, impl, dq.data_ptr(), L.stream_ptr()), "attn bwd")
+        torch.cuda.synchronize()
+        return ctx, dq
+
+    ctx, dq = run(1, 0.0)
+    x = qkv.double().requires_grad_(True)
+    q, k, v = (x[:, :, i * D:(i + 1) * D].reshape(T, B, H, hd).permute(1, 2, 0, 3) for i in range(3))
+    s = q @ k.transpose(-1, -2) / hd ** 0.5
+    mask = torch.arange(T, device="cuda")[None, :] >= lengths[:, None]
+    s = s.masked_fill(mask[:, None, None, :], float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).permute(2, 0, 1, 3).reshape(T, B, D)
+    ref.backward(dctx.double())
+    assert normwise(ctx, ref) < 2e-5, normwise(ctx, ref)
+    assert normwise(dq, x.grad) < 2e-5, normwise(dq, x.grad)
+    if T <= 64 and hd <= 96:
+        for p in (0.0, 0.2):
+            c1, d1 = run(1, p); c2, d2 = run(2, p)
+            assert normwise(c1, c2) < 2e-5 and normwise(d1, d2) < 2e-5, (p, normwise(c1, c2), normwise(d1, d2))
+
+
 # ---- training mode --------------------------------------------------------------------------------
 def test_train_mode_dropout_statistics_and_replay():
     """Dropout cannot match the reference's RNG stream; check keep-rate, determinism under the same
