@@ -45,6 +45,12 @@ typedef struct rd_dims {
   float ln_eps;      /* 1e-5                                                              */
   float pe_timescales[RD_D_PE / 2]; /* max_len ** linspace(0,1,8) computed in fp64 on host,
                                        cast to fp32 (code/models_rd.py:31,34)             */
+  int32_t obprop_mode; /* arithmetic of the two observation-propagation GEMMs on the tensor cores:
+                          0 = automatic: error-compensated 3xTF32 (fp32-level, gradients match the fp32 reference
+                              to ~1e-3) while 2*B*N*C^2 <= 2 GFLOP per layer, i.e. where the layer is launch-latency
+                              bound anyway; single-pass TF32 (operands rounded to TF32, forward error ~3e-4) above,
+                              where it is what reaches the HBM / tensor roofline
+                          1 = always single-pass TF32        2 = always 3xTF32                          */
 } rd_dims;
 
 /* Parameters that take part in the live path.  Names = state-dict keys. */

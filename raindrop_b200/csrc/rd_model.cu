@@ -21,6 +21,7 @@ struct Shape {
   int C, Dm, D, Df, hd;
   int64_t M1, M2;
   float p;  // effective dropout probability (0 in eval)
+  int tc, exact;   // ob-prop layers: tensor-core kernel usable / error-compensated (3xTF32) mode chosen
 };
 
 int make_shape(const rd_dims* d, Shape* s) {
@@ -40,6 +41,9 @@ int make_shape(const rd_dims* d, Shape* s) {
   s->M1 = (int64_t)s->B * s->N; s->M2 = (int64_t)s->T * s->B;
   s->p = (d->training && d->dropout_p > 0.f) ? d->dropout_p : 0.f;
   if (s->p >= 1.f) { set_error("dropout_p must be < 1"); return -2; }
+  if (d->obprop_mode < 0 || d->obprop_mode > 2) { set_error("obprop_mode must be 0 (auto), 1 (tf32) or 2 (3xtf32)"); return -2; }
+  s->tc = obprop_tc_supported(s->C) ? 1 : 0;
+  s->exact = (s->tc && obprop_tc_exact(s->M1, s->C, d->obprop_mode)) ? 1 : 0;
   return 0;
 }
 
@@ -49,7 +53,7 @@ struct Arena {
 };
 
 struct WsLayout {
-  int64_t rng, cnt, loss_ps, X0, H1, W1r, W2r, W2t, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
+  int64_t rng, cnt, loss_ps, X0, H1, W1r, W2r, W2t, W1lo, W2lo, W2tlo, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
   struct { int64_t qkv, P, Pd, ctx, r1, st1, x1, f, r2, st2; } l[RD_MAX_LAYERS];
   // error-compensation remainders and transposes of the encoder weights (rd_tc_gemm.cuh)
   struct { int64_t in_lo, in_t, in_tlo, out_lo, out_t, out_tlo, l1_lo, l1_t, l1_tlo, l2_lo, l2_t, l2_tlo; } wsp[RD_MAX_LAYERS];
@@ -65,7 +69,9 @@ WsLayout ws_layout(const Shape& s) {
   w.H1 = a.take(s.M1 * s.C);
   w.W1r = a.take((int64_t)s.C * s.C);   // TF32-rounded copies of the two lin_value weights
   w.W2r = a.take((int64_t)s.C * s.C);
-  w.W2t = a.take((int64_t)s.C * s.C);   // rounded W2^T for the backward d(input) GEMM
+  w.W2t = a.take((int64_t)s.C * s.C);   // (rounded) W2^T for the backward d(input) GEMM
+  const int64_t nlo = s.exact ? (int64_t)s.C * s.C : 0;     // error-compensated mode: remainders of W1, W2, W2^T
+  w.W1lo = a.take(nlo); w.W2lo = a.take(nlo); w.W2tlo = a.take(nlo);
   for (int i = 0; i <= s.L; ++i) w.Z[i] = a.take(s.M2 * s.D);
   // the T x T probabilities only reach HBM on the long-sequence path (the fused short-sequence kernels
   // keep them in shared memory and recompute them in backward)
@@ -245,17 +251,22 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
   if (s.p > 0.f) { pro.rng_state = rng_state; pro.rng_captured = rng; pro.advance = 1; }
   pro.zero_counter = reinterpret_cast<unsigned*>(ws + w.cnt);
   float* X0 = ws + w.X0; float* H1 = ws + w.H1;
-  // Tensor-core operands are kept exactly TF32-representable by their producers (lift, layer-1
-  // epilogue, rounded weight copies) so the MMA's operand truncation is exact.
-  const int tc = obprop_tc_supported(s.C) ? 1 : 0;
+  // Fast mode: tensor-core operands are kept exactly TF32-representable by their producers (lift, layer-1 epilogue,
+  // rounded weight copies) so the MMA's operand truncation is exact.  Error-compensated mode (latency-bound row
+  // counts): operands stay fp32, the weights come with their remainders, nothing is rounded.
+  const int tc = s.tc, exact = s.exact;
   const float* W1 = P->ob1_value_weight; const float* W2 = P->ob2_value_weight;
-  if (tc) { W1 = ws + w.W1r; W2 = ws + w.W2r; }   // rounded copies, produced by the weight-prep launch just below
+  if (tc && !exact) { W1 = ws + w.W1r; W2 = ws + w.W2r; }   // rounded copies, produced by the weight-prep launch just below
   for (int l0 = 0; l0 < s.L; l0 += 3) {   // every derived weight tensor of the step in one launch (<= 16 tensors each)
     WeightSplit items[16];
     int n = 0;
-    if (l0 == 0 && tc) {
+    if (l0 == 0 && tc && !exact) {
       items[n] = {P->ob1_value_weight, s.C, s.C, nullptr, nullptr, nullptr}; items[n++].rn = ws + w.W1r;
       items[n] = {P->ob2_value_weight, s.C, s.C, nullptr, nullptr, nullptr}; items[n].rn = ws + w.W2r; items[n++].rn_t = ws + w.W2t;
+    }
+    if (l0 == 0 && exact) {
+      items[n++] = {P->ob1_value_weight, s.C, s.C, ws + w.W1lo, nullptr, nullptr};
+      items[n++] = {P->ob2_value_weight, s.C, s.C, ws + w.W2lo, ws + w.W2t, ws + w.W2tlo};
     }
     for (int l = l0; l < s.L && l < l0 + 3; ++l) {
       const rd_encoder_layer_params& E = P->layer[l];
@@ -268,13 +279,15 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
   }
   float* Z0 = ws + w.Z[0];
   // lift of the raw observations and the positional encoding (written into Z0[..., 4N:]) in one launch
-  RD_TRY(lift_posenc(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, tc, X0, times, s.M2, dims->pe_timescales, Z0, s.D, s.Dm, st));
+  RD_TRY(lift_posenc(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, tc && !exact, X0, times, s.M2, dims->pe_timescales, Z0, s.D, s.Dm, st));
   {
     ObpropTcArgs a;
     a.x = X0; a.W = W1; a.bias = P->ob1_value_bias; a.scale = nscale; a.scale_mod = s.N;
-    a.rows = s.M1; a.C = s.C; a.out = H1; a.round_out = tc;
+    a.rows = s.M1; a.C = s.C; a.out = H1; a.round_out = tc && !exact;
+    a.W_lo = exact ? ws + w.W1lo : nullptr;
     RD_TRY(obprop_forward(a, st));
     a.x = H1; a.W = W2; a.bias = P->ob2_value_bias; a.out = Z0; a.round_out = 0;
+    a.W_lo = exact ? ws + w.W2lo : nullptr;
     a.perm = 1; a.pB = s.B; a.pN = s.N; a.pdob = s.dob; a.pD = s.D;
     RD_TRY(obprop_forward(a, st));
   }
@@ -460,14 +473,15 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
   // ---- observation propagation: gA = d(loss)/d(Z0) [T,B,D]          code/models_rd.py:322-343
   float* gO2 = sc + b.gO2; float* gO1 = sc + b.gO1;
   const float* X0 = ws + w.X0; const float* H1 = ws + w.H1;
-  const int tc = obprop_tc_supported(s.C) ? 1 : 0;
-  RD_TRY(obprop_out_grad(gA, ws + w.Z[0], nscale, s.B, s.T, s.N, s.dob, s.D, tc, gO2, st));
+  const int tc = s.tc;
+  RD_TRY(obprop_out_grad(gA, ws + w.Z[0], nscale, s.B, s.T, s.N, s.dob, s.D, tc && !s.exact, gO2, st));
   RD_TRY(tn(&wq, gO2, s.C, H1, s.C, G->ob2_value_weight, G->ob2_value_bias, s.C, s.C, s.M1, sc + b.wp_ob[0], partial, st));
   if (tc) {
     // dZ1 = (dZ2 . W2) * s * [H1 > 0] on the tensor cores: "NT" form against a transposed, TF32-rounded W2
     const float* W2t = ws + w.W2t;      // written by the forward's weight-prep launch
     ObpropTcArgs a;
     a.x = gO2; a.W = W2t; a.bias = nullptr; a.relu = 0; a.scale = nscale; a.scale_mod = s.N; a.gate = H1;
+    a.W_lo = s.exact ? ws + w.W2tlo : nullptr;
     a.rows = s.M1; a.C = s.C; a.out = gO1;
     RD_TRY(obprop_tc_fwd(a, st));
   } else {
@@ -513,12 +527,18 @@ int rd_obprop_fwd(const float* x, const float* weight, const float* bias, const 
   cudaStream_t st = (cudaStream_t)stream;
   ObpropTcArgs a;
   a.x = x; a.W = weight; a.bias = bias; a.scale = nscale; a.scale_mod = mod; a.rows = rows; a.C = C; a.out = out;
-  if (obprop_tc_supported(C) && scratch) {   // arbitrary caller data: round both operands to TF32 first
+  if (obprop_tc_supported(C) && scratch) {   // arbitrary caller data
     float* xr = (float*)scratch;
     float* wr = xr + round_up(rows * C, 64);
-    RD_TRY(round_tf32(x, rows * C, xr, st));
-    RD_TRY(round_tf32(weight, (int64_t)C * C, wr, st));
-    a.x = xr; a.W = wr;
+    if (obprop_tc_exact(rows, C, 0)) {        // latency-bound size: error-compensated kernel, operands as they are
+      WeightSplit it = {weight, C, C, wr, nullptr, nullptr};
+      RD_TRY(split_weights(&it, 1, st));
+      a.W_lo = wr;
+    } else {                                  // streaming size: round both operands to TF32 first, single pass
+      RD_TRY(round_tf32(x, rows * C, xr, st));
+      RD_TRY(round_tf32(weight, (int64_t)C * C, wr, st));
+      a.x = xr; a.W = wr;
+    }
   }
   return obprop_forward(a, st);
 }

@@ -34,7 +34,8 @@ namespace {
 constexpr int BM = 128;
 constexpr int BK = 32;                 // tf32 per k-block: 128 bytes = one swizzle row
 constexpr int MAX_STAGES = 4;
-constexpr int NTHREADS = 192;
+constexpr int NTHREADS = 192;                // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue
+constexpr int NTHREADS_EXACT = 320;          // + warps 6-9: remainder pass of the error-compensated mode
 constexpr int A_STAGE_BYTES = BM * BK * 4;   // 16 KB
 constexpr int STG_BYTES = 4096;              // 32 rows x 32 floats per epilogue warp buffer
 
@@ -56,15 +57,21 @@ __device__ __forceinline__ float epi1(float acc, float bias, float sc, int relu,
   return rnd ? rn_tf32(v) : v;
 }
 
-// PERM / GATE / RELU / ROUND are compile-time so the streaming epilogue carries no runtime branches
-template <bool PERM, bool GATE, bool RELU, bool ROUND>
-__global__ void __launch_bounds__(NTHREADS, 1)
+// PERM / GATE / RELU / ROUND are compile-time so the streaming epilogue carries no runtime branches.
+// EXACT: error-compensated products (3xTF32, fp32-level accuracy) for the latency-bound row counts where the
+// tensor pipe has slack: the weight tile comes with its precomputed remainder (tmWlo), four extra warps derive the
+// activation remainder x - trunc19(x) in shared memory, and every k-step issues lo.hi + hi.lo + hi.hi.
+template <bool PERM, bool GATE, bool RELU, bool ROUND, bool EXACT>
+__global__ void __launch_bounds__(EXACT ? NTHREADS_EXACT : NTHREADS, 1)
 obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
-                 const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
+                 const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const uint32_t stage_bytes = A_STAGE_BYTES + (uint32_t)p.BN * 128u;
+  const uint32_t w_tile = (uint32_t)p.BN * 128u;
+  // stage: x hi [| x lo] | W hi [| W lo]
+  const uint32_t stage_bytes = EXACT ? 2u * A_STAGE_BYTES + 2u * w_tile : A_STAGE_BYTES + w_tile;
+  const uint32_t w_off = EXACT ? 2u * A_STAGE_BYTES : (uint32_t)A_STAGE_BYTES;
   const uint32_t stg_base = base + (uint32_t)p.nstages * stage_bytes;        // 8 x 4 KB staging
   const uint32_t bias_base = stg_base + 8 * STG_BYTES;                        // 2 x 256 floats
   const uint32_t bar_base = bias_base + 2 * 256 * 4;
@@ -73,17 +80,19 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  auto ready_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 6 + s); };     // EXACT: remainders written
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmW) : "memory");
+    if (EXACT) asm volatile("prefetch.tensormap [%0];" ::"l"(&tmWlo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmOut) : "memory");
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), 4); }
       for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -105,10 +114,11 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const int m_t = tile / p.n_tiles, n_t = tile - m_t * p.n_tiles;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), stage_bytes);
+          mbar_expect_tx(full_bar(stage), EXACT ? A_STAGE_BYTES + 2u * w_tile : stage_bytes);
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
           tma_load_2d(&tmA, full_bar(stage), sa, kb * BK, m_t * BM);
-          tma_load_2d(&tmW, full_bar(stage), sa + A_STAGE_BYTES, kb * BK, n_t * p.BN);
+          tma_load_2d(&tmW, full_bar(stage), sa + w_off, kb * BK, n_t * p.BN);
+          if (EXACT) tma_load_2d(&tmWlo, full_bar(stage), sa + w_off + w_tile, kb * BK, n_t * p.BN);
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -123,18 +133,52 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(EXACT ? ready_bar(stage) : full_bar(stage), phase);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-          const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + A_STAGE_BYTES);
+          const uint64_t adesc = umma_desc_sw128(sa), bdesc = umma_desc_sw128(sa + w_off);
+          if (EXACT) {
+            const uint64_t alo = umma_desc_sw128(sa + A_STAGE_BYTES), blo = umma_desc_sw128(sa + w_off + w_tile);
 #pragma unroll
-          for (int kk = 0; kk < BK / 8; ++kk)  // advance 32 bytes (8 tf32) inside the swizzle row
-            umma_tf32(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+            for (int kk = 0; kk < BK / 8; ++kk) {
+              const uint64_t o = (uint64_t)(kk * 2);
+              umma_tf32(d_tmem, alo + o, bdesc + o, idesc, (kb | kk) ? 1u : 0u);     // small terms first
+              umma_tf32(d_tmem, adesc + o, blo + o, idesc, 1u);
+              umma_tf32(d_tmem, adesc + o, bdesc + o, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < BK / 8; ++kk)  // advance 32 bytes (8 tf32) inside the swizzle row
+              umma_tf32(d_tmem, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), idesc, (kb | kk) ? 1u : 0u);
+          }
           umma_commit(empty_bar(stage));  // smem slot reusable once these MMAs have read it
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));       // accumulator complete -> epilogue
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
+      }
+    }
+  } else if (EXACT && warp >= 6) {
+    // ===== remainder pass (warps 6..9): x_lo = x - trunc19(x), same swizzled addresses =================
+    const int lt = threadIdx.x - 192;
+    int stage = 0; uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+#pragma unroll
+        for (int v = 0; v < A_STAGE_BYTES / 16 / 128; ++v) {
+          const uint32_t o = (uint32_t)(lt + 128 * v) * 16u;
+          float4 x;
+          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(sa + o));
+          x.x -= __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); x.y -= __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          x.z -= __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); x.w -= __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + A_STAGE_BYTES + o), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(stage));
+        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
@@ -244,6 +288,15 @@ bool obprop_tc_supported(int C) {
   return env == 1 && C % 4 == 0 && C >= 16;
 }
 
+bool obprop_tc_exact(int64_t rows, int C, int mode) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("RD_OBPROP_EXACT"); env = e ? (e[0] == '0' ? 1 : 2) : 0; }
+  if (mode == 0) mode = env;
+  if (mode == 1) return false;
+  if (mode == 2) return true;
+  return 2.0 * (double)rows * C * C <= 2.0e9;
+}
+
 __global__ void round_tf32_kernel(const float* __restrict__ x, long long n, float* __restrict__ y) {
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) {
@@ -271,12 +324,14 @@ int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st) {
     set_error("obprop_tc_fwd: pointers must be 16-byte aligned");
     return -2;
   }
+  const bool exact = a.W_lo != nullptr;
+  if (exact && (reinterpret_cast<uintptr_t>(a.W_lo) & 15)) { set_error("obprop_tc_fwd: W_lo must be 16-byte aligned"); return -2; }
   TcParams p;
   p.M = (int)rows; p.C = C;
   plan_n(C, &p.BN, &p.n_tiles);
   p.m_tiles = (int)ceil_div(rows, BM);
   p.k_blocks = (int)ceil_div(C, BK);
-  const int stage_bytes = A_STAGE_BYTES + p.BN * 128;
+  const int stage_bytes = exact ? 2 * A_STAGE_BYTES + 2 * p.BN * 128 : A_STAGE_BYTES + p.BN * 128;
   const int fixed = 1024 + 8 * STG_BYTES + 2 * 256 * 4 + 256;
   p.nstages = (SMEM_LIMIT - fixed) / stage_bytes;
   if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
@@ -286,7 +341,7 @@ int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st) {
   p.relu = a.relu; p.round_out = a.round_out;
   p.perm = perm; p.pB = pB; p.pN = pN; p.pD = pD; p.out = out;
 
-  CUtensorMap tmA, tmW, tmOut;
+  CUtensorMap tmA, tmW, tmWlo, tmOut;
   {
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
     cuuint64_t str[1] = {(cuuint64_t)C * 4};
@@ -298,6 +353,8 @@ int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st) {
     cuuint64_t str[1] = {(cuuint64_t)C * 4};
     cuuint32_t box[2] = {BK, (cuuint32_t)p.BN};
     RD_TRY(encode(&tmW, W, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "W"));
+    if (exact) RD_TRY(encode(&tmWlo, a.W_lo, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_128B, "W_lo"));
+    else tmWlo = tmW;
   }
   if (!perm) {
     cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
@@ -309,18 +366,26 @@ int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st) {
   }
   int total = p.m_tiles * p.n_tiles;
   int grid = total < num_sms() ? total : num_sms();
-  auto launch = [&](auto kern, int) -> int {
+  auto launch = [&](auto kern, int nthreads) -> int {
     RD_TRY(ensure_max_smem((const void*)kern, SMEM_LIMIT));   // once per (instantiation, device)
-    kern<<<grid, NTHREADS, smem_bytes, st>>>(tmA, tmW, tmOut, p);
+    kern<<<grid, nthreads, smem_bytes, st>>>(tmA, tmW, tmWlo, tmOut, p);
     return 0;
   };
   int rc;
   const bool relu = a.relu != 0, rnd = a.round_out != 0;
-  if (perm && !a.gate && relu && !rnd) rc = launch(obprop_tc_kernel<true, false, true, false>, 0);        // layer 2 -> encoder input
-  else if (!perm && !a.gate && relu && rnd) rc = launch(obprop_tc_kernel<false, false, true, true>, 1);   // layer 1
-  else if (!perm && !a.gate && relu && !rnd) rc = launch(obprop_tc_kernel<false, false, true, false>, 2); // operator
-  else if (!perm && a.gate && !relu && !rnd) rc = launch(obprop_tc_kernel<false, true, false, false>, 3); // backward d(input)
-  else { set_error("obprop_tc_fwd: epilogue combination not instantiated"); return -2; }
+  if (!exact) {
+    if (perm && !a.gate && relu && !rnd) rc = launch(obprop_tc_kernel<true, false, true, false, false>, NTHREADS);        // layer 2 -> encoder input
+    else if (!perm && !a.gate && relu && rnd) rc = launch(obprop_tc_kernel<false, false, true, true, false>, NTHREADS);   // layer 1
+    else if (!perm && !a.gate && relu && !rnd) rc = launch(obprop_tc_kernel<false, false, true, false, false>, NTHREADS); // operator
+    else if (!perm && a.gate && !relu && !rnd) rc = launch(obprop_tc_kernel<false, true, false, false, false>, NTHREADS); // backward d(input)
+    else { set_error("obprop_tc_fwd: epilogue combination not instantiated"); return -2; }
+  } else {
+    if (rnd) { set_error("obprop_tc_fwd: the error-compensated mode does not round its output"); return -2; }
+    if (perm && !a.gate && relu) rc = launch(obprop_tc_kernel<true, false, true, false, true>, NTHREADS_EXACT);
+    else if (!perm && !a.gate && relu) rc = launch(obprop_tc_kernel<false, false, true, false, true>, NTHREADS_EXACT);
+    else if (!perm && a.gate && !relu) rc = launch(obprop_tc_kernel<false, true, false, false, true>, NTHREADS_EXACT);
+    else { set_error("obprop_tc_fwd: epilogue combination not instantiated"); return -2; }
+  }
   if (rc != 0) return rc;
   RD_CHECK_LAUNCH("obprop_tc_kernel");
   return 0;

@@ -68,12 +68,13 @@ class Plan:
         self.R_u = None             # [1, N*d_ob] device tensor
         self.rng_state = None       # int64[2] device tensor {seed, counter}
         self.owner = None           # weakref to the module (receives the flat gradient bucket)
+        self.obprop_mode = 0        # 0 auto, 1 single-pass TF32, 2 error-compensated 3xTF32 (rd_dims.obprop_mode)
         self.debug_keep_workspace = False   # tests: keep the last forward's workspace for workspace_view()
         self.last_workspace = None
         self.last_dims = None
 
     def dims(self, B, training):
-        key = (B, bool(training))
+        key = (B, bool(training), self.obprop_mode)
         cache = self.__dict__.setdefault("_dims_cache", {})
         d = cache.get(key)
         if d is not None:
@@ -89,6 +90,7 @@ class Plan:
         d.training = 1 if training else 0
         d.dropout_p = self.dropout
         d.ln_eps = 1e-5
+        d.obprop_mode = int(self.obprop_mode)
         for i, v in enumerate(self.timescales):
             d.pe_timescales[i] = float(v)
         return d
@@ -125,16 +127,16 @@ class RaindropV2Function(torch.autograd.Function):
                 _set_field(P, path, ptr_)
             plan.__dict__["_param_struct"] = (ptrs, P)
         sizes = plan.__dict__.setdefault("_ws_bytes", {})
-        ws_bytes = sizes.get((B, bool(training)))
+        ws_bytes = sizes.get((B, bool(training), plan.obprop_mode))
         if ws_bytes is None:
-            ws_bytes = sizes[(B, bool(training))] = (lib.rd_workspace_bytes(C.byref(dims)),
+            ws_bytes = sizes[(B, bool(training), plan.obprop_mode)] = (lib.rd_workspace_bytes(C.byref(dims)),
                                                      lib.rd_backward_scratch_bytes(C.byref(dims)))
         ws_bytes, sc_bytes = ws_bytes
         if ws_bytes == 0:
             L.check(-2, "rd_workspace_bytes")
         # activation workspace: recycled through a small per-(B, mode) pool (a forward whose backward has not run
         # yet keeps its workspace; everything else reuses the last one instead of a fresh multi-MB allocation)
-        pool = plan.__dict__.setdefault("_ws_pool", {}).setdefault((B, bool(training), src.device.index), [])
+        pool = plan.__dict__.setdefault("_ws_pool", {}).setdefault((B, bool(training), src.device.index, plan.obprop_mode), [])
         ws = pool.pop() if pool else torch.empty(ws_bytes // 4, dtype=torch.float32, device=src.device)
         logits = torch.empty(B, plan.n_classes, dtype=torch.float32, device=src.device)
         rng = plan.rng_state
@@ -315,6 +317,8 @@ def flat_forward(plan, training, flat, src, static, times, lengths):
     slots = plan.__dict__.setdefault("_slots", {})
     k = (B, bool(training), dev.index)
     slot = slots.get(k)
+    if slot is not None and slot.dims.obprop_mode != plan.obprop_mode:
+        slot = None                      # arithmetic mode changed: new workspace layout, new graphs
     key = (flat.flat_p.data_ptr(), flat.flat_g.data_ptr(), plan.R_u.data_ptr(), plan.node_scale.data_ptr(),
            plan.rng_state.data_ptr())
     if slot is None or slot.key != key:      # pointers changed (graph / R_u / optimiser re-created): rebuild

@@ -28,7 +28,7 @@ class RdDims(C.Structure):
                 ("nhead", C.c_int32), ("nhid", C.c_int32), ("nlayers", C.c_int32),
                 ("d_static", C.c_int32), ("n_classes", C.c_int32), ("training", C.c_int32),
                 ("dropout_p", C.c_float), ("ln_eps", C.c_float),
-                ("pe_timescales", C.c_float * (RD_D_PE // 2))]
+                ("pe_timescales", C.c_float * (RD_D_PE // 2)), ("obprop_mode", C.c_int32)]
 
 
 _LAYER_FIELDS = ["in_proj_weight", "in_proj_bias", "out_proj_weight", "out_proj_bias",

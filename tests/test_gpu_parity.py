@@ -17,22 +17,28 @@ from raindrop_b200.synth import make_batch, model_config, synth_weights, used_pa
 pytestmark = pytest.mark.gpu
 
 FWD_TOL = 1e-3     # north_star tolerance on forward tensors
-# Gradients.  The two observation-propagation GEMMs take TF32 operands.  Their forward error is ~3e-4,
-# but the gradient of a ReLU network is DISCONTINUOUS in forward perturbations: a pre-activation within
-# 3e-4 of zero flips its gate and moves a few isolated gradient entries by up to ~10 % of max|grad| while
-# the mean error stays ~0.3 % (measured with the CPU precision model, DESIGN.md section "Precision").
-# So against the fp32 reference we use
-#   * max-norm for every parameter outside the ob-prop layers   (GRAD_TOL),
-#   * relative L2 for the two lin_value weights/biases           (OBPROP_GRAD_L2),
-# and against the oracle evaluated under the kernels' rounding model (`tf32_model=True`) a tight
-# max-norm (relative L2 for the two lin_value tensors, where a single flipped gate of a small batch is visible) -- that is the check that proves the kernels compute what they claim.
+# The two observation-propagation GEMMs run in one of two arithmetic modes (rd_dims.obprop_mode):
+#   EXACT (2, and what "auto" picks at every latency-bound size incl. the benchmarked P19 B=128): error-compensated
+#       3xTF32, fp32-level.  Every one of the 34 gradients must match the fp32 reference to GRAD_TOL_EXACT max-norm
+#       and the ob-prop output to 1e-5.
+#   FAST (1, what "auto" picks in the HBM-/tensor-bound regime): single-pass TF32 on operands rounded to TF32.
+#       Forward error ~3e-4, but the gradient of a ReLU network is DISCONTINUOUS in forward perturbations: a
+#       pre-activation within 3e-4 of zero flips its gate and moves a few isolated gradient entries by up to ~10 % of
+#       max|grad| while the mean error stays ~0.3 % (DESIGN.md section "Precision").  There we use max-norm GRAD_TOL for
+#       every parameter outside the ob-prop layers, relative L2 OBPROP_GRAD_L2 for the two lin_value weights/biases,
+#       and a tight check against the oracle evaluated under the kernels' rounding model (`tf32_model=True`).
+GRAD_TOL_EXACT = 2e-3
 GRAD_TOL = 2e-2
 OBPROP_GRAD_L2 = 5e-2
 MODEL_TOL = 5e-3
+EXACT, FAST = 2, 1
 
 
-def _grad_check_fp32(name, got, ref):
-    if "lin_value" in name:
+def _grad_check_fp32(name, got, ref, mode=FAST):
+    if mode == EXACT:
+        e = normwise(got, ref)
+        assert e < GRAD_TOL_EXACT, (name, "normwise (exact mode)", e)
+    elif "lin_value" in name:
         e = rel_l2(got, ref)
         assert e < OBPROP_GRAD_L2, (name, "rel_l2", e)
     else:
@@ -42,12 +48,13 @@ def _grad_check_fp32(name, got, ref):
 GOLDEN_CASES = ["tiny_dense", "tiny_t0", "tiny_sparse", "tiny8_nostatic", "p19_b4", "p19_b5_leave10", "p12_b2", "pam_b2"]
 
 
-def _run_dropin(cfg, batch, weight_seed, train=False):
+def _run_dropin(cfg, batch, weight_seed, train=False, mode=0):
     from raindrop_b200 import functional as RF
     from raindrop_b200 import lib as L
     model = build_dropin(cfg, weight_seed)
     model.train(train)
     model._plan.debug_keep_workspace = True
+    model._plan.obprop_mode = mode
     d = to_dev(batch)
     logits, distance, third = model.forward(d["src"], d["static"], d["times"], d["lengths"])
     assert third is None and distance.dim() == 0
@@ -60,19 +67,21 @@ def _run_dropin(cfg, batch, weight_seed, train=False):
     return model, logits, distance, loss, enc_in, enc_out
 
 
+@pytest.mark.parametrize("mode", [EXACT, FAST], ids=["exact", "fast"])
 @pytest.mark.parametrize("name", GOLDEN_CASES)
-def test_golden_fixture(golden_dir, name):
-    """CUDA forward + backward vs the outputs of the reference's own unmodified files."""
+def test_golden_fixture(golden_dir, name, mode):
+    """CUDA forward + backward vs the outputs of the reference's own unmodified files, in both arithmetic modes of
+    the ob-prop GEMMs."""
     z, meta = load_golden(golden_dir, name)
     cfg, batch = case_setup(meta)
-    model, logits, distance, loss, enc_in, enc_out = _run_dropin(cfg, batch, meta["weight_seed"])
+    model, logits, distance, loss, enc_in, enc_out = _run_dropin(cfg, batch, meta["weight_seed"], mode=mode)
     errs = {}
-    assert normwise(logits, z["logits"]) < FWD_TOL
+    assert normwise(logits, z["logits"]) < (1e-4 if mode == EXACT else FWD_TOL)
     assert abs(loss.item() - float(z["loss"])) < 1e-3 * max(1.0, abs(float(z["loss"])))
     assert float(distance) == float(z["distance"]) == 0.0
     full = meta["full_tensors"]
     D4 = cfg["d_inp"] * cfg["d_ob"]
-    check_against_golden(z, full, "obs", enc_in[:, :, :D4], FWD_TOL, errs)
+    check_against_golden(z, full, "obs", enc_in[:, :, :D4], 1e-5 if mode == EXACT else FWD_TOL, errs)
     check_against_golden(z, full, "pe", enc_in[:, :, D4:], 1e-5, errs)
     # the encoder output at padded positions is never used by the reference (masked mean) -> compare valid rows
     lengths = batch["lengths"]
@@ -85,13 +94,15 @@ def test_golden_fixture(golden_dir, name):
     params = dict(model.named_parameters())
     for k in used_param_keys(cfg):
         assert params[k].grad is not None, k
-        if "lin_value" in k:
+        if mode == EXACT:
+            check_against_golden(z, full, "grad." + k, params[k].grad, GRAD_TOL_EXACT, errs)
+        elif "lin_value" in k:
             check_against_golden(z, full, "grad." + k, params[k].grad, OBPROP_GRAD_L2 * (1 if full else 2), errs, metric=rel_l2)
         else:
             check_against_golden(z, full, "grad." + k, params[k].grad, GRAD_TOL, errs)
     unused = [k for k, p in params.items() if k not in set(used_param_keys(cfg))]
     assert all(params[k].grad is None for k in unused)     # same 34 tensors get gradient as in the reference
-    print(name, "worst:", max(errs.items(), key=lambda kv: kv[1]))
+    print(name, "mode", mode, "worst:", max(errs.items(), key=lambda kv: kv[1]))
 
 
 @pytest.mark.parametrize("cfg_name,B,opts", [
@@ -110,14 +121,26 @@ def test_against_oracle(cfg_name, B, opts):
     ref_logits, _, _ = oracle.forward_dense(batch["src"], batch["static"], batch["times"], batch["lengths"], stages=stages)
     ref_loss = F.cross_entropy(ref_logits, batch["y"])
     ref_loss.backward()
-    model, logits, _, loss, enc_in, enc_out = _run_dropin(cfg, batch, 21)
     D4 = cfg["d_inp"] * cfg["d_ob"]
-    assert normwise(enc_in[:, :, :D4], stages["obs"]) < FWD_TOL
+    go = dict(oracle.named_parameters())
+    ref_grads = {k: go[k].grad.clone() for k in used_param_keys(cfg)}
+    # ---- error-compensated mode: fp32-level agreement with the fp32 oracle, every tensor -------------
+    model, logits, _, loss, enc_in, enc_out = _run_dropin(cfg, batch, 21, mode=EXACT)
+    assert normwise(enc_in[:, :, :D4], stages["obs"]) < 1e-5
     assert normwise(enc_in[:, :, D4:], stages["pe"]) < 1e-5
-    assert normwise(logits, ref_logits) < FWD_TOL
-    gp, go = dict(model.named_parameters()), dict(oracle.named_parameters())
+    assert normwise(logits, ref_logits) < 1e-4
+    gp = dict(model.named_parameters())
+    worst = max((normwise(gp[k].grad, ref_grads[k]), k) for k in used_param_keys(cfg))
+    print(cfg_name, B, "exact-mode worst gradient error", worst)
     for k in used_param_keys(cfg):
-        _grad_check_fp32(k, gp[k].grad, go[k].grad)
+        _grad_check_fp32(k, gp[k].grad, ref_grads[k], EXACT)
+    # ---- single-pass TF32 mode ----------------------------------------------------------------------
+    model, logits, _, loss, enc_in, enc_out = _run_dropin(cfg, batch, 21, mode=FAST)
+    assert normwise(enc_in[:, :, :D4], stages["obs"]) < FWD_TOL
+    assert normwise(logits, ref_logits) < FWD_TOL
+    gp = dict(model.named_parameters())
+    for k in used_param_keys(cfg):
+        _grad_check_fp32(k, gp[k].grad, ref_grads[k], FAST)
     # same model evaluated under the kernels' TF32 rounding model: everything must agree tightly
     oracle.zero_grad()
     st2 = {}
@@ -154,14 +177,26 @@ def test_random_shapes_against_oracle(seed):
     batch = make_batch(cfg, B, seed=seed, first_time_zero=bool(ri(0, 1)))
     oracle = build_oracle_model(cfg).eval()
     synth_weights(oracle, cfg, seed=40 + seed)
+    shape = {kk: cfg[kk] for kk in ("d_inp", "max_len", "batch", "nlayers", "n_classes", "static")}
+    # single-pass TF32 mode vs the oracle under the kernels' rounding model
     ref, _, _ = oracle.forward_dense(batch["src"], batch["static"], batch["times"], batch["lengths"], tf32_model=True)
     F.cross_entropy(ref, batch["y"]).backward()
-    model, logits, _, loss, enc_in, _ = _run_dropin(cfg, batch, 40 + seed)
+    model, logits, _, loss, enc_in, _ = _run_dropin(cfg, batch, 40 + seed, mode=FAST)
     assert normwise(logits, ref.detach()) < 2e-4, (cfg, normwise(logits, ref.detach()))
     gp, go = dict(model.named_parameters()), dict(oracle.named_parameters())
     for k in used_param_keys(cfg):
         e = rel_l2(gp[k].grad, go[k].grad)
-        assert e < 5e-2, (k, e, {kk: cfg[kk] for kk in ("d_inp", "max_len", "batch", "nlayers", "n_classes", "static")})
+        assert e < 5e-2, (k, e, shape)
+    # error-compensated mode (what "auto" selects at these sizes) vs the plain fp32 oracle
+    oracle.zero_grad()
+    ref, _, _ = oracle.forward_dense(batch["src"], batch["static"], batch["times"], batch["lengths"])
+    F.cross_entropy(ref, batch["y"]).backward()
+    model, logits, _, loss, enc_in, _ = _run_dropin(cfg, batch, 40 + seed, mode=0)
+    assert normwise(logits, ref.detach()) < 1e-4, (cfg, normwise(logits, ref.detach()))
+    gp = dict(model.named_parameters())
+    for k in used_param_keys(cfg):
+        e = normwise(gp[k].grad, go[k].grad)
+        assert e < GRAD_TOL_EXACT, (k, e, shape)
 
 
 def test_edge_cases():
