@@ -253,6 +253,31 @@ int rd_transformer_conv_fwd(const float* x, int32_t n_nodes, int32_t in_ch, int3
 int rd_gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_total, int32_t width, int32_t B,
                     float* out, void* stream);
 
+/* Whole-batch assembly in ONE launch: for j < B copies sample idx[j] of the resident tensors P [T, n_total, width],
+ * Ptime [T, n_total], Pstatic [n_total, d_static] (may be NULL), y [n_total] (may be NULL) into the batch buffers and
+ * writes lengths[j] = #(Ptime[:, idx[j]] > 0)  (code/Raindrop.py:311-317).  width % 4 == 0. */
+int rd_assemble_batch(const float* P, const float* Ptime, const float* Pstatic, const int64_t* y, const int64_t* idx,
+                      int32_t T, int64_t n_total, int32_t width, int32_t d_static, int32_t B, float* src, float* times,
+                      float* statics, int64_t* y_out, int64_t* lengths, void* stream);
+
+/* Per-feature statistics of the OBSERVED entries (value > 0) of raw [n, T, F]: mean and population standard deviation
+ * (floored at 1e-7), accumulated in double -- getStats, code/utils_rd.py:149-161.
+ * scratch: rd_feature_stats_scratch_bytes(n, T, F) bytes. */
+size_t rd_feature_stats_scratch_bytes(int64_t n, int32_t T, int32_t F);
+int rd_feature_stats(const float* raw, int64_t n, int32_t T, int32_t F, float* mean, float* std, void* scratch,
+                     void* stream);
+/* mask_normalize (code/utils_rd.py:164-175) fused with the concat of the observation mask and the permute to the
+ * training layout (code/Raindrop.py:233): raw [n, T, F] -> out [T, n, 2F] with
+ *   out[t, i, f] = raw > 0 ? (raw - mean_f) / (std_f + 1e-18) : 0      out[t, i, F + f] = raw > 0
+ * minutes (optional) [n, T] -> times_out [T, n] = minutes / 60 (code/utils_rd.py:235). */
+int rd_mask_normalize(const float* raw, const float* mean, const float* std, int64_t n, int32_t T, int32_t F,
+                      float* out, const float* minutes, float* times_out, void* stream);
+/* Leave-sensors-out masking of a batch P [T, B, width = 2F] (code/Raindrop.py:214-231): zero the VALUE columns
+ * idx[k], k < K; per_sample != 0: idx is [B, K] (feature_removal_level 'sample'), else [K] ('set').  The mask columns
+ * are left untouched, exactly as in the reference. */
+int rd_zero_features(float* P, int64_t T, int32_t B, int32_t width, const int64_t* idx, int32_t K, int32_t per_sample,
+                     void* stream);
+
 /* ---- training-step helpers (the caller-side ops of code/Raindrop.py:321-324) ----------------
  * mean cross entropy + d(loss)/d(logits), torch.nn.CrossEntropyLoss semantics. */
 int rd_cross_entropy_fwd_bwd(const float* logits, const int64_t* y, int32_t B, int32_t n_classes,

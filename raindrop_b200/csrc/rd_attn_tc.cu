@@ -55,12 +55,7 @@ __device__ __forceinline__ float lo_of(float v) { return v - __uint_as_float(__f
 
 // lo image (at +lo_off) of `bytes` bytes of hi image; same addresses, so the swizzle never has to be undone
 __device__ __forceinline__ void lo_pass(uint32_t hi, uint32_t lo_off, uint32_t bytes) {
-  for (uint32_t o = threadIdx.x * 16u; o < bytes; o += NTHR * 16u) {
-    float4 x;
-    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(hi + o));
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(hi + lo_off + o), "f"(lo_of(x.x)), "f"(lo_of(x.y)),
-                 "f"(lo_of(x.z)), "f"(lo_of(x.w)) : "memory");
-  }
+  lo_image<6>(hi, hi + lo_off, bytes / 16u, threadIdx.x, (uint32_t)NTHR);
 }
 
 // D[128 x N] (+)= A . B with error compensation.  Operand images: hi at base, lo at base + *_lo.

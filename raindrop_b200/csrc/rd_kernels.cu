@@ -73,6 +73,124 @@ __global__ void gather_batch_kernel(const float* __restrict__ src, const int64_t
   else dst[c] = __ldg(in + c);
 }
 
+// ---- device-side input pipeline (code/utils_rd.py:149-175,221-257, code/Raindrop.py:214-231,293-317) -------------
+// per-feature {count, sum, sum of squares} over the OBSERVED entries (value > 0) of raw[n, T, F], in double;
+// grid (chunks, F): each CTA walks a slice of the n*T entries of one feature, fixed-order tree reduce
+constexpr int FS_THREADS = 256;
+__global__ void __launch_bounds__(FS_THREADS) feature_stats_partial_kernel(const float* __restrict__ raw, long long nT, int F,
+                                                                          double* __restrict__ partial) {
+  __shared__ double sh[3][FS_THREADS];
+  const int f = blockIdx.y;
+  const long long per = (nT + gridDim.x - 1) / gridDim.x;
+  const long long i0 = (long long)blockIdx.x * per, i1 = min(nT, i0 + per);
+  double c = 0.0, s = 0.0, q = 0.0;
+  for (long long i = i0 + threadIdx.x; i < i1; i += FS_THREADS) {
+    const float v = __ldg(raw + i * F + f);
+    if (v > 0.f) { c += 1.0; s += (double)v; q += (double)v * (double)v; }
+  }
+  sh[0][threadIdx.x] = c; sh[1][threadIdx.x] = s; sh[2][threadIdx.x] = q;
+  __syncthreads();
+  for (int o = FS_THREADS / 2; o > 0; o >>= 1) {
+    if (threadIdx.x < o) {
+      sh[0][threadIdx.x] += sh[0][threadIdx.x + o]; sh[1][threadIdx.x] += sh[1][threadIdx.x + o]; sh[2][threadIdx.x] += sh[2][threadIdx.x + o];
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    double* o = partial + ((long long)f * gridDim.x + blockIdx.x) * 3;
+    o[0] = sh[0][0]; o[1] = sh[1][0]; o[2] = sh[2][0];
+  }
+}
+// mean / population std (np.mean, np.std of getStats, code/utils_rd.py:149-161), std floored at 1e-7
+__global__ void feature_stats_final_kernel(const double* __restrict__ partial, int chunks, int F, float* __restrict__ mean,
+                                           float* __restrict__ stdv) {
+  const int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= F) return;
+  double c = 0.0, s = 0.0, q = 0.0;
+  for (int k = 0; k < chunks; ++k) { const double* p = partial + ((long long)f * chunks + k) * 3; c += p[0]; s += p[1]; q += p[2]; }
+  const double m = c > 0.0 ? s / c : 0.0;            // np.mean of an empty selection is nan in the reference; 0 keeps the pipeline finite
+  double var = c > 0.0 ? q / c - m * m : 0.0;
+  if (var < 0.0) var = 0.0;
+  double sd = sqrt(var);
+  if (sd < 1e-7) sd = 1e-7;
+  mean[f] = (float)m;
+  stdv[f] = (float)sd;
+}
+// out[t, i, f] = raw[i, t, f] > 0 ? (raw - mean_f) / (std_f + 1e-18) : 0;  out[t, i, F + f] = raw[i, t, f] > 0
+// (mask_normalize + the permute(1, 0, 2) of code/Raindrop.py:233); times_out[t, i] = minutes[i, t] / 60
+__global__ void mask_normalize_kernel(const float* __restrict__ raw, const float* __restrict__ mean, const float* __restrict__ stdv,
+                                      long long n, int T, int F, float* __restrict__ out, const float* __restrict__ minutes,
+                                      float* __restrict__ times_out) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = n * T * F;
+  if (o < total) {
+    const int f = (int)(o % F);
+    const long long it = o / F;
+    const int t = (int)(it % T);
+    const long long i = it / T;
+    const float v = __ldg(raw + o);
+    const bool obs = v > 0.f;
+    // the reference divides in float64 and casts once: do the same so the values agree to the last fp32 bit or two
+    const double z = ((double)v - (double)__ldg(mean + f)) / ((double)__ldg(stdv + f) + 1e-18);
+    float* dst = out + ((long long)t * n + i) * (2 * F);
+    dst[f] = obs ? (float)z : 0.f;
+    dst[F + f] = obs ? 1.f : 0.f;
+  }
+  if (minutes && o < n * T) {
+    const int t = (int)(o % T);
+    const long long i = o / T;
+    times_out[(long long)t * n + i] = __ldg(minutes + o) / 60.0f;
+  }
+}
+// zero the VALUE columns idx[k] (k < K) of P[t, j, :] (width = 2F; mask columns untouched): the leave-sensors-out
+// settings of code/Raindrop.py:214-231.  per_sample != 0: idx is [B, K] (setting 'sample'), else [K] ('set')
+__global__ void zero_features_kernel(float* __restrict__ P, long long T, int B, int width, const int64_t* __restrict__ idx,
+                                     int K, int per_sample) {
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= T * B * K) return;
+  const int k = (int)(o % K);
+  const long long tj = o / K;
+  const int j = (int)(tj % B);
+  const long long f = idx[per_sample ? (long long)j * K + k : k];
+  if (f >= 0 && f < width / 2) P[tj * width + f] = 0.f;
+}
+// One launch assembles a training batch out of device-resident tensors (code/Raindrop.py:311-317 does this on the
+// host and copies 2 MB over PCIe): CTA j copies sample idx[j]'s [T, width] rows, its times, statics and label and
+// counts lengths[j] = #(times > 0).
+__global__ void __launch_bounds__(256) assemble_batch_kernel(const float* __restrict__ P, const float* __restrict__ Pt,
+                                                            const float* __restrict__ Ps, const int64_t* __restrict__ y,
+                                                            const int64_t* __restrict__ idx, int T, long long n_total, int width,
+                                                            int ds, int B, float* __restrict__ src, float* __restrict__ times,
+                                                            float* __restrict__ statics, int64_t* __restrict__ y_out,
+                                                            int64_t* __restrict__ lengths) {
+  __shared__ int cnt[8];
+  const int j = blockIdx.x;
+  const long long sidx = idx[j];
+  if (sidx < 0 || sidx >= n_total) return;
+  const int wq = width >> 2;                                   // width % 4 == 0 checked by the wrapper
+  for (int o = threadIdx.x; o < T * wq; o += 256) {
+    const int t = o / wq, c = o - t * wq;
+    reinterpret_cast<float4*>(src + ((long long)t * B + j) * width)[c] =
+        __ldg(reinterpret_cast<const float4*>(P + ((long long)t * n_total + sidx) * width) + c);
+  }
+  int local = 0;
+  for (int t = threadIdx.x; t < T; t += 256) {
+    const float tv = __ldg(Pt + (long long)t * n_total + sidx);
+    times[(long long)t * B + j] = tv;
+    local += tv > 0.f ? 1 : 0;
+  }
+  for (int o = 16; o > 0; o >>= 1) local += __shfl_xor_sync(0xffffffffu, local, o);
+  if ((threadIdx.x & 31) == 0) cnt[threadIdx.x >> 5] = local;
+  if (Ps) for (int k = threadIdx.x; k < ds; k += 256) statics[(long long)j * ds + k] = __ldg(Ps + sidx * ds + k);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int tot = 0;
+    for (int w = 0; w < 8; ++w) tot += cnt[w];
+    lengths[j] = tot;
+    if (y) y_out[j] = y[sidx];
+  }
+}
+
 __global__ void rng_capture_kernel(uint64_t* state, uint64_t* cap, int advance) {
   cap[0] = state[0];
   cap[1] = state[1];
@@ -476,6 +594,49 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
 }  // namespace
 
 // ---- wrappers ----------------------------------------------------------------------------------
+int64_t feature_stats_scratch_bytes(int64_t n, int T, int F) {
+  int64_t chunks = ceil_div(n * T, 4096);
+  if (chunks > 512) chunks = 512;
+  if (chunks < 1) chunks = 1;
+  return chunks * F * 3 * (int64_t)sizeof(double);
+}
+int feature_stats(const float* raw, int64_t n, int T, int F, float* mean, float* stdv, void* scratch, cudaStream_t st) {
+  int64_t chunks = ceil_div(n * T, 4096);
+  if (chunks > 512) chunks = 512;
+  if (chunks < 1) chunks = 1;
+  if (F > 65535) { set_error("feature_stats: too many features"); return -2; }
+  feature_stats_partial_kernel<<<dim3((unsigned)chunks, (unsigned)F), FS_THREADS, 0, st>>>(raw, n * T, F, (double*)scratch);
+  RD_CHECK_LAUNCH("feature_stats_partial_kernel");
+  feature_stats_final_kernel<<<blocks_for(F), TPB, 0, st>>>((const double*)scratch, (int)chunks, F, mean, stdv);
+  RD_CHECK_LAUNCH("feature_stats_final_kernel");
+  return 0;
+}
+int mask_normalize(const float* raw, const float* mean, const float* stdv, int64_t n, int T, int F, float* out,
+                   const float* minutes, float* times_out, cudaStream_t st) {
+  if (n * T * F <= 0) return 0;
+  mask_normalize_kernel<<<blocks_for(n * T * F), TPB, 0, st>>>(raw, mean, stdv, n, T, F, out, minutes, times_out);
+  RD_CHECK_LAUNCH("mask_normalize_kernel");
+  return 0;
+}
+int zero_features(float* P, int64_t T, int B, int width, const int64_t* idx, int K, int per_sample, cudaStream_t st) {
+  if (T * B * K <= 0) return 0;
+  zero_features_kernel<<<blocks_for(T * B * K), TPB, 0, st>>>(P, T, B, width, idx, K, per_sample);
+  RD_CHECK_LAUNCH("zero_features_kernel");
+  return 0;
+}
+int assemble_batch(const float* P, const float* Pt, const float* Ps, const int64_t* y, const int64_t* idx, int T, int64_t n_total,
+                   int width, int ds, int B, float* src, float* times, float* statics, int64_t* y_out, int64_t* lengths,
+                   cudaStream_t st) {
+  if ((width & 3) || ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(src)) & 15)) {
+    set_error("assemble_batch: width %% 4 == 0 and 16-byte aligned tensors required");
+    return -2;
+  }
+  if (B <= 0) return 0;
+  assemble_batch_kernel<<<B, 256, 0, st>>>(P, Pt, Ps, y, idx, T, n_total, width, ds, B, src, times, statics, y_out, lengths);
+  RD_CHECK_LAUNCH("assemble_batch_kernel");
+  return 0;
+}
+
 int rng_capture(uint64_t* state, uint64_t* cap, int advance, cudaStream_t st) {
   rng_capture_kernel<<<1, 1, 0, st>>>(state, cap, advance);
   RD_CHECK_LAUNCH("rng_capture_kernel");

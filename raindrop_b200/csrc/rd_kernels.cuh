@@ -10,6 +10,16 @@ int gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_tota
 
 int rng_capture(uint64_t* rng_state, uint64_t* captured, int advance, cudaStream_t st);
 
+// device-side input pipeline (rd_kernels.cu; mirrors code/utils_rd.py:149-175,221-257 and code/Raindrop.py:214-231,311-317)
+int64_t feature_stats_scratch_bytes(int64_t n, int T, int F);
+int feature_stats(const float* raw, int64_t n, int T, int F, float* mean, float* stdv, void* scratch, cudaStream_t st);
+int mask_normalize(const float* raw, const float* mean, const float* stdv, int64_t n, int T, int F, float* out,
+                   const float* minutes, float* times_out, cudaStream_t st);
+int zero_features(float* P, int64_t T, int B, int width, const int64_t* idx, int K, int per_sample, cudaStream_t st);
+int assemble_batch(const float* P, const float* Pt, const float* Ps, const int64_t* y, const int64_t* idx, int T, int64_t n_total,
+                   int width, int ds, int B, float* src, float* times, float* statics, int64_t* y_out, int64_t* lengths,
+                   cudaStream_t st);
+
 // X0[(b*N+n), t*d_ob+k] = dropout(relu(src[t,b,n] * R_u[n*d_ob+k]))    code/models_rd.py:285-296,323-327
 // round != 0: values are rounded (RN) to TF32 so the tensor-core layer reads them exactly.
 // The same launch writes the positional encoding of `times` into pe_out[tok*ld + col0 ..+16] (src == nullptr

@@ -700,6 +700,43 @@ int rd_gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_t
   return gather_batch(src, idx, T, n_total, width, B, out, (cudaStream_t)stream);
 }
 
+int rd_assemble_batch(const float* P, const float* Ptime, const float* Pstatic, const int64_t* y, const int64_t* idx,
+                      int32_t T, int64_t n_total, int32_t width, int32_t d_static, int32_t B, float* src, float* times,
+                      float* statics, int64_t* y_out, int64_t* lengths, void* stream) {
+  if (!P || !Ptime || !idx || !src || !times || !lengths || T < 1 || n_total < 1 || width < 1 || B < 0 || (Pstatic && (!statics || d_static < 1)) ||
+      (y && !y_out)) {
+    set_error("rd_assemble_batch: bad arguments");
+    return -2;
+  }
+  return assemble_batch(P, Ptime, Pstatic, y, idx, T, n_total, width, d_static, B, src, times, statics, y_out, lengths,
+                        (cudaStream_t)stream);
+}
+
+size_t rd_feature_stats_scratch_bytes(int64_t n, int32_t T, int32_t F) {
+  if (n < 1 || T < 1 || F < 1) return 0;
+  return (size_t)feature_stats_scratch_bytes(n, T, F);
+}
+
+int rd_feature_stats(const float* raw, int64_t n, int32_t T, int32_t F, float* mean, float* stdv, void* scratch, void* stream) {
+  if (!raw || !mean || !stdv || !scratch || n < 1 || T < 1 || F < 1) { set_error("rd_feature_stats: bad arguments"); return -2; }
+  return feature_stats(raw, n, T, F, mean, stdv, scratch, (cudaStream_t)stream);
+}
+
+int rd_mask_normalize(const float* raw, const float* mean, const float* stdv, int64_t n, int32_t T, int32_t F, float* out,
+                      const float* minutes, float* times_out, void* stream) {
+  if (!raw || !mean || !stdv || !out || n < 1 || T < 1 || F < 1 || (minutes && !times_out)) {
+    set_error("rd_mask_normalize: bad arguments");
+    return -2;
+  }
+  return mask_normalize(raw, mean, stdv, n, T, F, out, minutes, times_out, (cudaStream_t)stream);
+}
+
+int rd_zero_features(float* P, int64_t T, int32_t B, int32_t width, const int64_t* idx, int32_t K, int32_t per_sample,
+                     void* stream) {
+  if (!P || !idx || T < 0 || B < 0 || width < 2 || K < 0) { set_error("rd_zero_features: bad arguments"); return -2; }
+  return zero_features(P, T, B, width, idx, K, per_sample, (cudaStream_t)stream);
+}
+
 int rd_cross_entropy_fwd_bwd(const float* logits, const int64_t* y, int32_t B, int32_t ncls, float* loss,
                              float* d_logits, void* stream) {
   if (!logits || !y || !loss || B < 1 || ncls < 1) { set_error("rd_cross_entropy_fwd_bwd: bad arguments"); return -2; }

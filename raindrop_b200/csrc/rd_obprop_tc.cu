@@ -166,15 +166,7 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-#pragma unroll
-        for (int v = 0; v < A_STAGE_BYTES / 16 / 128; ++v) {
-          const uint32_t o = (uint32_t)(lt + 128 * v) * 16u;
-          float4 x;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(sa + o));
-          x.x -= __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); x.y -= __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
-          x.z -= __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); x.w -= __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + A_STAGE_BYTES + o), "f"(x.x), "f"(x.y), "f"(x.z), "f"(x.w) : "memory");
-        }
+        lo_image<8>(sa, sa + A_STAGE_BYTES, A_STAGE_BYTES / 16, (uint32_t)lt, 128u);
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready_bar(stage));
@@ -270,10 +262,12 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 }
 
-void plan_n(int C, int* BN, int* n_tiles) {
-  if (C <= 256) { *n_tiles = 1; *BN = (int)round_up(C, 16); return; }
-  int best_bn = 256, best_nt = (int)ceil_div(C, 256), best_pad = best_nt * 256;
-  for (int bn = 256; bn >= 128; bn -= 32) {   // multi-tile: BN % 32 == 0 so no epilogue chunk straddles tiles
+// max_bn: widest n-tile (256 for the single-pass kernel; the error-compensated kernel carries two images of both
+// operands per stage and takes 128 so that >= 2 stages still fit)
+void plan_n(int C, int max_bn, int* BN, int* n_tiles) {
+  if (C <= max_bn) { *n_tiles = 1; *BN = (int)round_up(C, 16); return; }
+  int best_bn = max_bn, best_nt = (int)ceil_div(C, max_bn), best_pad = best_nt * max_bn;
+  for (int bn = max_bn; bn >= max_bn / 2; bn -= 32) {   // multi-tile: BN % 32 == 0 so no epilogue chunk straddles tiles
     int nt = (int)ceil_div(C, bn);
     if (nt * bn < best_pad) { best_pad = nt * bn; best_bn = bn; best_nt = nt; }
   }
@@ -328,7 +322,7 @@ int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st) {
   if (exact && (reinterpret_cast<uintptr_t>(a.W_lo) & 15)) { set_error("obprop_tc_fwd: W_lo must be 16-byte aligned"); return -2; }
   TcParams p;
   p.M = (int)rows; p.C = C;
-  plan_n(C, &p.BN, &p.n_tiles);
+  plan_n(C, exact ? 128 : 256, &p.BN, &p.n_tiles);     // exact: 3x the MMAs per tile -> narrower tiles, more CTAs
   p.m_tiles = (int)ceil_div(rows, BM);
   p.k_blocks = (int)ceil_div(C, BK);
   const int stage_bytes = exact ? 2 * A_STAGE_BYTES + 2 * p.BN * 128 : A_STAGE_BYTES + p.BN * 128;

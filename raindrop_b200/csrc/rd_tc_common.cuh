@@ -118,6 +118,33 @@ __device__ __forceinline__ uint32_t umma_idesc_tf32(int M, int N, bool a_mn, boo
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// Remainder images for the error-compensated ("3xTF32") products: dst[i] = x - trunc19(x) for `nvec` 16-byte vectors
+// starting at shared address `src`, vector index = tid + k * nthreads.  All loads of a batch of NB vectors are issued
+// before the first store, so a thread has NB shared-memory round trips in flight instead of one.
+template <int NB>
+__device__ __forceinline__ void lo_image(uint32_t src, uint32_t dst, uint32_t nvec, uint32_t tid, uint32_t nthreads) {
+  for (uint32_t v0 = tid; v0 < nvec; v0 += NB * nthreads) {
+    float4 x[NB];
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t v = v0 + k * nthreads;
+      if (v < nvec)
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x[k].x), "=f"(x[k].y), "=f"(x[k].z), "=f"(x[k].w) : "r"(src + v * 16u));
+    }
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const uint32_t v = v0 + k * nthreads;
+      if (v < nvec) {
+        const float a = x[k].x - __uint_as_float(__float_as_uint(x[k].x) & 0xFFFFE000u);
+        const float b = x[k].y - __uint_as_float(__float_as_uint(x[k].y) & 0xFFFFE000u);
+        const float c = x[k].z - __uint_as_float(__float_as_uint(x[k].z) & 0xFFFFE000u);
+        const float d = x[k].w - __uint_as_float(__float_as_uint(x[k].w) & 0xFFFFE000u);
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst + v * 16u), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+      }
+    }
+  }
+}
+
 // ---- host side -----------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,

@@ -294,7 +294,6 @@ struct WGroup { CUtensorMap tmA[WG_MAX]; CUtensorMap tmB[WG_MAX]; WP it[WG_MAX];
 constexpr int W_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 remainder pass + epilogue
 constexpr int MN_BOX = 32 * 32 * 4;  // one {32 col, 32 row} fp32 box = 4096 bytes
 
-__device__ __forceinline__ float lo_part(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 __global__ void __launch_bounds__(W_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ WGroup g) {
@@ -400,14 +399,8 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
           asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 2u * A_TILE + off), "f"(r < r_end ? 1.f : 0.f) : "memory");
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
-        for (uint32_t v = lt; v < a_vec + b_vec; v += 128) {
-          const uint32_t src = v < a_vec ? sa + v * 16u : sa + 2u * A_TILE + (v - a_vec) * 16u;
-          const uint32_t dst = src + (v < a_vec ? (uint32_t)A_TILE : b_tile);
-          float4 x;
-          asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x.x), "=f"(x.y), "=f"(x.z), "=f"(x.w) : "r"(src));
-          asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "f"(lo_part(x.x)), "f"(lo_part(x.y)),
-                       "f"(lo_part(x.z)), "f"(lo_part(x.w)) : "memory");
-        }
+        lo_image<6>(sa, sa + A_TILE, a_vec, (uint32_t)lt, 128u);                              // dY tile
+        lo_image<6>(sa + 2u * A_TILE, sa + 2u * A_TILE + b_tile, b_vec, (uint32_t)lt, 128u);  // X tile
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready_bar(stage));

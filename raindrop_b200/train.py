@@ -16,6 +16,7 @@ import torch.distributed as dist
 
 from . import functional as RF
 from . import lib as L
+from .data import DeviceDataset  # noqa: F401  (re-exported: the batch assembler lives with the input pipeline)
 
 
 def allreduce_gradients(model, group=None):
@@ -43,35 +44,6 @@ def allreduce_gradients(model, group=None):
     for g in grads:
         g.copy_(buf[off:off + g.numel()].view_as(g))
         off += g.numel()
-
-
-class DeviceDataset:
-    """The training tensors of code/Raindrop.py:233-239 kept resident in HBM; a batch is assembled by
-    `rd_gather_batch` straight into a TrainStep's static buffers, so a step moves B indices (1 KB) over PCIe
-    instead of the 2 MB batch (`Ptrain_tensor[:, idx, :].cuda()`, code/Raindrop.py:311-315)."""
-
-    def __init__(self, P, Pstatic, Ptime, y, device):
-        self.P = P.to(device=device, dtype=torch.float32).contiguous()                 # [T, n, 2F]
-        self.Ptime = Ptime.to(device=device, dtype=torch.float32).contiguous()         # [T, n]
-        self.Pstatic = None if Pstatic is None else Pstatic.to(device=device, dtype=torch.float32).contiguous()
-        self.y = y.to(device=device, dtype=torch.int64).reshape(-1).contiguous()
-        self.n = self.P.shape[1]
-        self.lib = L.load()
-
-    def _gather(self, src, T, width, idx, out):
-        L.check(self.lib.rd_gather_batch(src.data_ptr(), idx.data_ptr(), T, self.n, width, idx.numel(), out.data_ptr(),
-                                         L.stream_ptr()), "rd_gather_batch")
-
-    def fill(self, step, idx):
-        """idx: int64 [B] (host or device) -> fills step.src/times/static/lengths/y on the device."""
-        idx = idx.to(device=self.P.device, dtype=torch.int64, non_blocking=True).contiguous()
-        T = self.P.shape[0]
-        self._gather(self.P, T, self.P.shape[2], idx, step.src)
-        self._gather(self.Ptime, T, 1, idx, step.times)
-        if self.Pstatic is not None and step.static is not None:
-            self._gather(self.Pstatic, 1, self.Pstatic.shape[1], idx, step.static)
-        step.y.copy_(self.y.index_select(0, idx))
-        step.lengths.copy_(torch.sum(step.times > 0, dim=0))              # code/Raindrop.py:317
 
 
 def shard_slice(n, rank, world):

@@ -81,7 +81,7 @@ def test_golden_fixture(golden_dir, name, mode):
     assert float(distance) == float(z["distance"]) == 0.0
     full = meta["full_tensors"]
     D4 = cfg["d_inp"] * cfg["d_ob"]
-    check_against_golden(z, full, "obs", enc_in[:, :, :D4], 1e-5 if mode == EXACT else FWD_TOL, errs)
+    check_against_golden(z, full, "obs", enc_in[:, :, :D4], 1e-4 if mode == EXACT else FWD_TOL, errs)   # exact: K <= 2400 products, dropped lo.lo terms
     check_against_golden(z, full, "pe", enc_in[:, :, D4:], 1e-5, errs)
     # the encoder output at padded positions is never used by the reference (masked mean) -> compare valid rows
     lengths = batch["lengths"]
@@ -126,7 +126,7 @@ def test_against_oracle(cfg_name, B, opts):
     ref_grads = {k: go[k].grad.clone() for k in used_param_keys(cfg)}
     # ---- error-compensated mode: fp32-level agreement with the fp32 oracle, every tensor -------------
     model, logits, _, loss, enc_in, enc_out = _run_dropin(cfg, batch, 21, mode=EXACT)
-    assert normwise(enc_in[:, :, :D4], stages["obs"]) < 1e-5
+    assert normwise(enc_in[:, :, :D4], stages["obs"]) < 1e-4
     assert normwise(enc_in[:, :, D4:], stages["pe"]) < 1e-5
     assert normwise(logits, ref_logits) < 1e-4
     gp = dict(model.named_parameters())
@@ -265,12 +265,20 @@ def test_whole_validation_set_batch():
     model = build_dropin(cfg, 4).eval()
     batch = make_batch(cfg, 3880, seed=9)
     d = to_dev(batch)
-    with torch.no_grad():
-        big, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
-        part, _, _ = model.forward(d["src"][:, 1000:1100], d["static"][1000:1100], d["times"][:, 1000:1100],
-                                   d["lengths"][1000:1100])
+
+    def both():
+        with torch.no_grad():
+            big, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+            part, _, _ = model.forward(d["src"][:, 1000:1100], d["static"][1000:1100], d["times"][:, 1000:1100],
+                                       d["lengths"][1000:1100])
+        return big, part
+    model._plan.obprop_mode = FAST           # same arithmetic at every batch size: results are batch-invariant
+    big, part = both()
     assert big.shape == (3880, 2) and torch.isfinite(big).all()
     assert normwise(part, big[1000:1100]) < 1e-5
+    model._plan.obprop_mode = 0              # auto: B = 3880 streams in single-pass TF32, B = 100 runs error-compensated
+    big, part = both()
+    assert normwise(part, big[1000:1100]) < 2e-4
 
 
 # ---- operator level -----------------------------------------------------------------------------
