@@ -445,6 +445,50 @@ def main():
     e2e = summarize(e2e_times, world, device)
     e2e_value = world * BATCH / (e2e["median"] * 1e-3)
 
+    # ---- leg 3: device-resident training set (raindrop_b200.data): no batch bytes over PCIe ---------------
+    # the whole (synthetic) training split lives in HBM; per step ONE kernel assembles the batch from the epoch's
+    # index matrix (uploaded once per epoch, code/Raindrop.py:292-309) straight into the TrainStep buffers
+    from raindrop_b200.data import DeviceDataset, EpochSampler
+    n_train = 16 * BATCH
+    pool = make_batch(cfg, n_train, seed=777 + rank, **opts)
+    dds = DeviceDataset(pool["src"], pool["static"], pool["times"], pool["y"], device=device)
+    import numpy as _np
+    _np.random.seed(1234 + rank)
+    sampler = EpochSampler(pool["y"].numpy(), batch_size=BATCH, strategy=2 if cfg["n_classes"] == 2 else 3, device=device)
+    epoch_idx = sampler.epoch()
+    dd_state = {"i": 0}
+
+    def dd_step():
+        dds.fill(ts, epoch_idx[dd_state["i"] % epoch_idx.shape[0]])
+        dd_state["i"] += 1
+        ts.step()
+
+    for _ in range(args.warmup):
+        dd_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    dd = summarize(timed_steps(dd_step, args.steps, flush), world, device)
+    dd_value = world * BATCH / (dd["median"] * 1e-3)
+
+    # ---- leg 4: whole-validation-set evaluation (evaluate_standard, code/utils_rd.py:310-320), sharded ----------
+    from raindrop_b200.train import evaluate_sharded
+    n_val = {"P19": 3880, "P12": 1199, "PAM": 533}.get(cfg_name, 4 * BATCH)
+    val = make_batch(cfg, n_val, seed=4242, **opts)
+    val_dev = {k: (v.to(device) if v is not None else None) for k, v in val.items()}
+    model2.eval()
+
+    def eval_step():
+        evaluate_sharded(model2, val_dev["src"], val_dev["static"], val_dev["times"])
+
+    for _ in range(3):
+        eval_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ev = summarize(timed_steps(eval_step, 10, flush), world, device)
+    model2.train()
+
     if rank != 0:
         _finish(world)
         return
@@ -470,6 +514,14 @@ def main():
                 "ms_max": round(e2e["max"], 4), "per_rank_median_ms": e2e["per_rank_median"],
                 "path": "pinned host batch -> H2D (copy stream, one batch ahead) -> models_rd.Raindrop_v2.forward -> "
                         "CrossEntropyLoss -> backward -> raindrop_b200.optim.FlatAdam.step -> loss.item()"},
+        "device_dataset": {"value": round(dd_value, 1), "unit": "samples/s", "ms_per_step": round(dd["median"], 4),
+                           "note": "training split resident in HBM (%d samples per rank), batch assembled on the device by "
+                                   "rd_assemble_batch from the epoch's balanced index matrix (1 launch) + TrainStep graph replay; "
+                                   "0 batch bytes over PCIe per step" % n_train},
+        "eval": {"value": round(n_val / (ev["median"] * 1e-3), 1), "unit": "samples/s", "batch": n_val,
+                 "ms_per_pass": round(ev["median"], 4),
+                 "note": "evaluate_sharded: the whole validation set as one batch per pass (code/utils_rd.py:310-320), "
+                         "samples sharded over %d rank(s), logits all-gathered; eval mode, no_grad" % world},
         "gpu_launches": launches_per_step * args.steps,
         "gpu_launches_per_step": launches_per_step,
         "final_loss": {"graph": round(loss_graph, 5), "e2e": round(state["loss"], 5)},

@@ -153,6 +153,20 @@ int rd_obprop_beta_fwd(const float* x, const float* p_t, const int64_t* edge_src
                        const float* value_w, const float* value_b, float* out, int64_t* edge_src_out,
                        int64_t* edge_tgt_out, float* alpha_out, void* scratch, void* stream);
 
+/* Backward of rd_obprop_beta_fwd (same inputs; the forward is recomputed; the top-K edge selection is piecewise
+ * constant and carries no gradient).  d_out [N, C]; d_alpha [K] or NULL = gradient w.r.t. the returned alpha (mean
+ * gamma of the kept edges, which becomes layer 2's edge weights in code/models_rd.py:332-336).  Writes d_x [N, C]
+ * (may be NULL), d_edge_w [E], d_p_t [T, 16] (may be NULL), d_increase_dim_{w [8C, C], b [8C]}, d_map_weights [N, 16],
+ * d_value_{w [C, C], b [C]} -- the tensors autograd reaches through code/Ob_propagation.py:161-211.
+ * scratch: rd_obprop_beta_bwd_scratch_bytes(N, T, d_ob, E) bytes. */
+size_t rd_obprop_beta_bwd_scratch_bytes(int32_t N, int32_t T, int32_t d_ob, int32_t E);
+int rd_obprop_beta_bwd(const float* x, const float* p_t, const int64_t* edge_src, const int64_t* edge_tgt,
+                       const float* edge_w, int32_t E, int32_t N, int32_t T, int32_t d_ob,
+                       const float* increase_dim_w, const float* increase_dim_b, const float* map_weights,
+                       const float* value_w, const float* value_b, const float* d_out, const float* d_alpha,
+                       float* d_x, float* d_edge_w, float* d_p_t, float* d_increase_dim_w, float* d_increase_dim_b,
+                       float* d_map_weights, float* d_value_w, float* d_value_b, void* scratch, void* stream);
+
 /* ---- whole Raindrop_v2 forward / backward ---------------------------------------------------
  * Replaces Raindrop_v2.forward (code/models_rd.py:278-387) for the live configuration
  * (sensor_wise_mask=False, aggreg='mean', use_beta=False) and its autograd backward
@@ -233,18 +247,30 @@ typedef struct rd_wgrad_item {
 size_t rd_linear_wgrad_partial_bytes(int64_t rows, int32_t out_features, int32_t in_features);
 int rd_linear_wgrad_group(const rd_wgrad_item* items, int32_t n, void* stream);
 
-/* TransformerConv.forward (code/transformer_conv.py:139-207), concat=True, root_weight=True,
- * beta=False, no edge features.  x [n_nodes, in]; weights [H*F, in]; edge_w may be NULL (then the
- * logits are q_i.k_j/sqrt(F)).  out [n_nodes, H*F]; alpha [E, H] (post-softmax, as returned).
- * scratch: rd_transformer_conv_scratch_bytes(...) */
-size_t rd_transformer_conv_scratch_bytes(int32_t n_nodes, int32_t in_ch, int32_t heads, int32_t out_ch,
-                                         int32_t E);
-int rd_transformer_conv_fwd(const float* x, int32_t n_nodes, int32_t in_ch, int32_t heads,
-                            int32_t out_ch, const int64_t* edge_src, const int64_t* edge_tgt,
-                            const float* edge_w, int32_t E, const float* wq, const float* bq,
-                            const float* wk, const float* bk, const float* wv, const float* bv,
-                            const float* ws, const float* bs, float* out, float* alpha,
+/* TransformerConv.forward (code/transformer_conv.py:139-207), concat=True, root_weight=True, beta=False, no edge
+ * features -- and its backward.  Batched over `n_graphs` independent graphs that share ONE edge list (legacy Raindrop v1
+ * applies the layer to every sample of a batch, code/models_rd.py:158-166): the row of node i of graph g in x / out is
+ * i * node_stride + g * graph_stride (single graph: n_graphs = 1, node_stride = 1, graph_stride = 0).
+ *   x [rows, in];  weights [H*F, in];  edge_w [E] or NULL (then the logits are q_i.k_j / sqrt(F));
+ *   out [rows, H*F];  alpha [n_graphs, E, H] (post-softmax, as returned by the reference).
+ * Backward: writes d_x (may be NULL), d_w* / d_b* (written, not accumulated; with edge_w the q/k projections take no
+ * part in the output, code/transformer_conv.py:199-200, so their gradients are zeros) and d_edge_w [E] (optional,
+ * only with edge_w).  scratch: rd_transformer_conv_scratch_bytes(..., backward) bytes. */
+size_t rd_transformer_conv_scratch_bytes(int32_t n_nodes, int32_t n_graphs, int32_t in_ch, int32_t heads,
+                                         int32_t out_ch, int32_t E, int32_t backward);
+int rd_transformer_conv_fwd(const float* x, int32_t n_nodes, int32_t n_graphs, int64_t node_stride,
+                            int64_t graph_stride, int32_t in_ch, int32_t heads, int32_t out_ch,
+                            const int64_t* edge_src, const int64_t* edge_tgt, const float* edge_w, int32_t E,
+                            const float* wq, const float* bq, const float* wk, const float* bk, const float* wv,
+                            const float* bv, const float* ws, const float* bs, float* out, float* alpha,
                             void* scratch, void* stream);
+int rd_transformer_conv_bwd(const float* x, int32_t n_nodes, int32_t n_graphs, int64_t node_stride,
+                            int64_t graph_stride, int32_t in_ch, int32_t heads, int32_t out_ch,
+                            const int64_t* edge_src, const int64_t* edge_tgt, const float* edge_w, int32_t E,
+                            const float* wq, const float* bq, const float* wk, const float* bk, const float* wv,
+                            const float* bv, const float* ws, const float* alpha, const float* d_out, float* d_x,
+                            float* d_wq, float* d_bq, float* d_wk, float* d_bk, float* d_wv, float* d_bv,
+                            float* d_ws, float* d_bs, float* d_edge_w, void* scratch, void* stream);
 
 /* ---- device-side batch assembly ---------------------------------------------------
  * out[t, j, :] = src[t, idx[j], :] for t < T, j < B: selects a batch out of a training set that stays

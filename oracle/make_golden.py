@@ -143,9 +143,68 @@ def operator_cases():
     print("operators          %d arrays" % len(out))
 
 
+def operator_grad_cases():
+    """Gradient fixtures of the two graph operators (reference autograd through code/Ob_propagation.py and
+    code/transformer_conv.py under the PyG shim): loss = sum(out * G) [+ sum(alpha * g) for use_beta=True, whose
+    returned alpha is differentiable and feeds layer 2 in code/models_rd.py:332-336].  Inputs / weights are the ones
+    of operators.npz; written to operators_grad.npz."""
+    ref = ref_harness.load_reference()
+    from raindrop_b200.synth import _stream
+    z = np.load(os.path.join(GOLDEN, "operators.npz"))
+    out = {}
+    ei = torch.from_numpy(z["obprop.edge_index"])
+    N, C = z["obprop.x"].shape
+    T, d_ob = z["obprop.p_t"].shape[0], 4
+    layer = ref.Observation_progation(in_channels=C, out_channels=C, heads=1, n_nodes=N, ob_dim=d_ob)
+    layer.load_state_dict({k[len("obprop.sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("obprop.sd.")})
+    G = torch.from_numpy(_stream(9, "opg.G", N * C)).float().view(N, C) - 0.5
+    out["obprop.G"] = G.numpy()
+    for ub in (False, True):
+        layer.zero_grad()
+        x = torch.from_numpy(z["obprop.x"]).clone().requires_grad_(True)
+        p_t = torch.from_numpy(z["obprop.p_t"]).clone().requires_grad_(True)
+        ew = torch.from_numpy(z["obprop.edge_w"]).clone().requires_grad_(True)
+        o, (ei2, al) = layer(x, p_t=p_t, edge_index=ei, edge_weights=ew, use_beta=ub, edge_attr=None, return_attention_weights=True)
+        loss = (o * G).sum()
+        tag = "obprop.beta%d." % int(ub)
+        if ub:
+            g = torch.from_numpy(_stream(9, "opg.g", al.numel())).float() - 0.5
+            out[tag + "g_alpha"] = g.numpy()
+            loss = loss + (al * g).sum()
+        loss.backward()
+        out[tag + "d_x"] = x.grad.numpy()
+        out[tag + "d_edge_w"] = (ew.grad if ew.grad is not None else torch.zeros_like(ew)).numpy()
+        if ub:
+            out[tag + "d_p_t"] = p_t.grad.numpy()
+        for k, prm in layer.named_parameters():
+            if prm.grad is not None:
+                out[tag + "grad." + k] = prm.grad.numpy()
+    xn0 = torch.from_numpy(z["tconv.x"])
+    for tag, heads, use_w in (("tconv.w.", 1, True), ("tconv.qk.", 2, False)):
+        conv = ref.TransformerConv(in_channels=7, out_channels=5, heads=heads)
+        conv.load_state_dict({k[len(tag + "sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + "sd.")})
+        xn = xn0.clone().requires_grad_(True)
+        ew = torch.from_numpy(z["obprop.edge_w"]).clone().requires_grad_(True)
+        G2 = torch.from_numpy(_stream(9, tag + "G", N * 5 * heads)).float().view(N, 5 * heads) - 0.5
+        o, _ = conv(xn, edge_index=ei, edge_weights=ew if use_w else None, edge_attr=None, return_attention_weights=True)
+        (o * G2).sum().backward()
+        out[tag + "G"] = G2.numpy()
+        out[tag + "d_x"] = xn.grad.numpy()
+        if use_w:
+            out[tag + "d_edge_w"] = ew.grad.numpy()
+        for k, prm in conv.named_parameters():
+            out[tag + "grad." + k] = (prm.grad if prm.grad is not None else torch.zeros_like(prm)).numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "operators_grad.npz"), **out)
+    print("operators_grad     %d arrays: %s" % (len(out), sorted(out)[:60]))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
+    if len(sys.argv) > 1 and sys.argv[1] == "operators_grad":      # add-on fixtures: leaves the existing files untouched
+        operator_grad_cases()
+        sys.exit(0)
     for case in CASES:
         run_case(*case)
     operator_cases()
+    operator_grad_cases()

@@ -107,6 +107,29 @@ __device__ __forceinline__ float4 mask4(const AttnTcP& p, uint64_t row_base, int
   return q;
 }
 
+// Attention-dropout keep bits of row r = threadIdx.x - 64 (warps 2, 3), computed while the tiles are still in flight:
+// the counter-based stream needs nothing but indices, and these warps have no accumulator rows to work on, so the
+// 16 Philox blocks per row leave the critical path of the softmax warps.  bit j of keep[r] = element (r, j) is kept.
+__device__ __forceinline__ void precompute_keep_bits(const AttnTcP& p, int b, int h, unsigned long long* keep) {
+  if (p.drop_p <= 0.f || threadIdx.x < 64) return;
+  const int r = threadIdx.x - 64;
+  const uint64_t row_base = ((uint64_t)(b * p.H + h) * p.T + r) * p.T;
+  unsigned long long bits = 0ull;
+  if (r < p.T) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      const float4 m = mask4(p, row_base, c, 1.f);
+      bits |= (unsigned long long)((m.x > 0.f ? 1u : 0u) | (m.y > 0.f ? 2u : 0u) | (m.z > 0.f ? 4u : 0u) | (m.w > 0.f ? 8u : 0u)) << (4 * c);
+    }
+  }
+  keep[r] = bits;
+}
+__device__ __forceinline__ float4 keep4(unsigned long long bits, int c, float ik, float drop_p) {
+  if (drop_p <= 0.f) return make_float4(1.f, 1.f, 1.f, 1.f);
+  const unsigned q = (unsigned)(bits >> (4 * c)) & 15u;
+  return make_float4(q & 1u ? ik : 0.f, q & 2u ? ik : 0.f, q & 4u ? ik : 0.f, q & 8u ? ik : 0.f);
+}
+
 // softmax of this thread's score row (already in registers, unscaled): s -> probabilities in place
 __device__ __forceinline__ void softmax_row(float (&s)[64], float scale, int nv, bool row_ok) {
   float mx = -INFINITY;
@@ -142,6 +165,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   const uint32_t bar = base + 4u * TILE;
   const uint32_t bar_qk = bar, bar_v = bar + 8, bar_s = bar + 16, bar_o = bar + 24, tmem_slot = bar + 32;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  unsigned long long* keep = reinterpret_cast<unsigned long long*>(smem_raw + (bar + 64 - smem_u32(smem_raw)));   // [64]
 
   if (warp == 0) {
     if (lane == 0) {
@@ -168,6 +192,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
       tma_load_5d(&tmQKV, bar_qk, KP + g * GRP, 32 * g, h, 1, b, 0);
     }
   }
+  precompute_keep_bits(p, b, h, keep);
   mbar_wait(bar_qk, 0);
   lo_pass(QV, TILE, TILE);
   lo_pass(KP, TILE, TILE);
@@ -193,10 +218,10 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
     load_row64(tS + ((uint32_t)(warp * 32) << 16), s);
     softmax_row(s, p.scale, nv, i < p.T);
     const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const uint64_t row_base = ((uint64_t)(b * p.H + h) * p.T + i) * p.T;
+    const unsigned long long bits = p.drop_p > 0.f ? keep[i] : 0ull;
 #pragma unroll
     for (int c = 0; c < 16; ++c) {
-      const float4 m = mask4(p, row_base, c, ik);
+      const float4 m = keep4(bits, c, ik, p.drop_p);
       store_chunk_hi_lo(KP, i, c, s[4 * c] * m.x, s[4 * c + 1] * m.y, s[4 * c + 2] * m.z, s[4 * c + 3] * m.w);
     }
     fence_async_smem();
@@ -258,6 +283,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   const uint32_t bar_qk = bar, bar_gv = bar + 8, bar_s = bar + 16, bar_dp = bar + 24, bar_m1 = bar + 32, bar_2 = bar + 40,
                  bar_m2 = bar + 48, bar_out = bar + 56, tmem_slot = bar + 64;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  unsigned long long* keep = reinterpret_cast<unsigned long long*>(smem_raw + (bar + 128 - smem_u32(smem_raw)));  // [64]
 
   if (warp == 0) {
     if (lane == 0) {
@@ -293,6 +319,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
       tma_load_4d(&tmDO, bar_gv, R3 + g * GRP, 32 * g, h, b, 0);
     }
   }
+  precompute_keep_bits(p, b, h, keep);
   mbar_wait(bar_qk, 0);
   lo_pass(R0, TILE, TILE);
   lo_pass(R1, TILE, TILE);
@@ -340,10 +367,10 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
     load_row64(tDP + lane_addr, w);                  // w = d(Pd)
     float dot = 0.f;
     const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const uint64_t row_base = ((uint64_t)(b * p.H + h) * p.T + i) * p.T;
+    const unsigned long long bits = p.drop_p > 0.f ? keep[i] : 0ull;
 #pragma unroll
     for (int c = 0; c < 16; ++c) {      // w := dP = d(Pd) * mask; Pd = P * mask goes to shared memory (read column-wise later)
-      const float4 m = mask4(p, row_base, c, ik);
+      const float4 m = keep4(bits, c, ik, p.drop_p);
       w[4 * c] *= m.x; w[4 * c + 1] *= m.y; w[4 * c + 2] *= m.z; w[4 * c + 3] *= m.w;
       dot += w[4 * c] * pr[4 * c] + w[4 * c + 1] * pr[4 * c + 1] + w[4 * c + 2] * pr[4 * c + 2] + w[4 * c + 3] * pr[4 * c + 3];
       store_chunk_mn(Pd, Pd_lo, i, c, pr[4 * c] * m.x, pr[4 * c + 1] * m.y, pr[4 * c + 2] * m.z, pr[4 * c + 3] * m.w);
@@ -423,8 +450,8 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   }
 }
 
-constexpr int FWD_SMEM = 1024 + 4 * TILE + 64;
-constexpr int BWD_SMEM = 1024 + 8 * TILE + GRP + 128;
+constexpr int FWD_SMEM = 1024 + 4 * TILE + 64 + 512;
+constexpr int BWD_SMEM = 1024 + 8 * TILE + GRP + 128 + 512;
 
 // qkv viewed as [T, B, 3, H, hd]: box = 32 columns x 64 timestamps of one (sample, q/k/v, head)
 int encode_qkv(CUtensorMap* m, const float* qkv, int B, int H, int T, int hd, CUtensorMapSwizzle sw) {

@@ -366,26 +366,63 @@ class ObPropLayerFunction(torch.autograd.Function):
         return d_x, d_w, d_b, None, None
 
 
+class ObPropBetaFunction(torch.autograd.Function):
+    """Observation_progation.forward(use_beta=True) for one sample (code/Ob_propagation.py:161-211) with gradients:
+    rd_obprop_beta_fwd / rd_obprop_beta_bwd.  Returns (out [N, C], alpha [K], pruned edge list [2, K] (data))."""
+
+    @staticmethod
+    def forward(ctx, x, p_t, edge_weights, src_i, tgt_i, d_ob, inc_w, inc_b, map_w, val_w, val_b):
+        lib = L.load()
+        x, p_t, w = _as_f32(x), _as_f32(p_t), _as_f32(edge_weights)
+        N, Cc = x.shape
+        T = Cc // d_ob
+        E = src_i.numel()
+        K = E // 2
+        out = torch.empty(N, Cc, dtype=torch.float32, device=x.device)
+        ei = torch.empty(2, K, dtype=torch.int64, device=x.device)
+        alpha = torch.empty(K, dtype=torch.float32, device=x.device)
+        sc = torch.empty(lib.rd_obprop_beta_scratch_bytes(N, T, d_ob, E) // 4, dtype=torch.float32, device=x.device)
+        ps = [_as_f32(t) for t in (inc_w, inc_b, map_w, val_w, val_b)]
+        rc = lib.rd_obprop_beta_fwd(x.data_ptr(), p_t.data_ptr(), src_i.data_ptr(), tgt_i.data_ptr(), w.data_ptr(), E, N, T,
+                                    d_ob, *[p.data_ptr() for p in ps], out.data_ptr(), ei[0].data_ptr(), ei[1].data_ptr(),
+                                    alpha.data_ptr(), sc.data_ptr(), L.stream_ptr(x.device))
+        L.check(rc, "rd_obprop_beta_fwd")
+        ctx.save_for_backward(x, p_t, w, src_i, tgt_i, *ps)
+        ctx.d_ob = d_ob
+        ctx.mark_non_differentiable(ei)
+        return out, alpha, ei
+
+    @staticmethod
+    def backward(ctx, d_out, d_alpha, _d_ei):
+        lib = L.load()
+        x, p_t, w, src_i, tgt_i, inc_w, inc_b, map_w, val_w, val_b = ctx.saved_tensors
+        N, Cc = x.shape
+        d_ob = ctx.d_ob
+        T, E = Cc // d_ob, src_i.numel()
+        dev = x.device
+        d_out = _as_f32(d_out) if d_out is not None else torch.zeros(N, Cc, dtype=torch.float32, device=dev)
+        d_alpha = None if d_alpha is None else _as_f32(d_alpha)
+        f32 = dict(dtype=torch.float32, device=dev)
+        d_x = torch.empty(N, Cc, **f32)
+        d_w = torch.empty(E, **f32); d_pt = torch.empty(T, 16, **f32)
+        g_iw = torch.empty_like(inc_w); g_ib = torch.empty_like(inc_b); g_mw = torch.empty_like(map_w)
+        g_vw = torch.empty_like(val_w); g_vb = torch.empty_like(val_b)
+        sc = torch.empty(lib.rd_obprop_beta_bwd_scratch_bytes(N, T, d_ob, E) // 4, **f32)
+        rc = lib.rd_obprop_beta_bwd(x.data_ptr(), p_t.data_ptr(), src_i.data_ptr(), tgt_i.data_ptr(), w.data_ptr(), E, N, T, d_ob,
+                                    inc_w.data_ptr(), inc_b.data_ptr(), map_w.data_ptr(), val_w.data_ptr(), val_b.data_ptr(),
+                                    d_out.data_ptr(), L.ptr(d_alpha), d_x.data_ptr(), d_w.data_ptr(), d_pt.data_ptr(),
+                                    g_iw.data_ptr(), g_ib.data_ptr(), g_mw.data_ptr(), g_vw.data_ptr(), g_vb.data_ptr(),
+                                    sc.data_ptr(), L.stream_ptr(dev))
+        L.check(rc, "rd_obprop_beta_bwd")
+        return d_x, d_pt, d_w, None, None, None, g_iw, g_ib, g_mw, g_vw, g_vb
+
+
 def obprop_beta(x, p_t, edge_index, edge_weights, d_ob, inc_w, inc_b, map_w, val_w, val_b):
-    """Observation_progation.forward(use_beta=True) for one sample (rd_obprop_beta_fwd); inference only.
-    Returns (out [N, C], edge_index_pruned [2, K], alpha [K])."""
-    lib = L.load()
-    x, p_t = _as_f32(x), _as_f32(p_t)
-    N, Cc = x.shape
-    T = Cc // d_ob
+    """Observation_progation.forward(use_beta=True) for one sample.  Returns (out [N, C], edge_index_pruned [2, K],
+    alpha [K]); differentiable w.r.t. x, p_t, edge_weights and the five parameters."""
     src_i, tgt_i = edge_index[0].contiguous().long(), edge_index[1].contiguous().long()
-    E = src_i.numel()
-    K = E // 2
-    w = _as_f32(edge_weights)
-    out = torch.empty(N, Cc, dtype=torch.float32, device=x.device)
-    ei = torch.empty(2, K, dtype=torch.int64, device=x.device)
-    alpha = torch.empty(K, dtype=torch.float32, device=x.device)
-    sc = torch.empty(lib.rd_obprop_beta_scratch_bytes(N, T, d_ob, E) // 4, dtype=torch.float32, device=x.device)
-    ps = [_as_f32(t) for t in (inc_w, inc_b, map_w, val_w, val_b)]
-    rc = lib.rd_obprop_beta_fwd(x.data_ptr(), p_t.data_ptr(), src_i.data_ptr(), tgt_i.data_ptr(), w.data_ptr(), E, N, T,
-                                d_ob, *[p.data_ptr() for p in ps], out.data_ptr(), ei[0].data_ptr(), ei[1].data_ptr(),
-                                alpha.data_ptr(), sc.data_ptr(), L.stream_ptr())
-    L.check(rc, "rd_obprop_beta_fwd")
+
+    out, alpha, ei = ObPropBetaFunction.apply(x, p_t, edge_weights, src_i, tgt_i, d_ob, inc_w, inc_b, map_w, val_w, val_b)
     return out, ei, alpha
 
 
@@ -426,25 +463,70 @@ def linear(x, weight, bias=None, relu=False):
     return out
 
 
-def transformer_conv(x, edge_index, edge_weights, heads, out_channels, wq, bq, wk, bk, wv, bv, ws, bs):
-    """TransformerConv forward (inference; code/transformer_conv.py:139-207).  Returns (out, alpha)."""
-    lib = L.load()
-    x = _as_f32(x)
-    n, in_ch = x.shape
-    src_i = edge_index[0].contiguous().long()
-    tgt_i = edge_index[1].contiguous().long()
-    E = src_i.numel()
-    ew = None if edge_weights is None else _as_f32(edge_weights)
-    out = torch.empty(n, heads * out_channels, dtype=torch.float32, device=x.device)
-    alpha = torch.empty(E, heads, dtype=torch.float32, device=x.device)
-    sc = torch.empty(max(1, lib.rd_transformer_conv_scratch_bytes(n, in_ch, heads, out_channels, E) // 4),
-                     dtype=torch.float32, device=x.device)
-    ps = [_as_f32(t) for t in (wq, bq, wk, bk, wv, bv, ws, bs)]
-    rc = lib.rd_transformer_conv_fwd(x.data_ptr(), n, in_ch, heads, out_channels, src_i.data_ptr(), tgt_i.data_ptr(),
-                                     L.ptr(ew), E, *[p.data_ptr() for p in ps], out.data_ptr(), alpha.data_ptr(),
-                                     sc.data_ptr(), L.stream_ptr())
-    L.check(rc, "rd_transformer_conv_fwd")
-    return out, alpha
+class TransformerConvFunction(torch.autograd.Function):
+    """TransformerConv.forward (code/transformer_conv.py:139-207) with gradients: rd_transformer_conv_fwd / _bwd.
+    x [rows, in] holds `n_graphs` graphs of `n_nodes` nodes sharing one edge list; row(node i, graph g) =
+    i * node_stride + g * graph_stride.  Returns (out [rows, H*F], alpha [n_graphs, E, H])."""
+
+    @staticmethod
+    def forward(ctx, x, edge_index, edge_weights, geom, heads, out_channels, wq, bq, wk, bk, wv, bv, ws, bs):
+        lib = L.load()
+        n_nodes, n_graphs, node_stride, graph_stride = geom
+        x = _as_f32(x)
+        rows, in_ch = x.shape
+        src_i = edge_index[0].contiguous().long()
+        tgt_i = edge_index[1].contiguous().long()
+        E = src_i.numel()
+        ew = None if edge_weights is None else _as_f32(edge_weights)
+        out = torch.empty(rows, heads * out_channels, dtype=torch.float32, device=x.device)
+        alpha = torch.empty(n_graphs, E, heads, dtype=torch.float32, device=x.device)
+        sc = torch.empty(max(1, lib.rd_transformer_conv_scratch_bytes(n_nodes, n_graphs, in_ch, heads, out_channels, E, 0) // 4),
+                         dtype=torch.float32, device=x.device)
+        ps = [_as_f32(t) for t in (wq, bq, wk, bk, wv, bv, ws, bs)]
+        rc = lib.rd_transformer_conv_fwd(x.data_ptr(), n_nodes, n_graphs, node_stride, graph_stride, in_ch, heads, out_channels,
+                                         src_i.data_ptr(), tgt_i.data_ptr(), L.ptr(ew), E, *[p.data_ptr() for p in ps],
+                                         out.data_ptr(), alpha.data_ptr(), sc.data_ptr(), L.stream_ptr(x.device))
+        L.check(rc, "rd_transformer_conv_fwd")
+        ctx.save_for_backward(x, src_i, tgt_i, alpha, *ps)
+        ctx.ew = ew
+        ctx.geom, ctx.heads, ctx.out_channels = geom, heads, out_channels
+        ctx.mark_non_differentiable(alpha)       # the reference only ever uses the returned alpha as data (detached by cdist/mean)
+        return out, alpha
+
+    @staticmethod
+    def backward(ctx, d_out, _d_alpha):
+        lib = L.load()
+        x, src_i, tgt_i, alpha, wq, bq, wk, bk, wv, bv, ws, bs = ctx.saved_tensors
+        n_nodes, n_graphs, node_stride, graph_stride = ctx.geom
+        heads, F_ = ctx.heads, ctx.out_channels
+        rows, in_ch = x.shape
+        E = src_i.numel()
+        d_out = _as_f32(d_out)
+        dev = x.device
+        d_x = torch.empty_like(x) if ctx.needs_input_grad[0] else None
+        gw = [torch.empty(heads * F_, in_ch, dtype=torch.float32, device=dev) for _ in range(4)]
+        gb = [torch.empty(heads * F_, dtype=torch.float32, device=dev) for _ in range(4)]
+        d_ew = torch.zeros(E, dtype=torch.float32, device=dev) if (ctx.ew is not None and ctx.needs_input_grad[2]) else None
+        sc = torch.empty(max(1, lib.rd_transformer_conv_scratch_bytes(n_nodes, n_graphs, in_ch, heads, F_, E, 1) // 4),
+                         dtype=torch.float32, device=dev)
+        rc = lib.rd_transformer_conv_bwd(x.data_ptr(), n_nodes, n_graphs, node_stride, graph_stride, in_ch, heads, F_,
+                                         src_i.data_ptr(), tgt_i.data_ptr(), L.ptr(ctx.ew), E, wq.data_ptr(), bq.data_ptr(),
+                                         wk.data_ptr(), bk.data_ptr(), wv.data_ptr(), bv.data_ptr(), ws.data_ptr(),
+                                         alpha.data_ptr(), d_out.data_ptr(), L.ptr(d_x), gw[0].data_ptr(), gb[0].data_ptr(),
+                                         gw[1].data_ptr(), gb[1].data_ptr(), gw[2].data_ptr(), gb[2].data_ptr(), gw[3].data_ptr(),
+                                         gb[3].data_ptr(), L.ptr(d_ew), sc.data_ptr(), L.stream_ptr(dev))
+        L.check(rc, "rd_transformer_conv_bwd")
+        return (d_x, None, d_ew, None, None, None, gw[0], gb[0], gw[1], gb[1], gw[2], gb[2], gw[3], gb[3])
+
+
+def transformer_conv(x, edge_index, edge_weights, heads, out_channels, wq, bq, wk, bk, wv, bv, ws, bs, geom=None):
+    """TransformerConv forward with autograd (code/transformer_conv.py:139-207).  Returns (out, alpha); alpha is
+    [E, heads] for a single graph, [n_graphs, E, heads] when `geom` = (n_nodes, n_graphs, node_stride, graph_stride)."""
+    single = geom is None
+    if single:
+        geom = (x.shape[0], 1, 1, 0)
+    out, alpha = TransformerConvFunction.apply(x, edge_index, edge_weights, geom, heads, out_channels, wq, bq, wk, bk, wv, bv, ws, bs)
+    return out, (alpha[0] if single else alpha)
 
 
 def workspace_view(plan, which):

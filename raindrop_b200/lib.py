@@ -78,6 +78,9 @@ SIGNATURES = {
                                 C.c_void_p]),
     "rd_obprop_beta_scratch_bytes": (C.c_size_t, [C.c_int32] * 4),
     "rd_obprop_beta_fwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p] * 11),
+    "rd_obprop_beta_bwd_scratch_bytes": (C.c_size_t, [C.c_int32] * 4),
+    "rd_obprop_beta_bwd": (C.c_int, [C.c_void_p] * 5 + [C.c_int32] * 4 + [C.c_void_p] * 5 + [C.c_void_p] * 2 + [C.c_void_p] * 8 +
+                           [C.c_void_p, C.c_void_p]),
     "rd_workspace_bytes": (C.c_size_t, [C.POINTER(RdDims)]),
     "rd_backward_scratch_bytes": (C.c_size_t, [C.POINTER(RdDims)]),
     "rd_workspace_offset": (C.c_int64, [C.POINTER(RdDims), C.c_int32, C.POINTER(C.c_int64)]),
@@ -98,10 +101,13 @@ SIGNATURES = {
                                             C.c_float, C.c_void_p, C.c_uint32, C.c_int32, C.c_void_p, C.c_void_p]),
     "rd_linear_wgrad_partial_bytes": (C.c_size_t, [C.c_int64, C.c_int32, C.c_int32]),
     "rd_linear_wgrad_group": (C.c_int, [C.POINTER(RdWgradItem), C.c_int32, C.c_void_p]),
-    "rd_transformer_conv_scratch_bytes": (C.c_size_t, [C.c_int32] * 5),
-    "rd_transformer_conv_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32,
-                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] +
-                                [C.c_void_p] * 8 + [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rd_transformer_conv_scratch_bytes": (C.c_size_t, [C.c_int32] * 7),
+    "rd_transformer_conv_fwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 8 +
+                                [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rd_transformer_conv_bwd": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32] + [C.c_void_p] * 7 +
+                                [C.c_void_p] * 2 + [C.c_void_p] * 10 + [C.c_void_p, C.c_void_p]),
     "rd_gather_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
                                   C.c_void_p]),
     "rd_assemble_batch": (C.c_int, [C.c_void_p] * 5 + [C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 6),

