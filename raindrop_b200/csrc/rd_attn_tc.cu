@@ -158,6 +158,7 @@ __device__ __forceinline__ void load_row64(uint32_t taddr, float (&v)[64]) {
 __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant__ CUtensorMap tmQKV,
                                                            const __grid_constant__ CUtensorMap tmQKVm, const AttnTcP p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tO = tmem + 64;
 
@@ -271,6 +273,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
                                                            const __grid_constant__ CUtensorMap tmDO,
                                                            const __grid_constant__ CUtensorMap tmDOm, const AttnTcP p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
@@ -301,6 +304,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tDP = tmem + 64, tDV = tmem + 128, tDQ = tmem + 224, tDK = tmem + 320;
 
@@ -490,7 +494,7 @@ int attn_tc_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T, i
   RD_TRY(encode_qkv(&tm, qkv, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B));
   RD_TRY(encode_qkv(&tmm, qkv, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   RD_TRY(ensure_max_smem((const void*)attn_tc_fwd_kernel, FWD_SMEM));
-  attn_tc_fwd_kernel<<<B * H, NTHR, FWD_SMEM, st>>>(tm, tmm, p);
+  launch_pdl(attn_tc_fwd_kernel, dim3(B * H), dim3(NTHR), FWD_SMEM, st, tm, tmm, p);
   RD_CHECK_LAUNCH("attn_tc_fwd_kernel");
   return 0;
 }
@@ -511,7 +515,7 @@ int attn_tc_bwd(const float* qkv, const float* dctx, const int64_t* lengths, int
   RD_TRY(encode_ctx(&tg, dctx, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B));
   RD_TRY(encode_ctx(&tgm, dctx, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
   RD_TRY(ensure_max_smem((const void*)attn_tc_bwd_kernel, BWD_SMEM));
-  attn_tc_bwd_kernel<<<B * H, NTHR, BWD_SMEM, st>>>(tq, tqm, tg, tgm, p);
+  launch_pdl(attn_tc_bwd_kernel, dim3(B * H), dim3(NTHR), BWD_SMEM, st, tq, tqm, tg, tgm, p);
   RD_CHECK_LAUNCH("attn_tc_bwd_kernel");
   return 0;
 }

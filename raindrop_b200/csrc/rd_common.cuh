@@ -24,6 +24,29 @@ int check_launch(const char* what);  // cudaPeekAtLastError -> 0 / -1
     if (_rc != 0) return _rc;    \
   } while (0)
 
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------
+// A training step is ~40 dependent launches of 5-20 us each, so the ~2 us between "last CTA of kernel N exits" and
+// "first CTA of kernel N+1 runs" is ~10 % of the step.  Kernels launched through launch_pdl() may be scheduled as soon
+// as every CTA of the previous kernel has executed pdl_launch_dependents() (first instruction of our kernels): their
+// CTAs take free SMs, run their prologue (barrier init, TMEM allocation, tensor-map prefetch) and then block in
+// pdl_wait() until the previous kernel has COMPLETED and flushed its writes.  Every kernel calls pdl_wait() before its
+// first global read of produced data and before its first global write, so the dependency semantics are unchanged.
+// Stream capture records these as programmatic edges, so the CUDA-graph replay keeps the overlap.  RD_PDL=0 disables.
+bool pdl_enabled();
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
 

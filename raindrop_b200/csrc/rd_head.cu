@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadP p, const float* __re
                                                       const int64_t* __restrict__ y, float* __restrict__ loss_ps,
                                                       float* __restrict__ dlogits, float* __restrict__ loss,
                                                       unsigned* __restrict__ counter) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* fs = sm; float* hs = fs + p.Df; float* red = sm + ((2 * p.Df + 3) & ~3);     // red (16-byte aligned): [8][D] pooling partials, later logits
   __shared__ int s_last;
@@ -99,7 +101,13 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadP p, const float* __re
   for (int c = warp; c < p.ncls; c += HT / 32) {
     const float* wr = p.w2 + (long long)c * p.Df;
     float a = 0.f;
-    for (int j = lane; j < p.Df; j += 32) a = fmaf(hs[j], __ldg(wr + j), a);
+    for (int jb = 0; jb < p.Df; jb += 256) {       // all weight loads of a 256-wide pass in flight before the FMAs
+      float w[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const int j = jb + lane + 32 * e; w[e] = j < p.Df ? __ldg(wr + j) : 0.f; }
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { const int j = jb + lane + 32 * e; if (j < p.Df) a = fmaf(hs[j], w[e], a); }
+    }
     a = warp_sum(a);
     if (lane == 0) { a += __ldg(p.b2 + c); logits[(long long)b * p.ncls + c] = a; lg[c] = a; }
   }
@@ -138,6 +146,8 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadP p, const float* __re
 __global__ void __launch_bounds__(HT) head_bwd_sample_kernel(HeadP p, const float* __restrict__ hpre,
                                                              const float* __restrict__ dlogits, float* __restrict__ dh,
                                                              float* __restrict__ dfeat, float* __restrict__ dx) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float sm[];
   float* ds_ = sm;                 // dh of this sample [Df]
   float* part = sm + p.Df;         // [groups][Df] partial dfeat
@@ -151,24 +161,42 @@ __global__ void __launch_bounds__(HT) head_bwd_sample_kernel(HeadP p, const floa
     dh[(long long)b * p.Df + j] = a;
   }
   __syncthreads();
-  // column k of W0 is coalesced across threads; the j range is split over `groups` thread groups
-  const int kpad = p.Df >= HT ? HT : ((p.Df + 31) / 32) * 32;
-  const int groups = HT / kpad;
-  const int jg = tid / kpad, kk = tid - jg * kpad;
-  if (jg < groups) {
-    const int jper = (p.Df + groups - 1) / groups;
-    const int j0 = jg * jper, j1 = min(p.Df, j0 + jper);
-    for (int k = kk; k < p.Df; k += kpad) {
-      float a = 0.f;
-#pragma unroll 8
-      for (int j = j0; j < j1; ++j) a = fmaf(ds_[j], __ldg(p.w0 + (long long)j * p.Df + k), a);
-      part[jg * p.Df + k] = a;
+  // dfeat[k] = sum_j dh[j] W0[j, k]: a warp owns rows j = warp, warp + 16, ...; its lanes sweep k in chunks of 256 with the
+  // loads of 4 rows x 8 columns in flight together; the 16 per-warp partial rows are then summed in a fixed order
+  const int warp = tid >> 5, lane = tid & 31, nwarp = HT / 32;
+  for (int kb = 0; kb < p.Df; kb += 256) {
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int j0 = warp; j0 < p.Df; j0 += 4 * nwarp) {
+      float w[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * nwarp;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int k = kb + lane + 32 * e;
+          w[u][e] = (j < p.Df && k < p.Df) ? __ldg(p.w0 + (long long)j * p.Df + k) : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + u * nwarp;
+        const float d = j < p.Df ? ds_[j] : 0.f;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] = fmaf(d, w[u][e], acc[e]);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = kb + lane + 32 * e;
+      if (k < p.Df) part[warp * p.Df + k] = acc[e];
     }
   }
   __syncthreads();
   for (int k = tid; k < p.Df; k += HT) {
     float a = part[k];
-    for (int g = 1; g < groups; ++g) a += part[g * p.Df + k];
+    for (int g = 1; g < nwarp; ++g) a += part[g * p.Df + k];
     dfeat[(long long)b * p.Df + k] = a;
     df[k] = a;          // only thread `k` touched part[.][k] above: no hazard
   }
@@ -190,6 +218,8 @@ __global__ void __launch_bounds__(HT) head_bwd_sample_kernel(HeadP p, const floa
 struct OuterItem { const float* L; long long ldl; const float* R; long long ldr; int J, K, kt, blk0; float* out; float* bias; };
 struct OuterGroup { OuterItem it[3]; int n, B; };
 __global__ void __launch_bounds__(256) head_outer_kernel(const __grid_constant__ OuterGroup g) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float Ls[32][33], Rs[32][33];
   int ii = 0;
   for (int k = 1; k < g.n; ++k) if ((int)blockIdx.x >= g.it[k].blk0) ii = k;
@@ -250,7 +280,7 @@ int head_fwd(int B, int T, int D, int N, int ds, int ncls, const float* x, const
   const size_t smem = (size_t)(((2 * p.Df + 3) & ~3) + red) * sizeof(float);
   if (smem > 48 * 1024 || (D & 3)) { set_error("head_fwd: feature width %d not supported", p.Df); return -2; }
   if (y && (!loss_ps || !dlogits || !loss || !counter)) { set_error("head_fwd: labels given without loss outputs"); return -2; }
-  head_fwd_kernel<<<B, HT, smem, st>>>(p, x, feat, hpre, logits, y, loss_ps, dlogits, loss, counter);
+  launch_pdl(head_fwd_kernel, dim3(B), dim3(HT), smem, st, p, x, feat, hpre, logits, y, loss_ps, dlogits, loss, counter);
   RD_CHECK_LAUNCH("head_fwd_kernel");
   return 0;
 }
@@ -259,11 +289,9 @@ int head_bwd(int B, int T, int D, int N, int ds, int ncls, const int64_t* length
              const float* w2, const float* feat, const float* hpre, const float* dlogits, float* dh, float* dfeat, float* dx,
              float* g_w0, float* g_b0, float* g_w2, float* g_b2, float* g_emb_w, float* g_emb_b, cudaStream_t st) {
   HeadP p = make(B, T, D, N, ds, ncls, statics, nullptr, nullptr, w0, nullptr, w2, nullptr, lengths);
-  const int kpad = p.Df >= HT ? HT : ((p.Df + 31) / 32) * 32;
-  const int groups = HT / kpad;
-  const size_t smem = (size_t)(1 + groups) * p.Df * sizeof(float);
+  const size_t smem = (size_t)(1 + HT / 32) * p.Df * sizeof(float);       // dh + one partial dfeat row per warp
   if (smem > 48 * 1024) { set_error("head_bwd: feature width %d too large", p.Df); return -2; }
-  head_bwd_sample_kernel<<<B, HT, smem, st>>>(p, hpre, dlogits, dh, dfeat, dx);
+  launch_pdl(head_bwd_sample_kernel, dim3(B), dim3(HT), smem, st, p, hpre, dlogits, dh, dfeat, dx);
   RD_CHECK_LAUNCH("head_bwd_sample_kernel");
   OuterGroup g;
   g.B = B; g.n = 0;
@@ -276,7 +304,7 @@ int head_bwd(int B, int T, int D, int N, int ds, int ncls, const int64_t* length
   add(dh, p.Df, feat, p.Df, p.Df, p.Df, g_w0, g_b0);                   // d mlp_static.0
   add(dlogits, ncls, hpre, p.Df, ncls, p.Df, g_w2, g_b2);              // d mlp_static.2
   if (ds > 0) add(dfeat + D, p.Df, statics, ds, N, ds, g_emb_w, g_emb_b);   // d emb
-  head_outer_kernel<<<blk, 256, 0, st>>>(g);
+  launch_pdl(head_outer_kernel, dim3(blk), dim3(256), 0, st, g);
   RD_CHECK_LAUNCH("head_outer_kernel");
   return 0;
 }

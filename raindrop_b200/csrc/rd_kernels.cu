@@ -3,6 +3,7 @@
 // streaming kernels: coalesced along the fastest tensor dimension, one warp per row for the
 // row-wise reductions (warp-shuffle, no shared memory), grid sized from the element count.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "rd_kernels.cuh"
@@ -20,6 +21,11 @@ void set_error(const char* fmt, ...) {
 const char* last_error() { return g_err; }
 static unsigned long long g_launches = 0;
 unsigned long long launch_count() { return g_launches; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("RD_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  return v == 1;
+}
 int check_launch(const char* what) {
   ++g_launches;
   cudaError_t e = cudaPeekAtLastError();
@@ -163,6 +169,8 @@ __global__ void __launch_bounds__(256) assemble_batch_kernel(const float* __rest
                                                             int ds, int B, float* __restrict__ src, float* __restrict__ times,
                                                             float* __restrict__ statics, int64_t* __restrict__ y_out,
                                                             int64_t* __restrict__ lengths) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ int cnt[8];
   const int j = blockIdx.x;
   const long long sidx = idx[j];
@@ -206,6 +214,8 @@ __global__ void lift_posenc_kernel(const float* __restrict__ src, const float* _
                                    int d_ob, float drop_p, const uint64_t* __restrict__ rng, int round,
                                    float* __restrict__ X0, long long n_lift, const float* __restrict__ times,
                                    long long n_tokens, TS8 ts, float* __restrict__ pe_out, long long ld, int col0) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (o < n_lift) {
     const long long row = o / T;
@@ -270,6 +280,8 @@ __global__ void node_scale_kernel(const int64_t* __restrict__ tgt, const float* 
 __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, long long rows, int D, float eps,
                                      float* __restrict__ y, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -296,6 +308,8 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(
     const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ dy, long long rows, int D, float* __restrict__ dx, float* __restrict__ dx_drop,
     float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial) {
+  pdl_launch_dependents();
+  pdl_wait();
   extern __shared__ float lsm[];                     // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
@@ -500,6 +514,8 @@ __global__ void attn_softmax_bwd_kernel(const float* __restrict__ P, float* __re
 __global__ void obprop_out_grad_kernel(const float* __restrict__ dZ, const float* __restrict__ Z,
                                        const float* __restrict__ s, int B, int T, int N, int d_ob, int D,
                                        int round, float* __restrict__ dZ2) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long C = (long long)T * d_ob;
   long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= (long long)B * N * C) return;
@@ -563,6 +579,8 @@ __global__ void cross_entropy_kernel(const float* __restrict__ logits, const int
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
                             float* __restrict__ v, long long n, float lr, const float* __restrict__ lr_dev, float b1,
                             float b2, float eps, float gscale, int64_t* __restrict__ step) {
+  pdl_launch_dependents();
+  pdl_wait();
   __shared__ float bc[3];
   if (threadIdx.x == 0) {
     double t = (double)(*reinterpret_cast<volatile int64_t*>(step) + 1);
@@ -632,7 +650,8 @@ int assemble_batch(const float* P, const float* Pt, const float* Ps, const int64
     return -2;
   }
   if (B <= 0) return 0;
-  assemble_batch_kernel<<<B, 256, 0, st>>>(P, Pt, Ps, y, idx, T, n_total, width, ds, B, src, times, statics, y_out, lengths);
+  launch_pdl(assemble_batch_kernel, dim3(B), dim3(256), 0, st, P, Pt, Ps, y, idx, T, (long long)n_total, width, ds, B, src, times, statics,
+             y_out, lengths);
   RD_CHECK_LAUNCH("assemble_batch_kernel");
   return 0;
 }
@@ -671,8 +690,8 @@ int lift_posenc(const float* src, const float* R_u, int B, int T, int N, int d_o
   TS8 ts;
   if (times) memcpy(ts.v, ts8_host, sizeof(ts.v)); else memset(ts.v, 0, sizeof(ts.v));
   if (n_lift + n_pe <= 0) return 0;
-  lift_posenc_kernel<<<blocks_for(n_lift + n_pe), TPB, 0, st>>>(src, R_u, B, T, N, d_ob, drop_p, rng, round, X0, n_lift, times,
-                                                               times ? n_tokens : 0, ts, pe_out, ld, col0);
+  launch_pdl(lift_posenc_kernel, dim3(blocks_for(n_lift + n_pe)), dim3(TPB), 0, st, src, R_u, B, T, N, d_ob, drop_p, rng, round, X0,
+             (long long)n_lift, times, (long long)(times ? n_tokens : 0), ts, pe_out, (long long)ld, col0);
   RD_CHECK_LAUNCH("lift_posenc_kernel");
   return 0;
 }
@@ -690,7 +709,7 @@ int node_scale(const int64_t* edge_tgt, const float* edge_w, int E, int N, float
 
 int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int D, float eps, float* y,
                   float* stats, cudaStream_t st) {
-  layernorm_fwd_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, gamma, beta, rows, D, eps, y, stats);
+  launch_pdl(layernorm_fwd_kernel, dim3(blocks_for(rows * 32)), dim3(TPB), 0, st, x, gamma, beta, (long long)rows, D, eps, y, stats);
   RD_CHECK_LAUNCH("layernorm_fwd_kernel");
   return 0;
 }
@@ -708,8 +727,8 @@ int layernorm_bwd(const float* x, const float* stats, const float* gamma, const 
   int chunks;
   if ((D & 3) == 0 && D <= 128 * LNB_MAXIT && (bits & 15) == 0) {     // fused single pass
     chunks = (int)ceil_div(rows, LNB_ROWS);
-    layernorm_bwd_fused_kernel<<<chunks, 256, 8 * 2 * D * sizeof(float), st>>>(
-        x, stats, gamma, dy, rows, D, dx, drop_p > 0.f ? dx_drop : nullptr, drop_p, rng, site, scratch);
+    launch_pdl(layernorm_bwd_fused_kernel, dim3(chunks), dim3(256), 8 * 2 * D * sizeof(float), st, x, stats, gamma, dy, (long long)rows, D,
+               dx, drop_p > 0.f ? dx_drop : (float*)nullptr, drop_p, rng, site, scratch);
     RD_CHECK_LAUNCH("layernorm_bwd_fused_kernel");
   } else {
     layernorm_bwd_dx_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, stats, gamma, dy, rows, D, dx,
@@ -745,7 +764,7 @@ int attn_softmax_bwd(const float* P, float* dP, int B, int H, int T, float drop_
 int obprop_out_grad(const float* dZ, const float* Z, const float* s, int B, int T, int N, int d_ob, int D,
                     int round, float* dZ2, cudaStream_t st) {
   int64_t total = (int64_t)B * N * T * d_ob;
-  obprop_out_grad_kernel<<<blocks_for(total), TPB, 0, st>>>(dZ, Z, s, B, T, N, d_ob, D, round, dZ2);
+  launch_pdl(obprop_out_grad_kernel, dim3(blocks_for(total)), dim3(TPB), 0, st, dZ, Z, s, B, T, N, d_ob, D, round, dZ2);
   RD_CHECK_LAUNCH("obprop_out_grad_kernel");
   return 0;
 }
@@ -773,7 +792,7 @@ int cross_entropy(const float* logits, const int64_t* y, int B, int ncls, float*
 
 int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float b1, float b2,
          float eps, float gscale, int64_t* step, cudaStream_t st) {
-  adam_kernel<<<blocks_for(n), TPB, 0, st>>>(p, g, m, v, n, lr, lr_dev, b1, b2, eps, gscale, step);
+  launch_pdl(adam_kernel, dim3(blocks_for(n)), dim3(TPB), 0, st, p, g, m, v, (long long)n, lr, lr_dev, b1, b2, eps, gscale, step);
   RD_CHECK_LAUNCH("adam_kernel");
   return 0;
 }

@@ -66,6 +66,7 @@ __global__ void __launch_bounds__(EXACT ? NTHREADS_EXACT : NTHREADS, 1)
 obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                  const __grid_constant__ CUtensorMap tmWlo, const __grid_constant__ CUtensorMap tmOut, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t w_tile = (uint32_t)p.BN * 128u;
@@ -103,6 +104,7 @@ obprop_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
@@ -362,7 +364,7 @@ int obprop_tc_fwd(const ObpropTcArgs& a, cudaStream_t st) {
   int grid = total < num_sms() ? total : num_sms();
   auto launch = [&](auto kern, int nthreads) -> int {
     RD_TRY(ensure_max_smem((const void*)kern, SMEM_LIMIT));   // once per (instantiation, device)
-    kern<<<grid, nthreads, smem_bytes, st>>>(tmA, tmW, tmWlo, tmOut, p);
+    launch_pdl(kern, dim3(grid), dim3(nthreads), smem_bytes, st, tmA, tmW, tmWlo, tmOut, p);
     return 0;
   };
   int rc;

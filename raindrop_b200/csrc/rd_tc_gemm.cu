@@ -41,6 +41,7 @@ __global__ void __launch_bounds__(NTHREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmC, const P p) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_tile = (uint32_t)p.BN * 128u;
@@ -74,6 +75,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();          // everything above is private to this CTA; the previous kernel's output is first touched below
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
@@ -298,6 +300,7 @@ constexpr int MN_BOX = 32 * 32 * 4;  // one {32 col, 32 row} fp32 box = 4096 byt
 __global__ void __launch_bounds__(W_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ WGroup g) {
   extern __shared__ uint8_t smem_raw[];
+  pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   int pi = 0;
@@ -340,6 +343,7 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
@@ -445,6 +449,8 @@ struct RItem { const float* partial; float* dW; float* db; int nsplit, M, N, Mpa
 constexpr int RG_MAX = WG_MAX + CS_MAX;
 struct RGroup { RItem it[RG_MAX]; long long total; int n; };
 __global__ void wgrad_reduce_kernel(const __grid_constant__ RGroup g) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= g.total) return;
   int k = 0;
@@ -497,6 +503,8 @@ WPlan wgrad_plan(int M, int N, long long rows) {
 struct SplitItems { WeightSplit it[16]; long long start[17]; int n; StepPrologue pro; };
 
 __global__ void split_weights_kernel(const __grid_constant__ SplitItems s) {
+  pdl_launch_dependents();
+  pdl_wait();
   long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i == 0) {     // step prologue riding along: dropout counter capture (+ advance) and ticket reset
     if (s.pro.rng_state) {
@@ -579,7 +587,7 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
   const int grid = total < num_sms() ? total : num_sms();
   auto launch = [&](auto kern, int id) -> int {
     RD_TRY(ensure_attr((const void*)kern, id));
-    kern<<<grid, NTHREADS, smem_bytes, st>>>(tmB, tmBlo, tmC, p);
+    launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem_bytes, st, tmB, tmBlo, tmC, p);
     return 0;
   };
   const int id = (a.relu ? 8 : 0) | (a.gate ? 4 : 0) | (a.drop_p > 0.f ? 2 : 0) | (a.resid ? 1 : 0);
@@ -667,10 +675,10 @@ int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs,
   r.total = tot;
   if (n > 0) {
     RD_TRY(ensure_attr((const void*)tc_wgrad_kernel, 15));
-    tc_wgrad_kernel<<<cta, W_THREADS, smem_bytes, st>>>(g);
+    launch_pdl(tc_wgrad_kernel, dim3(cta), dim3(W_THREADS), smem_bytes, st, g);
     RD_CHECK_LAUNCH("tc_wgrad_kernel");
   }
-  wgrad_reduce_kernel<<<(unsigned)ceil_div(tot, 256), 256, 0, st>>>(r);
+  launch_pdl(wgrad_reduce_kernel, dim3((unsigned)ceil_div(tot, 256)), dim3(256), 0, st, r);
   RD_CHECK_LAUNCH("wgrad_reduce_kernel");
   return 0;
 }
@@ -689,7 +697,7 @@ int split_weights(const WeightSplit* items, int n, cudaStream_t st, const StepPr
   for (int i = 0; i < n; ++i) { s.it[i] = items[i]; s.start[i + 1] = s.start[i] + (long long)items[i].rows * items[i].cols; }
   s.pro = pro ? *pro : StepPrologue{};
   const long long total = s.start[n] > 0 ? s.start[n] : 1;
-  split_weights_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(s);
+  launch_pdl(split_weights_kernel, dim3((unsigned)ceil_div(total, 256)), dim3(256), 0, st, s);
   RD_CHECK_LAUNCH("split_weights_kernel");
   return 0;
 }

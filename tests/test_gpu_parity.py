@@ -473,6 +473,8 @@ def test_graph_operator_gradients(golden_dir):
                 got = params[name].grad
                 if np.abs(ref).max() == 0:
                     assert got is None or float(got.abs().max()) == 0.0, name          # q/k unused when edge weights are supplied
+                elif np.abs(ref).max() < 1e-7:
+                    assert float(got.abs().max()) < 1e-6, name       # lin_key.bias: a per-target constant shift of the logits, softmax-invariant
                 else:
                     assert normwise(got, ref) < 2e-5, (tag, name, normwise(got, ref))
     # batched form: many graphs sharing one edge list == the per-graph loop (legacy Raindrop v1, code/models_rd.py:158-166)
