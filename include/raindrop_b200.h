@@ -45,6 +45,11 @@ typedef struct rd_dims {
   float ln_eps;      /* 1e-5                                                              */
   float pe_timescales[RD_D_PE / 2]; /* max_len ** linspace(0,1,8) computed in fp64 on host,
                                        cast to fp32 (code/models_rd.py:31,34)             */
+  int32_t d_pe;        /* width of the positional encoding concatenated to the encoder input; 0 = 16 (Raindrop_v2,
+                          code/models_rd.py:215).  Legacy Raindrop v1 uses 36 (code/models_rd.py:68); only the
+                          rd_encoder_head_* entry points accept values other than 16                              */
+  int32_t emb_dim;     /* width of emb = Linear(d_static, emb_dim): 0 = N (Raindrop_v2, code/models_rd.py:224);
+                          d_model for legacy Raindrop v1 (code/models_rd.py:98)                                    */
   int32_t obprop_mode; /* arithmetic of the two observation-propagation GEMMs on the tensor cores:
                           0 = automatic: error-compensated 3xTF32 (fp32-level, gradients match the fp32 reference
                               to ~1e-3) while 2*B*N*C^2 <= 2 GFLOP per layer, i.e. where the layer is launch-latency
@@ -206,10 +211,28 @@ int rd_raindrop_v2_bwd(const rd_dims* dims, const rd_params* params, const float
                        const float* d_logits, const rd_grads* grads, void* scratch, int32_t phases,
                        void* stream);
 
+/* ---- temporal encoder + pooling + head on a caller-provided encoder input ------------------------------------
+ * The second half of Raindrop_v2.forward (code/models_rd.py:354-385) and all of legacy Raindrop v1 after its
+ * per-sample TransformerConv (code/models_rd.py:168-191): nn.TransformerEncoder with key-padding mask, masked mean
+ * (divisor lengths + 1), concat emb(static), mlp_static.  The caller writes the encoder input cat(features, pe)
+ * [T, B, D = N*d_ob + d_pe] into the workspace buffer RD_WS_ENC_IN first (rd_workspace_offset), then calls _fwd;
+ * _bwd fills every encoder / emb / mlp_static gradient of `grads` (the ob-prop members are ignored) and writes
+ * d(loss)/d(encoder input) to d_enc_in [T, B, D].  Same workspace / scratch sizes and rng protocol as
+ * rd_raindrop_v2_fwd / _bwd. */
+int rd_encoder_head_fwd(const rd_dims* dims, const rd_params* params, const float* statics, const int64_t* lengths,
+                        uint64_t* rng_state, void* workspace, float* logits, const int64_t* y, float* loss,
+                        float* d_logits, void* stream);
+int rd_encoder_head_bwd(const rd_dims* dims, const rd_params* params, const float* statics, const int64_t* lengths,
+                        const void* workspace, const float* d_logits, const rd_grads* grads, void* scratch,
+                        float* d_enc_in, void* stream);
+/* y[i] = x[i] * keep(site, i) / (1 - p): nn.Dropout driven by the library's counter-based stream (rng_captured =
+ * {seed, counter} on the device).  The same call on a gradient is its backward. */
+int rd_dropout(const float* x, int64_t n, float p, const uint64_t* rng_captured, uint32_t site, float* y, void* stream);
+
 /* ---- pieces exposed on their own (module-level drop-ins and tests) -------------------------
- * pe[t,b,:] = [sin(times/ts_k), cos(times/ts_k)]  -> out[(t*B+b)*ld + col0 + 0..15]
+ * pe[t,b,:] = [sin(times/ts_k), cos(times/ts_k)], k < d_pe/2 (d_pe <= 64)  -> out[(t*B+b)*ld + col0 + 0..d_pe-1]
  * Replaces PositionalEncodingTF.getPE (code/models_rd.py:28-37) without the host round trip. */
-int rd_positional_encoding(const float* times, int64_t n_tokens, const float* timescales_host,
+int rd_positional_encoding(const float* times, int64_t n_tokens, const float* timescales_host, int32_t d_pe,
                            float* out, int64_t ld, int32_t col0, void* stream);
 
 /* out[rows, out_f] = [relu](x[rows, in_f] . weight[out_f, in_f]^T + bias): the encoder's projection

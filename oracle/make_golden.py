@@ -198,13 +198,51 @@ def operator_grad_cases():
     print("operators_grad     %d arrays: %s" % (len(out), sorted(out)[:60]))
 
 
+def v1_case():
+    """Legacy `Raindrop` v1 (code/models_rd.py:46-191; hard-coded to 36 sensors / 215 steps): logits, loss and the
+    gradient of every parameter that gets one, B = 3, eval mode.  Weights: seeded default init, but `encoder` / `emb`
+    re-drawn at a useful scale (the reference initialises them to +-1e-10, which would hide the graph layer)."""
+    ref = ref_harness.load_reference()
+    from raindrop_b200.synth import CONFIGS
+    cfg = dict(CONFIGS["P12"]); cfg["name"] = "P12"
+    B = 3
+    batch = make_batch(dict(cfg, d_ob=2), B, seed=77)
+    torch.manual_seed(5)
+    gs = (torch.rand(36, 36) < 0.5).float() * torch.rand(36, 36)
+    model = ref.Raindrop(36, 72, 2, 144, 2, 0.2, 215, 9, 100, 0.5, "mean", 2, gs.clone()).eval()
+    with torch.no_grad():
+        model.encoder.weight.uniform_(-0.3, 0.3)
+        model.emb.weight.uniform_(-0.3, 0.3)
+    logits, distance, _ = model.forward(batch["src"], batch["static"], batch["times"], batch["lengths"])
+    loss = F.cross_entropy(logits, batch["y"])
+    model.zero_grad()
+    loss.backward()
+    out = dict(logits=logits.detach().numpy(), loss=np.float32(loss.item()), distance=np.float32(float(distance)),
+               global_structure=gs.numpy())
+    for k, v in model.state_dict().items():
+        out["sd." + k] = v.numpy()
+    for k, prm in model.named_parameters():
+        if prm.grad is not None:
+            out["grad." + k] = prm.grad.numpy()
+    meta = dict(case="v1_p12_b3", batch=B, data_seed=77, torch=torch.__version__, reference_commit="892eb57",
+                generator="oracle/make_golden.py v1")
+    out["meta"] = np.frombuffer(json.dumps(meta).encode(), dtype=np.uint8)
+    np.savez_compressed(os.path.join(GOLDEN, "v1_p12_b3.npz"), **out)
+    print("v1_p12_b3  logits[0]=%s loss=%.6f distance=%g grads for %d tensors" %
+          (logits[0].tolist(), loss.item(), float(distance), sum(1 for k in out if k.startswith("grad."))))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
     if len(sys.argv) > 1 and sys.argv[1] == "operators_grad":      # add-on fixtures: leaves the existing files untouched
         operator_grad_cases()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "v1":
+        v1_case()
+        sys.exit(0)
     for case in CASES:
         run_case(*case)
     operator_cases()
     operator_grad_cases()
+    v1_case()

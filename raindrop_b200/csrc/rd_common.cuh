@@ -31,7 +31,8 @@ int check_launch(const char* what);  // cudaPeekAtLastError -> 0 / -1
 // CTAs take free SMs, run their prologue (barrier init, TMEM allocation, tensor-map prefetch) and then block in
 // pdl_wait() until the previous kernel has COMPLETED and flushed its writes.  Every kernel calls pdl_wait() before its
 // first global read of produced data and before its first global write, so the dependency semantics are unchanged.
-// Stream capture records these as programmatic edges, so the CUDA-graph replay keeps the overlap.  RD_PDL=0 disables.
+// Stream capture records these as programmatic edges.  Measured on B200 (P19 B=128, graph replay): 0.698 ms with vs
+// 0.692 ms without -- inside a graph the launches are already back to back -- so it is OFF unless RD_PDL=1.
 bool pdl_enabled();
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }

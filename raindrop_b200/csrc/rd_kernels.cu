@@ -23,7 +23,7 @@ static unsigned long long g_launches = 0;
 unsigned long long launch_count() { return g_launches; }
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("RD_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
+  if (v < 0) { const char* e = getenv("RD_PDL"); v = (e && e[0] == '1') ? 1 : 0; }   // measured: no gain inside a CUDA graph -> opt-in
   return v == 1;
 }
 int check_launch(const char* what) {
@@ -205,7 +205,7 @@ __global__ void rng_capture_kernel(uint64_t* state, uint64_t* cap, int advance) 
   if (advance) state[1] = state[1] + 1;
 }
 
-struct TS8 { float v[8]; };
+struct TS8 { float v[32]; int d_pe; };      // up to 32 timescales (d_pe <= 64)
 // One launch for the two element-wise producers of the forward's inputs:
 //   o <  n_lift : X0[(b*N+n), t*d_ob + 0..d_ob) = dropout(relu(src[t,b,n] * R_u[n*d_ob + k]))   code/models_rd.py:285-296,323-327
 //                 (one thread per (row, t); for d_ob == 4 one 128-bit store and ONE Philox block per thread)
@@ -244,11 +244,11 @@ __global__ void lift_posenc_kernel(const float* __restrict__ src, const float* _
     return;
   }
   o -= n_lift;
-  if (o >= n_tokens * 16) return;
-  long long tok = o >> 4;
-  int j = (int)(o & 15);
-  float scaled = __ldg(times + tok) / ts.v[j & 7];
-  pe_out[tok * ld + col0 + j] = (j < 8) ? sinf(scaled) : cosf(scaled);
+  if (o >= n_tokens * ts.d_pe) return;
+  const long long tok = o / ts.d_pe;
+  const int j = (int)(o - tok * ts.d_pe), half = ts.d_pe >> 1;
+  const float scaled = __ldg(times + tok) / ts.v[j < half ? j : j - half];
+  pe_out[tok * ld + col0 + j] = (j < half) ? sinf(scaled) : cosf(scaled);
 }
 
 // one warp per node: segment max, then sum of exp, then s = sum(exp / (sum + 1e-16))
@@ -683,12 +683,15 @@ int gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_tota
 }
 
 int lift_posenc(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p, const uint64_t* rng,
-                int round, float* X0, const float* times, int64_t n_tokens, const float* ts8_host, float* pe_out, int64_t ld,
-                int col0, cudaStream_t st) {
+                int round, float* X0, const float* times, int64_t n_tokens, const float* ts_host, int d_pe, float* pe_out,
+                int64_t ld, int col0, cudaStream_t st) {
+  if (times && (d_pe < 2 || d_pe > 64 || (d_pe & 1))) { set_error("positional encoding width must be even and <= 64"); return -2; }
   const int64_t n_lift = src ? (int64_t)B * N * T : 0;      // one thread per (row, t)
-  const int64_t n_pe = times ? n_tokens * 16 : 0;
+  const int64_t n_pe = times ? n_tokens * d_pe : 0;
   TS8 ts;
-  if (times) memcpy(ts.v, ts8_host, sizeof(ts.v)); else memset(ts.v, 0, sizeof(ts.v));
+  memset(&ts, 0, sizeof(ts));
+  ts.d_pe = times ? d_pe : 2;
+  if (times) memcpy(ts.v, ts_host, sizeof(float) * (d_pe / 2));
   if (n_lift + n_pe <= 0) return 0;
   launch_pdl(lift_posenc_kernel, dim3(blocks_for(n_lift + n_pe)), dim3(TPB), 0, st, src, R_u, B, T, N, d_ob, drop_p, rng, round, X0,
              (long long)n_lift, times, (long long)(times ? n_tokens : 0), ts, pe_out, (long long)ld, col0);
@@ -696,9 +699,9 @@ int lift_posenc(const float* src, const float* R_u, int B, int T, int N, int d_o
   return 0;
 }
 
-int posenc(const float* times, int64_t n_tokens, const float* ts8_host, float* out, int64_t ld, int col0,
+int posenc(const float* times, int64_t n_tokens, const float* ts_host, int d_pe, float* out, int64_t ld, int col0,
            cudaStream_t st) {
-  return lift_posenc(nullptr, nullptr, 0, 0, 0, 0, 0.f, nullptr, 0, nullptr, times, n_tokens, ts8_host, out, ld, col0, st);
+  return lift_posenc(nullptr, nullptr, 0, 0, 0, 0, 0.f, nullptr, 0, nullptr, times, n_tokens, ts_host, d_pe, out, ld, col0, st);
 }
 
 int node_scale(const int64_t* edge_tgt, const float* edge_w, int E, int N, float* s, cudaStream_t st) {

@@ -25,13 +25,13 @@ int assemble_batch(const float* P, const float* Pt, const float* Ps, const int64
 // The same launch writes the positional encoding of `times` into pe_out[tok*ld + col0 ..+16] (src == nullptr
 // or times == nullptr skips that half).
 int lift_posenc(const float* src, const float* R_u, int B, int T, int N, int d_ob, float drop_p, const uint64_t* rng,
-                int round, float* X0, const float* times, int64_t n_tokens, const float* ts8_host, float* pe_out, int64_t ld,
-                int col0, cudaStream_t st);
+                int round, float* X0, const float* times, int64_t n_tokens, const float* ts_host, int d_pe, float* pe_out,
+                int64_t ld, int col0, cudaStream_t st);
 
 // y [cols, rows] = RN_tf32(x [rows, cols])^T
 int transpose_round(const float* x, int rows, int cols, float* y, cudaStream_t st);
 
-int posenc(const float* times, int64_t n_tokens, const float* ts8_host, float* out, int64_t ld, int col0,
+int posenc(const float* times, int64_t n_tokens, const float* ts_host, int d_pe, float* out, int64_t ld, int col0,
            cudaStream_t st);
 
 int node_scale(const int64_t* edge_tgt, const float* edge_w, int E, int N, float* s, cudaStream_t st);

@@ -18,7 +18,7 @@ namespace {
 
 struct Shape {
   int B, T, N, dob, H, nhid, L, ds, ncls;
-  int C, Dm, D, Df, hd;
+  int C, Dm, D, Df, hd, dpe, emb;
   int64_t M1, M2;
   float p;  // effective dropout probability (0 in eval)
   int tc, exact;   // ob-prop layers: tensor-core kernel usable / error-compensated (3xTF32) mode chosen
@@ -34,10 +34,13 @@ int make_shape(const rd_dims* d, Shape* s) {
               s->B, s->T, s->N, s->dob, s->H, s->nhid, s->L, s->ds, s->ncls);
     return -2;
   }
-  s->C = s->T * s->dob; s->Dm = s->N * s->dob; s->D = s->Dm + RD_D_PE;
+  s->dpe = d->d_pe > 0 ? d->d_pe : RD_D_PE;
+  s->emb = d->emb_dim > 0 ? d->emb_dim : s->N;
+  if (s->dpe > 64 || (s->dpe & 3)) { set_error("d_pe = %d must be a multiple of 4 and <= 64", s->dpe); return -2; }
+  s->C = s->T * s->dob; s->Dm = s->N * s->dob; s->D = s->Dm + s->dpe;
   if (s->D % s->H != 0) { set_error("d_model+16 = %d not divisible by nhead = %d", s->D, s->H); return -2; }
   s->hd = s->D / s->H;
-  s->Df = s->D + (s->ds > 0 ? s->N : 0);
+  s->Df = s->D + (s->ds > 0 ? s->emb : 0);
   s->M1 = (int64_t)s->B * s->N; s->M2 = (int64_t)s->T * s->B;
   s->p = (d->training && d->dropout_p > 0.f) ? d->dropout_p : 0.f;
   if (s->p >= 1.f) { set_error("dropout_p must be < 1"); return -2; }
@@ -238,9 +241,12 @@ static int obprop_forward(const ObpropTcArgs& a, cudaStream_t st) {
 
 static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* src, const float* statics,
                         const float* times, const int64_t* lengths, const float* nscale, uint64_t* rng_state,
-                        float* ws, float* logits, const int64_t* y, float* loss, float* d_logits, cudaStream_t st) {
+                        float* ws, float* logits, const int64_t* y, float* loss, float* d_logits, int encoder_only,
+                        cudaStream_t st) {
   Shape s;
   RD_TRY(make_shape(dims, &s));
+  if (!encoder_only && (s.dpe != RD_D_PE || s.emb != s.N)) { set_error("Raindrop_v2 has d_pe = 16 and emb_dim = d_inp"); return -2; }
+  if (encoder_only) { s.tc = 0; s.exact = 0; }      // no observation propagation on this entry: no lin_value copies
   if (s.ds > 0 && (!statics || !P->emb_weight || !P->emb_bias)) { set_error("static branch needs statics/emb"); return -2; }
   WsLayout w = ws_layout(s);
   uint64_t* rng = reinterpret_cast<uint64_t*>(ws + w.rng);
@@ -278,8 +284,10 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
     RD_TRY(split_weights(items, n, st, l0 == 0 ? &pro : nullptr));
   }
   float* Z0 = ws + w.Z[0];
+  if (!encoder_only) {
   // lift of the raw observations and the positional encoding (written into Z0[..., 4N:]) in one launch
-  RD_TRY(lift_posenc(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, tc && !exact, X0, times, s.M2, dims->pe_timescales, Z0, s.D, s.Dm, st));
+  RD_TRY(lift_posenc(src, P->R_u, s.B, s.T, s.N, s.dob, s.p, rng, tc && !exact, X0, times, s.M2, dims->pe_timescales, RD_D_PE, Z0,
+                     s.D, s.Dm, st));
   {
     ObpropTcArgs a;
     a.x = X0; a.W = W1; a.bias = P->ob1_value_bias; a.scale = nscale; a.scale_mod = s.N;
@@ -290,6 +298,7 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
     a.W_lo = exact ? ws + w.W2lo : nullptr;
     a.perm = 1; a.pB = s.B; a.pN = s.N; a.pdob = s.dob; a.pD = s.D;
     RD_TRY(obprop_forward(a, st));
+  }
   }
 
   const float scale = 1.f / sqrtf((float)s.hd);
@@ -353,7 +362,7 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
     RD_TRY(layernorm_fwd(r2, E.norm2_weight, E.norm2_bias, s.M2, s.D, dims->ln_eps, ws + w.Z[l + 1], ws + w.l[l].st2, st));
   }
   float* feat = ws + w.feat; float* hpre = ws + w.hpre;
-  RD_TRY(head_fwd(s.B, s.T, s.D, s.N, s.ds, s.ncls, ws + w.Z[s.L], lengths, statics, P->emb_weight, P->emb_bias,
+  RD_TRY(head_fwd(s.B, s.T, s.D, s.emb, s.ds, s.ncls, ws + w.Z[s.L], lengths, statics, P->emb_weight, P->emb_bias,
                   P->mlp0_weight, P->mlp0_bias, P->mlp2_weight, P->mlp2_bias, feat, hpre, logits, y, ws + w.loss_ps, d_logits,
                   loss, reinterpret_cast<unsigned*>(ws + w.cnt), st));
   return 0;
@@ -361,7 +370,7 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
 
 static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* statics, const int64_t* lengths,
                         const float* nscale, const float* ws, const float* dlogits, const rd_grads* G, float* sc,
-                        int phases, cudaStream_t st) {
+                        int phases, float* d_z0_out, cudaStream_t st) {
   Shape s;
   RD_TRY(make_shape(dims, &s));
   if ((phases & ~3) || phases == 0) { set_error("rd_raindrop_v2_bwd: phases must be 1, 2 or 3"); return -2; }
@@ -377,7 +386,7 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
   // ---- head: logits = mlp2(relu(mlp0(feat))), pooled = masked mean          code/models_rd.py:366-385
   const float* feat = ws + w.feat; const float* hpre = ws + w.hpre;
   float* dfeat = sc + b.dfeat; float* dhpre = sc + b.dhpre;
-  RD_TRY(head_bwd(s.B, s.T, s.D, s.N, s.ds, s.ncls, lengths, statics, P->mlp0_weight, P->mlp2_weight, feat, hpre, dlogits,
+  RD_TRY(head_bwd(s.B, s.T, s.D, s.emb, s.ds, s.ncls, lengths, statics, P->mlp0_weight, P->mlp2_weight, feat, hpre, dlogits,
                   dhpre, dfeat, gA, G->mlp0_weight, G->mlp0_bias, G->mlp2_weight, G->mlp2_bias, G->emb_weight, G->emb_bias, st));
 
   const float scale = 1.f / sqrtf((float)s.hd);
@@ -461,7 +470,8 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     }
     RD_TRY(tn(&wq, dqkv, 3 * s.D, x, s.D, GE.in_proj_weight, GE.in_proj_bias, 3 * s.D, s.D, s.M2, sc + b.l[l].wp[3], partial, st));
     {
-      GemmP g = nt(dqkv, 3 * s.D, ws + w.wsp[l].in_t, 3 * s.D, gA, s.D, s.M2, s.D, 3 * s.D);
+      // the first layer's input gradient is d(loss)/d(encoder input): optionally delivered straight to the caller
+      GemmP g = nt(dqkv, 3 * s.D, ws + w.wsp[l].in_t, 3 * s.D, (l == 0 && d_z0_out) ? d_z0_out : gA, s.D, s.M2, s.D, 3 * s.D);
       g.resid = res; g.resid_ld = s.D;
       RD_TRY(linear_nt(g, ws + w.wsp[l].in_tlo, st));
     }
@@ -673,7 +683,7 @@ int rd_raindrop_v2_fwd(const rd_dims* dims, const rd_params* params, const float
     return -2;
   }
   return raindrop_fwd(dims, params, src, statics, times, lengths, node_scale, rng_state, (float*)workspace, logits,
-                      y, loss, d_logits, (cudaStream_t)stream);
+                      y, loss, d_logits, 0, (cudaStream_t)stream);
 }
 
 int rd_raindrop_v2_bwd(const rd_dims* dims, const rd_params* params, const float* statics, const int64_t* lengths,
@@ -684,14 +694,39 @@ int rd_raindrop_v2_bwd(const rd_dims* dims, const rd_params* params, const float
     return -2;
   }
   return raindrop_bwd(dims, params, statics, lengths, node_scale, (const float*)workspace, d_logits, grads,
-                      (float*)scratch, phases, (cudaStream_t)stream);
+                      (float*)scratch, phases, nullptr, (cudaStream_t)stream);
 }
 
-int rd_positional_encoding(const float* times, int64_t n_tokens, const float* timescales_host, float* out,
+int rd_positional_encoding(const float* times, int64_t n_tokens, const float* timescales_host, int32_t d_pe, float* out,
                            int64_t ld, int32_t col0, void* stream) {
   if (!times || !timescales_host || !out || n_tokens < 0) { set_error("rd_positional_encoding: bad arguments"); return -2; }
   if (n_tokens == 0) return 0;
-  return posenc(times, n_tokens, timescales_host, out, ld, col0, (cudaStream_t)stream);
+  return posenc(times, n_tokens, timescales_host, d_pe, out, ld, col0, (cudaStream_t)stream);
+}
+
+int rd_encoder_head_fwd(const rd_dims* dims, const rd_params* params, const float* statics, const int64_t* lengths,
+                        uint64_t* rng_state, void* workspace, float* logits, const int64_t* y, float* loss, float* d_logits,
+                        void* stream) {
+  if (!dims || !params || !lengths || !workspace || !logits) { set_error("rd_encoder_head_fwd: NULL argument"); return -2; }
+  return raindrop_fwd(dims, params, nullptr, statics, nullptr, lengths, nullptr, rng_state, (float*)workspace, logits, y, loss,
+                      d_logits, 1, (cudaStream_t)stream);
+}
+
+int rd_encoder_head_bwd(const rd_dims* dims, const rd_params* params, const float* statics, const int64_t* lengths,
+                        const void* workspace, const float* d_logits, const rd_grads* grads, void* scratch, float* d_enc_in,
+                        void* stream) {
+  if (!dims || !params || !lengths || !workspace || !d_logits || !grads || !scratch || !d_enc_in) {
+    set_error("rd_encoder_head_bwd: NULL argument");
+    return -2;
+  }
+  return raindrop_bwd(dims, params, statics, lengths, nullptr, (const float*)workspace, d_logits, grads, (float*)scratch,
+                      RD_BWD_ENCODER, d_enc_in, (cudaStream_t)stream);
+}
+
+int rd_dropout(const float* x, int64_t n, float p, const uint64_t* rng_captured, uint32_t site, float* y, void* stream) {
+  if (!x || !y || !rng_captured || n < 0 || p < 0.f || p >= 1.f) { set_error("rd_dropout: bad arguments"); return -2; }
+  if (n == 0) return 0;
+  return apply_dropout(x, n, p, rng_captured, site, y, (cudaStream_t)stream);
 }
 
 int rd_gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_total, int32_t width, int32_t B, float* out,

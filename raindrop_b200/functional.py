@@ -57,12 +57,16 @@ def pe_timescales(max_len, d_pe=16):
 class Plan:
     """Everything about one model instance that the kernels need besides the tensors."""
 
-    def __init__(self, d_inp, d_ob, nhead, nhid, nlayers, d_static, n_classes, max_len, dropout, static):
+    def __init__(self, d_inp, d_ob, nhead, nhid, nlayers, d_static, n_classes, max_len, dropout, static, d_pe=16, emb_dim=0,
+                 obprop=True):
         self.N, self.d_ob, self.nhead, self.nhid, self.nlayers = d_inp, d_ob, nhead, nhid, nlayers
+        self.d_pe, self.emb_dim = d_pe, emb_dim
         self.d_static = d_static if static else 0
         self.n_classes, self.T, self.dropout = n_classes, max_len, float(dropout)
         self.static = static
         self.fields = used_param_fields(nlayers, static)
+        if not obprop:          # legacy v1: no observation-propagation layers
+            self.fields = self.fields[:-N_OBPROP_FIELDS]
         self.timescales = pe_timescales(max_len)
         self.node_scale = None      # [N] device tensor (rd_node_scale)
         self.R_u = None             # [1, N*d_ob] device tensor
@@ -91,6 +95,8 @@ class Plan:
         d.dropout_p = self.dropout
         d.ln_eps = 1e-5
         d.obprop_mode = int(self.obprop_mode)
+        d.d_pe = 0 if self.d_pe == 16 else int(self.d_pe)
+        d.emb_dim = int(self.emb_dim)
         for i, v in enumerate(self.timescales):
             d.pe_timescales[i] = float(v)
         return d
@@ -438,13 +444,12 @@ def node_scale(edge_index, edge_weights, n_nodes):
 
 
 def positional_encoding(times, max_len, d_pe=16):
-    """[T, B] -> [T, B, 16] on the device (rd_positional_encoding)."""
-    assert d_pe == 16
+    """[T, B] -> [T, B, d_pe] on the device (rd_positional_encoding); d_pe even, <= 64."""
     lib = L.load()
     t = _as_f32(times)
     out = torch.empty(t.shape + (d_pe,), dtype=torch.float32, device=t.device)
-    ts = (C.c_float * 8)(*[float(v) for v in pe_timescales(max_len, d_pe)])
-    L.check(lib.rd_positional_encoding(t.data_ptr(), t.numel(), ts, out.data_ptr(), d_pe, 0, L.stream_ptr()),
+    ts = (C.c_float * (d_pe // 2))(*[float(v) for v in pe_timescales(max_len, d_pe)])
+    L.check(lib.rd_positional_encoding(t.data_ptr(), t.numel(), ts, d_pe, out.data_ptr(), d_pe, 0, L.stream_ptr(t.device)),
             "rd_positional_encoding")
     return out
 
@@ -527,6 +532,111 @@ def transformer_conv(x, edge_index, edge_weights, heads, out_channels, wq, bq, w
         geom = (x.shape[0], 1, 1, 0)
     out, alpha = TransformerConvFunction.apply(x, edge_index, edge_weights, geom, heads, out_channels, wq, bq, wk, bk, wv, bv, ws, bs)
     return out, (alpha[0] if single else alpha)
+
+
+class LinearFunction(torch.autograd.Function):
+    """y = x W^T + b on the error-compensated tensor-core GEMM (rd_linear_fwd); backward: dX through the same kernel
+    against W^T, dW / db through the grouped weight-gradient kernel (rd_linear_wgrad_group)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return linear(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x, weight = ctx.saved_tensors
+        dy = _as_f32(dy)
+        dx = linear(dy, weight.t().contiguous()) if ctx.needs_input_grad[0] else None
+        rows, out_f = dy.shape
+        in_f = x.shape[1]
+        dW = torch.empty_like(weight)
+        db = torch.empty(out_f, dtype=torch.float32, device=dy.device)
+        part = torch.empty(max(1, lib.rd_linear_wgrad_partial_bytes(rows, out_f, in_f) // 4), dtype=torch.float32, device=dy.device)
+        it = (L.RdWgradItem * 1)()
+        it[0].d_out, it[0].x, it[0].rows, it[0].out_features, it[0].in_features = dy.data_ptr(), _as_f32(x).data_ptr(), rows, out_f, in_f
+        it[0].d_weight, it[0].d_bias, it[0].partial = dW.data_ptr(), db.data_ptr(), part.data_ptr()
+        L.check(lib.rd_linear_wgrad_group(it, 1, L.stream_ptr(dy.device)), "rd_linear_wgrad_group")
+        return dx, dW, (db if ctx.has_bias else None)
+
+
+class DropoutFunction(torch.autograd.Function):
+    """nn.Dropout on the library's counter-based stream (rd_dropout); the backward re-applies the same mask."""
+
+    @staticmethod
+    def forward(ctx, x, p, rng, site):
+        lib = L.load()
+        x = _as_f32(x)
+        y = torch.empty_like(x)
+        L.check(lib.rd_dropout(x.data_ptr(), x.numel(), p, rng.data_ptr(), site, y.data_ptr(), L.stream_ptr(x.device)), "rd_dropout")
+        ctx.p, ctx.site = p, site
+        ctx.save_for_backward(rng)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        (rng,) = ctx.saved_tensors
+        dy = _as_f32(dy)
+        dx = torch.empty_like(dy)
+        L.check(lib.rd_dropout(dy.data_ptr(), dy.numel(), ctx.p, rng.data_ptr(), ctx.site, dx.data_ptr(), L.stream_ptr(dy.device)),
+                "rd_dropout")
+        return dx, None, None, None
+
+
+class EncoderHeadFunction(torch.autograd.Function):
+    """Temporal encoder + masked-mean pooling + mlp_static on a given encoder input z0 [T, B, D] (rd_encoder_head_fwd /
+    _bwd): the part of the model that legacy Raindrop v1 shares with Raindrop_v2 (code/models_rd.py:168-191)."""
+
+    @staticmethod
+    def forward(ctx, plan, training, z0, static, lengths, *params):
+        lib = L.load()
+        z0 = _as_f32(z0)
+        T, B, D = z0.shape
+        dims = plan.dims(B, training)
+        keep = [_as_f32(t) for t in params]
+        P = L.RdParams()
+        for (key, path), t in zip(plan.fields, keep):
+            _set_field(P, path, t.data_ptr())
+        ws = torch.empty(lib.rd_workspace_bytes(C.byref(dims)) // 4, dtype=torch.float32, device=z0.device)
+        n = C.c_int64(0)
+        off = lib.rd_workspace_offset(C.byref(dims), L.WS_ENC_IN, C.byref(n))
+        if off < 0 or n.value != z0.numel():
+            raise L.RaindropB200Error("encoder input must be [T=%d, B, D=%d], got %s" % (plan.T, n.value // max(1, T * B), tuple(z0.shape)))
+        ws[off // 4: off // 4 + n.value].copy_(z0.reshape(-1))
+        logits = torch.empty(B, plan.n_classes, dtype=torch.float32, device=z0.device)
+        rc = lib.rd_encoder_head_fwd(C.byref(dims), C.byref(P), L.ptr(static), lengths.data_ptr(), L.ptr(plan.rng_state),
+                                     ws.data_ptr(), logits.data_ptr(), None, None, None, L.stream_ptr(z0.device))
+        L.check(rc, "rd_encoder_head_fwd")
+        ctx.plan, ctx.dims, ctx.P, ctx.ws, ctx.keep = plan, dims, P, ws, (keep, static, lengths)
+        ctx.shape = (T, B, D)
+        return logits
+
+    @staticmethod
+    def backward(ctx, d_logits):
+        lib = L.load()
+        plan, dims = ctx.plan, ctx.dims
+        keep, static, lengths = ctx.keep
+        d_logits = _as_f32(d_logits)
+        dev = d_logits.device
+        offs, total = [], 0
+        for t in keep:
+            offs.append(total)
+            total += t.numel()
+        flat = torch.empty(total, dtype=torch.float32, device=dev)
+        G = L.RdGrads()
+        for (key, path), off in zip(plan.fields, offs):
+            _set_field(G, path, flat.data_ptr() + 4 * off)
+        sc = torch.empty(lib.rd_backward_scratch_bytes(C.byref(dims)) // 4, dtype=torch.float32, device=dev)
+        dz = torch.empty(ctx.shape, dtype=torch.float32, device=dev)
+        rc = lib.rd_encoder_head_bwd(C.byref(dims), C.byref(ctx.P), L.ptr(static), lengths.data_ptr(), ctx.ws.data_ptr(),
+                                     d_logits.data_ptr(), C.byref(G), sc.data_ptr(), dz.data_ptr(), L.stream_ptr(dev))
+        L.check(rc, "rd_encoder_head_bwd")
+        grads = torch._utils._unflatten_dense_tensors(flat, keep)
+        ctx.ws = None
+        return (None, None, dz, None, None) + tuple(grads)
 
 
 def workspace_view(plan, which):

@@ -28,7 +28,8 @@ class RdDims(C.Structure):
                 ("nhead", C.c_int32), ("nhid", C.c_int32), ("nlayers", C.c_int32),
                 ("d_static", C.c_int32), ("n_classes", C.c_int32), ("training", C.c_int32),
                 ("dropout_p", C.c_float), ("ln_eps", C.c_float),
-                ("pe_timescales", C.c_float * (RD_D_PE // 2)), ("obprop_mode", C.c_int32)]
+                ("pe_timescales", C.c_float * (RD_D_PE // 2)), ("d_pe", C.c_int32), ("emb_dim", C.c_int32),
+                ("obprop_mode", C.c_int32)]
 
 
 _LAYER_FIELDS = ["in_proj_weight", "in_proj_bias", "out_proj_weight", "out_proj_bias",
@@ -90,8 +91,12 @@ SIGNATURES = {
     "rd_raindrop_v2_bwd": (C.c_int, [C.POINTER(RdDims), C.POINTER(RdParams), C.c_void_p, C.c_void_p,
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(RdGrads), C.c_void_p,
                                      C.c_int32, C.c_void_p]),
-    "rd_positional_encoding": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_void_p,
+    "rd_positional_encoding": (C.c_int, [C.c_void_p, C.c_int64, C.POINTER(C.c_float), C.c_int32, C.c_void_p,
                                          C.c_int64, C.c_int32, C.c_void_p]),
+    "rd_encoder_head_fwd": (C.c_int, [C.POINTER(RdDims), C.POINTER(RdParams)] + [C.c_void_p] * 9),
+    "rd_encoder_head_bwd": (C.c_int, [C.POINTER(RdDims), C.POINTER(RdParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                      C.POINTER(RdGrads), C.c_void_p, C.c_void_p, C.c_void_p]),
+    "rd_dropout": (C.c_int, [C.c_void_p, C.c_int64, C.c_float, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "rd_linear_scratch_bytes": (C.c_size_t, [C.c_int32, C.c_int32]),
     "rd_linear_fwd": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                                 C.c_void_p, C.c_void_p, C.c_void_p]),

@@ -153,6 +153,17 @@ class TransformerConv(nn.Module):
             return out, (edge_index, alpha)
         return out
 
+    def forward_batched(self, x, edge_index, edge_weights=None):
+        """x [n_nodes, n_graphs, in]: the layer applied to every graph x[:, g, :] (same edge list) in ONE call -- the
+        per-sample loop of legacy Raindrop v1 (code/models_rd.py:158-166).  Returns (out [n_nodes, n_graphs, H*F],
+        alpha [n_graphs, E, H])."""
+        n_nodes, n_graphs, in_ch = x.shape
+        out, alpha = RF.transformer_conv(x.reshape(n_nodes * n_graphs, in_ch), edge_index, edge_weights, self.heads,
+                                         self.out_channels, self.lin_query.weight, self.lin_query.bias, self.lin_key.weight,
+                                         self.lin_key.bias, self.lin_value.weight, self.lin_value.bias, self.lin_skip.weight,
+                                         self.lin_skip.bias, geom=(n_nodes, n_graphs, n_graphs, 1))
+        return out.view(n_nodes, n_graphs, -1), alpha
+
     def __repr__(self):
         return "{}({}, {}, heads={})".format(self.__class__.__name__, self.in_channels, self.out_channels, self.heads)
 
@@ -284,14 +295,25 @@ class Raindrop_v2(nn.Module):
 
 
 class Raindrop(nn.Module):
-    """Legacy v1 model (code/models_rd.py:46-191): hard-coded to 36 sensors / 215 steps and never
-    constructed by code/Raindrop.py.  Kept for API surface and state-dict compatibility; its forward
-    (per-sample TransformerConv) is outside the hot path this package accelerates."""
+    """Legacy v1 model (code/models_rd.py:46-191), hard-coded to 36 sensors like the reference.  Same constructor, same
+    state-dict keys, `forward(src, static, times, lengths) -> (logits, distance, None)`.
+
+    What the reference computes, and where it runs here:
+      src = encoder(values) * sqrt(d_model); dropout                      (:131-135)  rd_linear_fwd, rd_dropout
+      per sample: TransformerConv over the T timestamps as nodes with the 36 x 36 sensor graph's edges (so only the
+      first 36 timestamps exchange messages) and the supplied edge weights (:148-166)
+                                                                          rd_transformer_conv_fwd/_bwd, all samples in one call
+      cat positional encoding (d_pe = 36), nn.TransformerEncoder, masked mean / (lengths + 1), cat emb(static),
+      mlp_static (:168-189)                                               rd_encoder_head_fwd/_bwd (the Raindrop_v2 kernels)
+    `distance` = mean pairwise distance of the per-sample attention vectors (:165-166): the edge weights are shared by
+    all samples, so it is 0 -- evaluated from the returned alphas, not assumed."""
 
     def __init__(self, d_inp=36, d_model=64, nhead=4, nhid=128, nlayers=2, dropout=0.3, max_len=215, d_static=9,
                  MAX=100, perc=0.5, aggreg='mean', n_classes=2, global_structure=None):
         super().__init__()
         from torch.nn import TransformerEncoder, TransformerEncoderLayer
+        if aggreg != 'mean':
+            raise NotImplementedError("aggreg must be 'mean' (the only branch of code/models_rd.py:182)")
         self.model_type = 'Transformer'
         self.global_structure = global_structure
         d_pe, d_enc = 36, 36
@@ -303,7 +325,7 @@ class Raindrop(nn.Module):
         self.transconv = TransformerConv(in_channels=36, out_channels=36 * self.dim, heads=1)
         d_final = 36 * (self.dim + 1) + d_model
         self.mlp_static = nn.Sequential(nn.Linear(d_final, d_final), nn.ReLU(), nn.Linear(d_final, n_classes))
-        self.d_inp, self.d_model = d_inp, d_model
+        self.d_inp, self.d_model, self.max_len, self.n_classes = d_inp, d_model, max_len, n_classes
         self.encoder = nn.Linear(d_inp, d_enc)
         self.emb = nn.Linear(d_static, d_model)
         self.MLP_replace_transformer = nn.Linear(72, 36)
@@ -313,7 +335,45 @@ class Raindrop(nn.Module):
         self.dropout = nn.Dropout(dropout)
         self.encoder.weight.data.uniform_(-1e-10, 1e-10)
         self.emb.weight.data.uniform_(-1e-10, 1e-10)
+        if d_inp != 36 or 36 * self.dim != d_model:
+            raise ValueError("Raindrop v1 is hard-coded to 36 sensors and d_model = 36 * k (code/models_rd.py:68-88)")
+        # the shared encoder/head kernels see "36 sensors x dim channels" + a 36-wide positional encoding
+        self._plan = RF.Plan(36, self.dim, nhead, nhid, nlayers, d_static, n_classes, max_len, dropout, True, d_pe=36,
+                             emb_dim=d_model, obprop=False)
+        self._seed = int(torch.initial_seed()) & 0x7FFFFFFFFFFFFFFF
+        self._drop_p = float(dropout)
+
+    def used_parameters(self):
+        sd = dict(self.named_parameters())
+        return [sd[k] for k, _ in self._plan.fields]
 
     def forward(self, src, static, times, lengths):
-        raise NotImplementedError("Raindrop v1 is legacy in the reference (not constructed by code/Raindrop.py); "
-                                  "use Raindrop_v2")
+        device = _device_of(src)
+        plan = self._plan
+        if plan.rng_state is None or plan.rng_state.device != device:
+            plan.rng_state = torch.tensor([self._seed, 0], dtype=torch.int64, device=device)
+        src = src.to(device=device, dtype=torch.float32)
+        times = times.to(device=device, dtype=torch.float32).contiguous()
+        lengths = lengths.to(device=device, dtype=torch.int64).contiguous()
+        static = static.to(device=device, dtype=torch.float32).contiguous()
+        T, B = src.shape[0], src.shape[1]
+        if T != self.max_len or src.shape[2] != 2 * self.d_inp:
+            raise ValueError("src must be [max_len=%d, B, 72], got %s" % (self.max_len, tuple(src.shape)))
+        values = src[:, :, :self.d_inp].reshape(T * B, self.d_inp)                                  # :128-129
+        x = RF.LinearFunction.apply(values, self.encoder.weight, self.encoder.bias) * math.sqrt(self.d_model)   # :131
+        if self.training and self._drop_p > 0:                                                        # :134
+            x = RF.DropoutFunction.apply(x, self._drop_p, plan.rng_state.clone(), 2)
+        gs = self.global_structure
+        if gs is None:
+            raise ValueError("Raindrop v1 needs global_structure (code/models_rd.py:148)")
+        adj = gs.detach().to(device=device, dtype=torch.float32).clone()
+        adj[torch.arange(36, device=device), torch.arange(36, device=device)] = 1                   # :149
+        edge_index = torch.nonzero(adj).T.contiguous()
+        edge_weights = adj[edge_index[0], edge_index[1]].contiguous()
+        out, alpha = self.transconv.forward_batched(x.view(T, B, self.d_inp), edge_index, edge_weights)   # :155-166
+        alpha_all = alpha[:, :, 0]                                                                    # [B, E]
+        distance = torch.mean(torch.cdist(alpha_all, alpha_all, p=2, compute_mode='donot_use_mm_for_euclid_dist'))   # :165-166
+        pe = self.pos_encoder(times)                                                                   # [T, B, 36]
+        z0 = torch.cat([out, pe], dim=-1)                                                              # :168
+        logits = RF.EncoderHeadFunction.apply(plan, self.training, z0, static, lengths, *self.used_parameters())
+        return logits, distance, None

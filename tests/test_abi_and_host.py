@@ -34,7 +34,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layout_matches_header_sizes():
     import ctypes as C
-    assert C.sizeof(L.RdDims) == 4 * 10 + 4 * 2 + 4 * 8 + 4
+    assert C.sizeof(L.RdDims) == 4 * 10 + 4 * 2 + 4 * 8 + 4 * 3
     assert C.sizeof(L.RdParams) == 8 * 11 + 8 * 12 * L.RD_MAX_LAYERS
     assert C.sizeof(L.RdGrads) == 8 * 10 + 8 * 12 * L.RD_MAX_LAYERS
 

@@ -504,6 +504,37 @@ def test_graph_operator_gradients(golden_dir):
         assert normwise(a_, p.grad) < 1e-5
 
 
+def test_legacy_raindrop_v1_against_reference(golden_dir):
+    """Legacy `Raindrop` v1 (code/models_rd.py:46-191): logits / loss / distance and all 36 gradients vs the fixture
+    produced by the reference's own class (oracle/make_golden.py v1_case)."""
+    from raindrop_b200.models_rd import Raindrop
+    from raindrop_b200.synth import CONFIGS
+    z = np.load(golden_dir + "/v1_p12_b3.npz")
+    cfg = dict(CONFIGS["P12"]); cfg["name"] = "P12"
+    batch = make_batch(dict(cfg, d_ob=2), 3, seed=77)
+    model = Raindrop(36, 72, 2, 144, 2, 0.2, 215, 9, 100, 0.5, "mean", 2, torch.from_numpy(z["global_structure"]))
+    assert sorted(model.state_dict()) == sorted(k[3:] for k in z.files if k.startswith("sd."))
+    model.load_state_dict({k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")})
+    model = model.cuda().eval()
+    d = to_dev(batch)
+    logits, distance, third = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+    assert third is None and float(distance) == float(z["distance"]) == 0.0
+    assert normwise(logits, z["logits"]) < 1e-4, normwise(logits, z["logits"])
+    loss = F.cross_entropy(logits, d["y"])
+    assert abs(loss.item() - float(z["loss"])) < 1e-4
+    loss.backward()
+    params = dict(model.named_parameters())
+    with_grad = sorted(k[5:] for k in z.files if k.startswith("grad."))
+    assert sorted(k for k, p in params.items() if p.grad is not None and float(p.grad.abs().max()) > 0) == with_grad
+    worst = max((normwise(params[k].grad, z["grad." + k]), k) for k in with_grad)
+    print("v1 worst gradient error", worst)
+    assert worst[0] < 2e-3, worst
+    # train mode runs (dropout on the library's stream) and is reproducible for a fixed (seed, counter)
+    model.train()
+    a, _, _ = model.forward(d["src"], d["static"], d["times"], d["lengths"])
+    assert torch.isfinite(a).all() and not torch.equal(a, logits)
+
+
 def test_device_dataset_gather_is_bit_exact():
     """rd_gather_batch == torch indexing of the host tensors (index work: bit exact), incl. odd widths."""
     from raindrop_b200.train import DeviceDataset, TrainStep
