@@ -340,6 +340,12 @@ int rd_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg
                  float lr, const float* lr_dev, float beta1, float beta2, float eps, float grad_scale,
                  int64_t* step, void* stream);
 
+/* debug: when `buffer` is non-NULL ([n_ctas][16] uint64 on the device), the tensor-core attention forward kernel writes
+ * %globaltimer phase stamps into it (tools/attn_timing.py); NULL switches it off. */
+int rd_debug_attention_timing(uint64_t* buffer);
+/* same for the projection GEMM kernel behind rd_linear_fwd: [n_ctas][8] uint64 */
+int rd_debug_gemm_timing(uint64_t* buffer);
+
 /* debug: materialise the dropout keep/scale mask (0 or 1/(1-p)) of one dropout site, so tests can
  * replay train-mode forward/backward in the oracle with identical masks.  `site` ids in DESIGN.md. */
 int rd_debug_dropout_mask(const uint64_t* rng_captured, uint32_t site, int64_t n, float p, float* out,

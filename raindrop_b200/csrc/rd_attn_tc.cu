@@ -49,7 +49,16 @@ struct AttnTcP {
   int B, H, T, hd, D;
   float scale, drop_p;
   const uint64_t* rng; uint32_t site;
+  unsigned long long* dbg;      // optional phase timestamps (rd_debug_attention_timing): [CTA][16] of %globaltimer
 };
+
+__device__ __forceinline__ void stamp(const AttnTcP& p, int slot) {
+  if (p.dbg && threadIdx.x == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.dbg[(size_t)blockIdx.x * 16 + slot] = t;
+  }
+}
 
 __device__ __forceinline__ float lo_of(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
@@ -185,6 +194,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   pdl_wait();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tO = tmem + 64;
+  stamp(p, 0);
 
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_qk, 2u * TILE);
@@ -195,16 +205,21 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
     }
   }
   precompute_keep_bits(p, b, h, keep);
+  stamp(p, 1);
   mbar_wait(bar_qk, 0);
+  stamp(p, 2);
   lo_pass(QV, TILE, TILE);
   lo_pass(KP, TILE, TILE);
   fence_async_smem();
   __syncthreads();
+  stamp(p, 3);
   if (threadIdx.x == 0) {
     tc_fence_after();
     mma3<false, false>(tS, QV, TILE, KP, TILE, 4 * NG, umma_idesc_tf32(128, 64, false, false));
     umma_commit(bar_s);
+    stamp(p, 4);
     mbar_wait(bar_s, 0);                       // Q is dead: its region receives V
+    stamp(p, 5);
     mbar_expect_tx(bar_v, (uint32_t)TILE);
 #pragma unroll
     for (int g = 0; g < NG; ++g) tma_load_5d(&tmQKVm, bar_v, QV + g * GRP, 32 * g, h, 2, b, 0);     // MN image
@@ -227,21 +242,26 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
       store_chunk_hi_lo(KP, i, c, s[4 * c] * m.x, s[4 * c + 1] * m.y, s[4 * c + 2] * m.z, s[4 * c + 3] * m.w);
     }
     fence_async_smem();
+    stamp(p, 6);
   }
   mbar_wait(bar_v, 0);
+  stamp(p, 7);
   lo_pass(QV, TILE, TILE);
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
+  stamp(p, 8);
   if (threadIdx.x == 0) {
     tc_fence_after();
     mma3<false, true>(tO, KP, PT, QV, TILE, 8, umma_idesc_tf32(128, 96, false, true));
     umma_commit(bar_o);
+    stamp(p, 9);
   }
   if (warp < 2) {
     const int i = threadIdx.x;
     mbar_wait(bar_o, 0);
     __syncwarp();
+    stamp(p, 10);
     tc_fence_after();
     float* dst = p.ctx + ((long long)i * p.B + b) * p.D + h * p.hd;
 #pragma unroll
@@ -257,12 +277,14 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
       }
     }
   }
+  stamp(p, 11);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
   }
+  stamp(p, 12);
 }
 
 // =================================================================================================
@@ -475,6 +497,9 @@ int encode_ctx(CUtensorMap* m, const float* x, int B, int H, int T, int hd, CUte
 
 }  // namespace
 
+static unsigned long long* g_attn_dbg = nullptr;
+void attn_tc_set_debug(unsigned long long* buf) { g_attn_dbg = buf; }
+
 bool attn_tc_supported(int T, int hd) {
   static int env = -1;
   if (env < 0) { const char* e = getenv("RD_ATTN_TC"); env = (e && e[0] == '0') ? 0 : 1; }
@@ -489,7 +514,7 @@ int attn_tc_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T, i
   }
   AttnTcP p{};
   p.ctx = ctx; p.lengths = lengths; p.B = B; p.H = H; p.T = T; p.hd = hd; p.D = H * hd;
-  p.scale = 1.f / sqrtf((float)hd); p.drop_p = drop_p; p.rng = rng; p.site = site;
+  p.scale = 1.f / sqrtf((float)hd); p.drop_p = drop_p; p.rng = rng; p.site = site; p.dbg = g_attn_dbg;
   CUtensorMap tm, tmm;
   RD_TRY(encode_qkv(&tm, qkv, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B));
   RD_TRY(encode_qkv(&tmm, qkv, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));

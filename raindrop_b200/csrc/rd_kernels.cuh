@@ -78,6 +78,7 @@ int attn_small_bwd(const float* qkv, const float* dctx, const int64_t* lengths, 
 
 // the same on the tensor cores (rd_attn_tc.cu: tcgen05 3xTF32, TMA-staged head slices, T <= 64, hd <= 96, hd % 4 == 0)
 bool attn_tc_supported(int T, int hd);
+void attn_tc_set_debug(unsigned long long* buf);   // phase timestamps of the forward kernel: [CTA][16] (debug)
 int attn_tc_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T, int hd, float drop_p,
                 const uint64_t* rng, uint32_t site, float* ctx, cudaStream_t st);
 int attn_tc_bwd(const float* qkv, const float* dctx, const int64_t* lengths, int B, int H, int T, int hd,

@@ -33,7 +33,16 @@ struct P {
   const float* gate; long long gate_ld; float gate_scale;
   float drop_p; const uint64_t* rng; uint32_t drop_site;
   const float* resid; long long resid_ld;
+  unsigned long long* dbg;     // optional %globaltimer phase stamps [CTA][8] (rd_debug_gemm_timing)
 };
+
+__device__ __forceinline__ void gstamp(const P& p, int slot) {
+  if (p.dbg) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    p.dbg[(size_t)blockIdx.x * 8 + slot] = t;
+  }
+}
 
 // epilogue features are compile-time: the epilogue is on the critical path of these small GEMMs
 template <bool RELU, bool GATE, bool DROP, bool RESID>
@@ -42,6 +51,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
                const __grid_constant__ CUtensorMap tmC, const P p) {
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
+  if (threadIdx.x == 0) gstamp(p, 0);
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_tile = (uint32_t)p.BN * 128u;
@@ -76,6 +86,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   __syncthreads();
   tc_fence_after();
   pdl_wait();          // everything above is private to this CTA; the previous kernel's output is first touched below
+  if (threadIdx.x == 0) gstamp(p, 1);
   const uint32_t tmem_base = *tmem_slot_ptr;
   const int total_tiles = p.m_tiles * p.n_tiles;
 
@@ -106,6 +117,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(full_bar(stage), phase);
+          if (kb == 0) gstamp(p, 2);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
           const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE);
@@ -121,6 +133,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
+        gstamp(p, 3);
         acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
     }
@@ -154,6 +167,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       };
       if (GATE || RESID) prefetch(0);
       mbar_wait(tfull_bar(acc), acc_phase);
+      if (threadIdx.x == 64) gstamp(p, 4);
       tc_fence_after();
       for (int ch = 0; ch < n_chunks; ++ch) {
         uint32_t v[32];
@@ -206,7 +220,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
       if (lane == 0) mbar_arrive(tempty_bar(acc));
       acc ^= 1; if (acc == 0) acc_phase ^= 1u;
     }
+    if (threadIdx.x == 64) gstamp(p, 5);
     if (lane == 0) bulk_wait_read<0>();
+    if (threadIdx.x == 64) gstamp(p, 6);
   } else {
     // ===== A loaders: global -> registers -> hi/lo split -> swizzled smem ================================
     const int lt = threadIdx.x - 192;           // 0..127
@@ -267,6 +283,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    if (lane == 0) gstamp(p, 7);
   }
 }
 
@@ -544,6 +561,9 @@ int ensure_attr(const void* fn, int) { return ensure_max_smem(fn, SMEM_LIMIT); }
 
 }  // namespace
 
+static unsigned long long* g_gemm_dbg = nullptr;
+void tc_gemm_set_debug(unsigned long long* buf) { g_gemm_dbg = buf; }
+
 bool tc_gemm_supported(const TcGemmArgs& a) {
   static int env = -1;
   if (env < 0) { const char* e = getenv("RD_TC_GEMM"); env = (e && e[0] == '0') ? 0 : 1; }
@@ -572,6 +592,7 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
   const int smem_bytes = fixed + p.nstages * stage_bytes;
   p.bias = a.bias; p.relu = a.relu; p.gate = a.gate; p.gate_ld = a.gate_ld; p.gate_scale = a.gate_scale;
   p.drop_p = a.drop_p; p.rng = a.rng; p.drop_site = a.drop_site; p.resid = a.resid; p.resid_ld = a.resid_ld;
+  p.dbg = g_gemm_dbg;
 
   CUtensorMap tmB, tmBlo, tmC;
   cuuint64_t bd[2] = {(cuuint64_t)a.K, (cuuint64_t)a.N};

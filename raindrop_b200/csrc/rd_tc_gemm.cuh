@@ -20,6 +20,7 @@ struct TcGemmArgs {
   const float* resid = nullptr; long long resid_ld = 0;
 };
 bool tc_gemm_supported(const TcGemmArgs& a);
+void tc_gemm_set_debug(unsigned long long* buf);     // %globaltimer phase stamps [CTA][8] (debug)
 int tc_gemm(const TcGemmArgs& a, cudaStream_t st);
 
 // Weight gradient on the tensor cores: dW[Nout, Kin] = sum_r dY[r, Nout]^T X[r, Kin], db[Nout] = sum_r dY[r, :]
