@@ -485,6 +485,8 @@ def test_graph_operator_gradients(golden_dir):
     eib = torch.stack([src_e, tgt_e]); wb = torch.rand(6, generator=torch.Generator().manual_seed(2)).cuda()
     P = [conv.lin_query.weight, conv.lin_query.bias, conv.lin_key.weight, conv.lin_key.bias, conv.lin_value.weight,
          conv.lin_value.bias, conv.lin_skip.weight, conv.lin_skip.bias]
+    for p in P:
+        p.grad = None         # (they still hold the gradients of the fixture check above)
     ob, _ = RF.transformer_conv(xb.reshape(Tn * Bn, 7), eib, None, 2, 5, *P, geom=(Tn, Bn, Bn, 1))
     Gb = torch.randn(Tn * Bn, 10, generator=torch.Generator().manual_seed(3)).cuda()
     (ob * Gb).sum().backward()
