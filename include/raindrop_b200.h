@@ -304,7 +304,7 @@ int rd_gather_batch(const float* src, const int64_t* idx, int64_t T, int64_t n_t
 
 /* Whole-batch assembly in ONE launch: for j < B copies sample idx[j] of the resident tensors P [T, n_total, width],
  * Ptime [T, n_total], Pstatic [n_total, d_static] (may be NULL), y [n_total] (may be NULL) into the batch buffers and
- * writes lengths[j] = #(Ptime[:, idx[j]] > 0)  (code/Raindrop.py:311-317).  width % 4 == 0. */
+ * writes lengths[j] = #(Ptime[:, idx[j]] > 0)  (code/Raindrop.py:311-317). */
 int rd_assemble_batch(const float* P, const float* Ptime, const float* Pstatic, const int64_t* y, const int64_t* idx,
                       int32_t T, int64_t n_total, int32_t width, int32_t d_static, int32_t B, float* src, float* times,
                       float* statics, int64_t* y_out, int64_t* lengths, void* stream);

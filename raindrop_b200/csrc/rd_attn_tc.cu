@@ -224,6 +224,10 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
 #pragma unroll
     for (int g = 0; g < NG; ++g) tma_load_5d(&tmQKVm, bar_v, QV + g * GRP, 32 * g, h, 2, b, 0);     // MN image
   }
+  // Lanes 1..31 of warp 0 must not run ahead of lane 0: divergent paths of one warp execute one at a time, so sibling
+  // lanes spinning on an mbarrier (or starting their softmax) would time-slice with the MMA issue loop -- measured 3.3 us
+  // for 36 MMAs -- and lane 0 would then redo the softmax alone.  Park them at a warp barrier instead.
+  __syncwarp();
   if (warp < 2) {      // rows 0..63: masked softmax + dropout; P (hi, lo) replaces K in shared memory
     const int i = threadIdx.x;
     const long long len = p.lengths[b];
@@ -257,6 +261,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
     umma_commit(bar_o);
     stamp(p, 9);
   }
+  __syncwarp();
   if (warp < 2) {
     const int i = threadIdx.x;
     mbar_wait(bar_o, 0);
@@ -356,6 +361,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
     mma3<false, false>(tS, R0, TILE, R1, TILE, 4 * NG, umma_idesc_tf32(128, 64, false, false));
     umma_commit(bar_s);
   }
+  __syncwarp();        // (see the forward kernel: sibling lanes must not spin while lane 0 issues MMAs)
   mbar_wait(bar_gv, 0);
   lo_pass(R2, TILE, TILE);
   lo_pass(R3, TILE, TILE);
@@ -375,6 +381,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
       tma_load_5d(&tmQKVm, bar_m1, R3 + g * GRP, 32 * g, h, 1, b, 0);
     }
   }
+  __syncwarp();
   // ---- phase 2: softmax / dS math on rows 0..63, Pd and dS images into R0 / R1 ----------------------
   if (warp < 2) {
     const int i = threadIdx.x;
@@ -428,6 +435,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
 #pragma unroll
     for (int g = 0; g < NG; ++g) tma_load_5d(&tmQKVm, bar_m2, R2 + g * GRP, 32 * g, h, 0, b, 0);
   }
+  __syncwarp();
   auto store_out = [&](uint32_t t0, int which) {     // accumulator rows 0..63 -> d_qkv[t, b, which*D + h*hd + d]
     const int i = threadIdx.x;
     float* dst = p.dqkv + ((long long)i * p.B + b) * 3 * p.D + h * p.hd + which * p.D;
@@ -462,6 +470,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
     mma3<true, true>(tDK, dSm, dSm_lo - dSm, R2, TILE, 8, umma_idesc_tf32(128, 96, true, true));
     umma_commit(bar_out);
   }
+  __syncwarp();
   if (warp < 2) {
     mbar_wait(bar_out, 0);
     __syncwarp();

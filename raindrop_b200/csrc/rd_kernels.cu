@@ -175,11 +175,18 @@ __global__ void __launch_bounds__(256) assemble_batch_kernel(const float* __rest
   const int j = blockIdx.x;
   const long long sidx = idx[j];
   if (sidx < 0 || sidx >= n_total) return;
-  const int wq = width >> 2;                                   // width % 4 == 0 checked by the wrapper
-  for (int o = threadIdx.x; o < T * wq; o += 256) {
-    const int t = o / wq, c = o - t * wq;
-    reinterpret_cast<float4*>(src + ((long long)t * B + j) * width)[c] =
-        __ldg(reinterpret_cast<const float4*>(P + ((long long)t * n_total + sidx) * width) + c);
+  if ((width & 3) == 0) {                                      // 128-bit copies (tensors 16-byte aligned: checked by the wrapper)
+    const int wq = width >> 2;
+    for (int o = threadIdx.x; o < T * wq; o += 256) {
+      const int t = o / wq, c = o - t * wq;
+      reinterpret_cast<float4*>(src + ((long long)t * B + j) * width)[c] =
+          __ldg(reinterpret_cast<const float4*>(P + ((long long)t * n_total + sidx) * width) + c);
+    }
+  } else {                                                     // e.g. PAM: 2 * 17 sensors
+    for (int o = threadIdx.x; o < T * width; o += 256) {
+      const int t = o / width, c = o - t * width;
+      src[((long long)t * B + j) * width + c] = __ldg(P + ((long long)t * n_total + sidx) * width + c);
+    }
   }
   int local = 0;
   for (int t = threadIdx.x; t < T; t += 256) {
@@ -645,8 +652,8 @@ int zero_features(float* P, int64_t T, int B, int width, const int64_t* idx, int
 int assemble_batch(const float* P, const float* Pt, const float* Ps, const int64_t* y, const int64_t* idx, int T, int64_t n_total,
                    int width, int ds, int B, float* src, float* times, float* statics, int64_t* y_out, int64_t* lengths,
                    cudaStream_t st) {
-  if ((width & 3) || ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(src)) & 15)) {
-    set_error("assemble_batch: width %% 4 == 0 and 16-byte aligned tensors required");
+  if ((width & 3) == 0 && ((reinterpret_cast<uintptr_t>(P) | reinterpret_cast<uintptr_t>(src)) & 15)) {
+    set_error("assemble_batch: 16-byte aligned tensors required when width %% 4 == 0");
     return -2;
   }
   if (B <= 0) return 0;

@@ -9,9 +9,9 @@
 //               double buffered so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 2-5   epilogue: tcgen05.ld -> bias / relu / gate / dropout / residual -> swizzled smem ->
 //               TMA store (coalesced 128-byte lines)
-//   warps 6-9   A loaders: coalesced 128-bit global loads of the activation tile (register
-//               prefetch one k-block ahead), split into hi / lo on the fly, written straight into
-//               the 128B-swizzled K-major layout the UMMA descriptor expects
+//   warps 6-9   remainder pass: the activation tile arrives by TMA like the weight tile (128B-swizzled K-major image,
+//               up to 4 k-blocks in flight -- register-staged loads were L2-latency bound: 0.63 us per k-block at
+//               K = 456 against a 0.3 us MMA floor); these warps only derive A_lo = A - trunc19(A) in shared memory
 #include <stdlib.h>
 
 #include "rd_tc_common.cuh"
@@ -47,8 +47,8 @@ __device__ __forceinline__ void gstamp(const P& p, int slot) {
 // epilogue features are compile-time: the epilogue is on the critical path of these small GEMMs
 template <bool RELU, bool GATE, bool DROP, bool RESID>
 __global__ void __launch_bounds__(NTHREADS, 1)
-tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
-               const __grid_constant__ CUtensorMap tmC, const P p) {
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmC, const P p) {
   extern __shared__ uint8_t smem_raw[];
   pdl_launch_dependents();
   if (threadIdx.x == 0) gstamp(p, 0);
@@ -64,17 +64,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
+  auto ready_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 5 + s); };     // A_lo written
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
   if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmA) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmB) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmBlo) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmC) : "memory");
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 5); mbar_init(empty_bar(s), 1); }  // 1 TMA + 4 loader warps
+      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), 4); }
       for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -91,14 +93,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
   const int total_tiles = p.m_tiles * p.n_tiles;
 
   if (warp == 0) {
-    // ===== TMA producer: weight tile (hi = the raw weight) and its remainder ======================
+    // ===== TMA producer: activation tile, weight tile (hi = the raw weight) and the weight remainder ==============
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_t = tile % p.n_tiles;
+        const int n_t = tile % p.n_tiles, m_t = tile / p.n_tiles;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), 2u * b_tile);
+          mbar_expect_tx(full_bar(stage), (uint32_t)A_TILE + 2u * b_tile);
+          tma_load_2d(&tmA, full_bar(stage), base + (uint32_t)stage * stage_bytes, kb * BK, m_t * BM);
           const uint32_t sb = base + (uint32_t)stage * stage_bytes + 2u * A_TILE;
           tma_load_2d(&tmB, full_bar(stage), sb, kb * BK, n_t * p.BN);
           tma_load_2d(&tmBlo, full_bar(stage), sb + b_tile, kb * BK, n_t * p.BN);
@@ -116,7 +119,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(full_bar(stage), phase);
+          mbar_wait(ready_bar(stage), phase);
           if (kb == 0) gstamp(p, 2);
           tc_fence_after();
           const uint32_t sa = base + (uint32_t)stage * stage_bytes;
@@ -224,58 +227,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmB, const __grid_constant__ 
     if (lane == 0) bulk_wait_read<0>();
     if (threadIdx.x == 64) gstamp(p, 6);
   } else {
-    // ===== A loaders: global -> registers -> hi/lo split -> swizzled smem ================================
+    // ===== remainder pass: A_lo = A - trunc19(A), same swizzled addresses =============================================
     const int lt = threadIdx.x - 192;           // 0..127
-    const int chunk = lt & 7, rsub = lt >> 3;   // 8 lanes cover one 128-byte row segment
     int stage = 0; uint32_t phase = 0;
-    float4 cur[8], nxt[8];
-    auto issue = [&](int tile, int kb, float4 (&r)[8]) {
-      const long long m0 = (long long)(tile / p.n_tiles) * BM;
-      const int k = kb * BK + chunk * 4;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const long long gr = m0 + it * 16 + rsub;
-        r[it] = (gr < p.M && k < p.K) ? __ldg(reinterpret_cast<const float4*>(p.A + gr * p.lda + k)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < p.k_blocks; ++kb) {
+        mbar_wait(full_bar(stage), phase);
+        const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+        lo_image<8>(sa, sa + A_TILE, A_TILE / 16, (uint32_t)lt, 128u);
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(ready_bar(stage));
+        if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
       }
-    };
-    // (tile, k-block) work units in order; loads run TWO units ahead of the stores (three rotating
-    // register buffers) so that an L2 round trip is hidden behind two MMA k-blocks
-    int lt_tile = blockIdx.x, lt_kb = 0;          // next unit to LOAD
-    auto advance = [&](int& t, int& k) { if (++k == p.k_blocks) { k = 0; t += gridDim.x; } };
-    auto store = [&](const float4 (&r)[8]) {
-      mbar_wait(empty_bar(stage), phase ^ 1u);
-      const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-#pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = it * 16 + rsub;
-        const uint32_t off = (uint32_t)(row * 128 + ((chunk ^ (row & 7)) << 4));
-        const float4 a = r[it];
-        float4 lo;
-        lo.x = a.x - __uint_as_float(__float_as_uint(a.x) & 0xFFFFE000u);
-        lo.y = a.y - __uint_as_float(__float_as_uint(a.y) & 0xFFFFE000u);
-        lo.z = a.z - __uint_as_float(__float_as_uint(a.z) & 0xFFFFE000u);
-        lo.w = a.w - __uint_as_float(__float_as_uint(a.w) & 0xFFFFE000u);
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + off), "f"(a.x), "f"(a.y), "f"(a.z), "f"(a.w) : "memory");
-        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(sa + A_TILE + off), "f"(lo.x), "f"(lo.y), "f"(lo.z), "f"(lo.w) : "memory");
-      }
-      fence_async_smem();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(full_bar(stage));
-      if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
-    };
-    float4 r2[8];
-    int st_tile = blockIdx.x, st_kb = 0;          // next unit to STORE
-    if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, cur); advance(lt_tile, lt_kb); }
-    if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, nxt); advance(lt_tile, lt_kb); }
-    while (st_tile < total_tiles) {
-      if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, r2); advance(lt_tile, lt_kb); }
-      store(cur); advance(st_tile, st_kb);
-      if (st_tile >= total_tiles) break;
-      if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, cur); advance(lt_tile, lt_kb); }
-      store(nxt); advance(st_tile, st_kb);
-      if (st_tile >= total_tiles) break;
-      if (lt_tile < total_tiles) { issue(lt_tile, lt_kb, nxt); advance(lt_tile, lt_kb); }
-      store(r2); advance(st_tile, st_kb);
     }
   }
   tc_fence_before();
@@ -594,7 +558,13 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
   p.drop_p = a.drop_p; p.rng = a.rng; p.drop_site = a.drop_site; p.resid = a.resid; p.resid_ld = a.resid_ld;
   p.dbg = g_gemm_dbg;
 
-  CUtensorMap tmB, tmBlo, tmC;
+  CUtensorMap tmA, tmB, tmBlo, tmC;
+  {
+    cuuint64_t ad[2] = {(cuuint64_t)a.K, (cuuint64_t)a.M};
+    cuuint64_t as_[1] = {(cuuint64_t)a.lda * 4};
+    cuuint32_t ab[2] = {BK, BM};
+    RD_TRY(encode(&tmA, a.A, 2, ad, as_, ab, CU_TENSOR_MAP_SWIZZLE_128B, "A"));
+  }
   cuuint64_t bd[2] = {(cuuint64_t)a.K, (cuuint64_t)a.N};
   cuuint64_t bs[1] = {(cuuint64_t)a.K * 4};
   cuuint32_t bb[2] = {BK, (cuuint32_t)p.BN};
@@ -608,7 +578,7 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
   const int grid = total < num_sms() ? total : num_sms();
   auto launch = [&](auto kern, int id) -> int {
     RD_TRY(ensure_attr((const void*)kern, id));
-    launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem_bytes, st, tmB, tmBlo, tmC, p);
+    launch_pdl(kern, dim3(grid), dim3(NTHREADS), smem_bytes, st, tmA, tmB, tmBlo, tmC, p);
     return 0;
   };
   const int id = (a.relu ? 8 : 0) | (a.gate ? 4 : 0) | (a.drop_p > 0.f ? 2 : 0) | (a.resid ? 1 : 0);

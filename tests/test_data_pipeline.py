@@ -148,6 +148,14 @@ def test_device_dataset_fill_and_feature_removal_are_bit_exact():
     ds.fill(buf, idx, removed=np.array([0, 5, 33]))
     ref = full["src"][:, idx].clone(); ref[:, :, [0, 5, 33]] = 0
     assert torch.equal(buf.src.cpu(), ref)
+    # odd width (PAM: 2 * 17 columns -> scalar copy path)
+    cfgp = model_config("PAM", dropout=0.2)
+    fp = make_batch(cfgp, 20, seed=3)
+    dsp = RD.DeviceDataset(fp["src"], None, fp["times"], fp["y"])
+    bp = RD.BatchBuffers(cfgp["max_len"], 7, 2 * cfgp["d_inp"], 0)
+    ip = torch.tensor([3, 0, 19, 7, 7, 12, 1])
+    dsp.fill(bp, ip)
+    assert torch.equal(bp.src.cpu(), fp["src"][:, ip]) and torch.equal(bp.lengths.cpu(), torch.sum(fp["times"][:, ip] > 0, dim=0))
     # a dataset without statics (PAM)
     ds2 = RD.DeviceDataset(full["src"], None, full["times"], full["y"])
     buf2 = RD.BatchBuffers(cfg["max_len"], B, 2 * cfg["d_inp"], 0)
