@@ -71,19 +71,29 @@ __device__ __forceinline__ void lo_pass(uint32_t hi, uint32_t lo_off, uint32_t b
 //   KMAJOR operand: contraction over columns; k-step ks covers columns 8*ks..8*ks+7 (group ks/4, 32 bytes * (ks%4))
 //   MN operand:     contraction over rows;    k-step ks covers rows 8*ks..8*ks+7 (1024 bytes apart), groups GRP apart,
 //                   image in the 32-byte-atom swizzle
+// The four base descriptors are built once; a k-step only moves the 14-bit start-address field (units of 16 bytes), so
+// the single issuing thread spends a handful of instructions per MMA (building descriptors inside the loop made the
+// issue of 36 MMAs take 3 us -- one thread's dependent 64-bit arithmetic, not the tensor pipe).
 template <bool A_MN, bool B_MN>
 __device__ __forceinline__ void mma3(uint32_t d_tmem, uint32_t a, uint32_t a_lo, uint32_t b, uint32_t b_lo, int ksteps,
                                      uint32_t idesc) {
-  for (int ks = 0; ks < ksteps; ++ks) {
-    const uint32_t ao = A_MN ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * GRP + (uint32_t)(ks & 3) * 32u;
-    const uint32_t bo = B_MN ? (uint32_t)ks * 1024u : (uint32_t)(ks >> 2) * GRP + (uint32_t)(ks & 3) * 32u;
-    const uint64_t ah = A_MN ? umma_desc_mn_sw128(a + ao, GRP) : umma_desc_sw128(a + ao);
-    const uint64_t al = A_MN ? umma_desc_mn_sw128(a + a_lo + ao, GRP) : umma_desc_sw128(a + a_lo + ao);
-    const uint64_t bh = B_MN ? umma_desc_mn_sw128(b + bo, GRP) : umma_desc_sw128(b + bo);
-    const uint64_t bl = B_MN ? umma_desc_mn_sw128(b + b_lo + bo, GRP) : umma_desc_sw128(b + b_lo + bo);
-    umma_tf32(d_tmem, al, bh, idesc, ks ? 1u : 0u);     // small terms first
-    umma_tf32(d_tmem, ah, bl, idesc, 1u);
-    umma_tf32(d_tmem, ah, bh, idesc, 1u);
+  uint64_t ah = A_MN ? umma_desc_mn_sw128(a, GRP) : umma_desc_sw128(a);
+  uint64_t al = A_MN ? umma_desc_mn_sw128(a + a_lo, GRP) : umma_desc_sw128(a + a_lo);
+  uint64_t bh = B_MN ? umma_desc_mn_sw128(b, GRP) : umma_desc_sw128(b);
+  uint64_t bl = B_MN ? umma_desc_mn_sw128(b + b_lo, GRP) : umma_desc_sw128(b + b_lo);
+  constexpr uint64_t A_STEP = A_MN ? 64 : 2, B_STEP = B_MN ? 64 : 2;                 // one k-step, in 16-byte units
+  constexpr uint64_t A_GRP = A_MN ? 256 : (GRP >> 4), B_GRP = B_MN ? 256 : (GRP >> 4);   // four k-steps
+#pragma unroll 1
+  for (int g = 0; g < ksteps; g += 4) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (g + j < ksteps) {
+        umma_tf32(d_tmem, al + j * A_STEP, bh + j * B_STEP, idesc, (g | j) ? 1u : 0u);     // small terms first
+        umma_tf32(d_tmem, ah + j * A_STEP, bl + j * B_STEP, idesc, 1u);
+        umma_tf32(d_tmem, ah + j * A_STEP, bh + j * B_STEP, idesc, 1u);
+      }
+    }
+    ah += A_GRP; al += A_GRP; bh += B_GRP; bl += B_GRP;
   }
 }
 
@@ -125,7 +135,7 @@ __device__ __forceinline__ void precompute_keep_bits(const AttnTcP& p, int b, in
   const uint64_t row_base = ((uint64_t)(b * p.H + h) * p.T + r) * p.T;
   unsigned long long bits = 0ull;
   if (r < p.T) {
-#pragma unroll
+#pragma unroll 1        // rolled: 16 unrolled Philox blocks are 1600 instructions of straight-line code per CTA
     for (int c = 0; c < 16; ++c) {
       const float4 m = mask4(p, row_base, c, 1.f);
       bits |= (unsigned long long)((m.x > 0.f ? 1u : 0u) | (m.y > 0.f ? 2u : 0u) | (m.z > 0.f ? 4u : 0u) | (m.w > 0.f ? 8u : 0u)) << (4 * c);
@@ -133,32 +143,23 @@ __device__ __forceinline__ void precompute_keep_bits(const AttnTcP& p, int b, in
   }
   keep[r] = bits;
 }
-__device__ __forceinline__ float4 keep4(unsigned long long bits, int c, float ik, float drop_p) {
-  if (drop_p <= 0.f) return make_float4(1.f, 1.f, 1.f, 1.f);
-  const unsigned q = (unsigned)(bits >> (4 * c)) & 15u;
-  return make_float4(q & 1u ? ik : 0.f, q & 2u ? ik : 0.f, q & 4u ? ik : 0.f, q & 8u ? ik : 0.f);
-}
 
-// softmax of this thread's score row (already in registers, unscaled): s -> probabilities in place
-__device__ __forceinline__ void softmax_row(float (&s)[64], float scale, int nv, bool row_ok) {
+// Row softmax in rolled passes over 16-column chunks of the accumulator row (re-read from TMEM each pass): the kernel
+// runs each phase once per CTA, so fully unrolled 64-wide code was instruction-fetch bound (~7 clocks per instruction).
+// exp(x - m) = ex2((x - m) * log2 e), one MUFU per element.
+struct RowStat { float mxs, inv; };      // max * (scale * log2 e), 1 / sum (0 for a padded row)
+__device__ __forceinline__ float row_max(uint32_t trow, int nv) {
   float mx = -INFINITY;
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    float v[16];
+    tmem_ld16(trow + 16 * cc, v);
 #pragma unroll
-  for (int j = 0; j < 64; ++j) { s[j] *= scale; if (j < nv) mx = fmaxf(mx, s[j]); }
-  float sum = 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) { s[j] = j < nv ? expf(s[j] - mx) : 0.f; sum += s[j]; }
-  const float inv = (row_ok && nv > 0) ? 1.f / sum : 0.f;
-#pragma unroll
-  for (int j = 0; j < 64; ++j) s[j] *= inv;
+    for (int j = 0; j < 16; ++j) mx = fmaxf(mx, 16 * cc + j < nv ? v[j] : -INFINITY);
+  }
+  return mx;
 }
-
-__device__ __forceinline__ void load_row64(uint32_t taddr, float (&v)[64]) {
-  uint32_t a[32], c[32];
-  tmem_ld32(taddr, a);
-  tmem_ld32(taddr + 32, c);
-#pragma unroll
-  for (int j = 0; j < 32; ++j) { v[j] = __uint_as_float(a[j]); v[32 + j] = __uint_as_float(c[j]); }
-}
+__device__ __forceinline__ float exp_el(float v, float sl2, float mxs, bool valid) { return valid ? ex2_approx(fmaf(v, sl2, -mxs)) : 0.f; }
 
 // =================================================================================================
 // forward: ctx[t, b, h*hd + d] = sum_j dropout(softmax(scale * Q K^T))[t, j] V[j, d]
@@ -215,7 +216,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   stamp(p, 3);
   if (threadIdx.x == 0) {
     tc_fence_after();
-    mma3<false, false>(tS, QV, TILE, KP, TILE, 4 * NG, umma_idesc_tf32(128, 64, false, false));
+    mma3<false, false>(tS, QV, TILE, KP, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
     umma_commit(bar_s);
     stamp(p, 4);
     mbar_wait(bar_s, 0);                       // Q is dead: its region receives V
@@ -225,8 +226,8 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
     for (int g = 0; g < NG; ++g) tma_load_5d(&tmQKVm, bar_v, QV + g * GRP, 32 * g, h, 2, b, 0);     // MN image
   }
   // Lanes 1..31 of warp 0 must not run ahead of lane 0: divergent paths of one warp execute one at a time, so sibling
-  // lanes spinning on an mbarrier (or starting their softmax) would time-slice with the MMA issue loop -- measured 3.3 us
-  // for 36 MMAs -- and lane 0 would then redo the softmax alone.  Park them at a warp barrier instead.
+  // lanes spinning on an mbarrier (or starting their softmax) would time-slice with the MMA issue loop and lane 0 would
+  // then redo the softmax alone.  Park them at a warp barrier instead.
   __syncwarp();
   if (warp < 2) {      // rows 0..63: masked softmax + dropout; P (hi, lo) replaces K in shared memory
     const int i = threadIdx.x;
@@ -235,15 +236,36 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
     mbar_wait(bar_s, 0);
     __syncwarp();
     tc_fence_after();
-    float s[64];
-    load_row64(tS + ((uint32_t)(warp * 32) << 16), s);
-    softmax_row(s, p.scale, nv, i < p.T);
-    const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const unsigned long long bits = p.drop_p > 0.f ? keep[i] : 0ull;
+    const uint32_t trow = tS + ((uint32_t)(warp * 32) << 16);
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const float mxs = row_max(trow, nv) * sl2;
+    float sum = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      float v[16];
+      tmem_ld16(trow + 16 * cc, v);
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-      const float4 m = keep4(bits, c, ik, p.drop_p);
-      store_chunk_hi_lo(KP, i, c, s[4 * c] * m.x, s[4 * c + 1] * m.y, s[4 * c + 2] * m.z, s[4 * c + 3] * m.w);
+      for (int j = 0; j < 16; ++j) sum += exp_el(v[j], sl2, mxs, 16 * cc + j < nv);
+    }
+    const bool drop = p.drop_p > 0.f;
+    const float invk = ((i < p.T && nv > 0) ? 1.f / sum : 0.f) * (drop ? 1.f / (1.f - p.drop_p) : 1.f);
+    const unsigned long long bits = drop ? keep[i] : ~0ull;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {      // P * keep / (1 - p): hi and lo images for O = P V
+      float v[16];
+      tmem_ld16(trow + 16 * cc, v);
+      const unsigned kb = (unsigned)(bits >> (16 * cc)) & 0xFFFFu;
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = 4 * c4 + q;
+          const float e = exp_el(v[j], sl2, mxs, 16 * cc + j < nv);
+          o[q] = (kb >> j) & 1u ? e * invk : 0.f;
+        }
+        store_chunk_hi_lo(KP, i, 4 * cc + c4, o[0], o[1], o[2], o[3]);
+      }
     }
     fence_async_smem();
     stamp(p, 6);
@@ -334,6 +356,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   pdl_wait();
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tDP = tmem + 64, tDV = tmem + 128, tDQ = tmem + 224, tDK = tmem + 320;
+  stamp(p, 0);
 
   // ---- phase 1: K-major images of Q, K, V, dO; S = Q K^T and dP = dO V^T ---------------------------
   if (threadIdx.x == 0) {
@@ -352,14 +375,16 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   }
   precompute_keep_bits(p, b, h, keep);
   mbar_wait(bar_qk, 0);
+  stamp(p, 1);
   lo_pass(R0, TILE, TILE);
   lo_pass(R1, TILE, TILE);
   fence_async_smem();
   __syncthreads();
   if (threadIdx.x == 0) {     // recompute the scores
     tc_fence_after();
-    mma3<false, false>(tS, R0, TILE, R1, TILE, 4 * NG, umma_idesc_tf32(128, 64, false, false));
+    mma3<false, false>(tS, R0, TILE, R1, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
     umma_commit(bar_s);
+    stamp(p, 2);
   }
   __syncwarp();        // (see the forward kernel: sibling lanes must not spin while lane 0 issues MMAs)
   mbar_wait(bar_gv, 0);
@@ -369,11 +394,13 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   __syncthreads();
   if (threadIdx.x == 0) {     // dPd[i, j] = sum_d dO[i, d] V[j, d]
     tc_fence_after();
-    mma3<false, false>(tDP, R3, TILE, R2, TILE, 4 * NG, umma_idesc_tf32(128, 64, false, false));
+    mma3<false, false>(tDP, R3, TILE, R2, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
     umma_commit(bar_dp);
+    stamp(p, 3);
     // every phase-1 image is dead once both accumulators are complete: fetch the MN images of dO and K
     mbar_wait(bar_s, 0);
     mbar_wait(bar_dp, 0);
+    stamp(p, 4);
     mbar_expect_tx(bar_m1, 2u * TILE);
 #pragma unroll
     for (int g = 0; g < NG; ++g) {
@@ -388,36 +415,62 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
     const long long len = p.lengths[b];
     const int nv = (int)(len < p.T ? (len < 0 ? 0 : len) : p.T);
     const uint32_t lane_addr = (uint32_t)(warp * 32) << 16;
-    float pr[64], w[64];
     mbar_wait(bar_s, 0);
     __syncwarp();
     tc_fence_after();
-    load_row64(tS + lane_addr, pr);
-    softmax_row(pr, p.scale, nv, i < p.T);          // pr = probabilities
+    const uint32_t srow = tS + lane_addr, drow = tDP + lane_addr;
+    const float sl2 = p.scale * 1.4426950408889634f;
+    const float mxs = row_max(srow, nv) * sl2;
     mbar_wait(bar_dp, 0);                            // Q, K, V, dO images are dead from here on
     __syncwarp();
     tc_fence_after();
-    load_row64(tDP + lane_addr, w);                  // w = d(Pd)
-    float dot = 0.f;
-    const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
-    const unsigned long long bits = p.drop_p > 0.f ? keep[i] : 0ull;
+    const bool drop = p.drop_p > 0.f;
+    const float ik = drop ? 1.f / (1.f - p.drop_p) : 1.f;
+    const unsigned long long bits = drop ? keep[i] : ~0ull;
+    float sum = 0.f, dotr = 0.f;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {      // sum of exponentials and rowsum(dP * P) (un-normalised) in one pass
+      float v[16], g[16];
+      tmem_ld16(srow + 16 * cc, v);
+      tmem_ld16(drow + 16 * cc, g);
+      const unsigned kb = (unsigned)(bits >> (16 * cc)) & 0xFFFFu;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {      // w := dP = d(Pd) * mask; Pd = P * mask goes to shared memory (read column-wise later)
-      const float4 m = keep4(bits, c, ik, p.drop_p);
-      w[4 * c] *= m.x; w[4 * c + 1] *= m.y; w[4 * c + 2] *= m.z; w[4 * c + 3] *= m.w;
-      dot += w[4 * c] * pr[4 * c] + w[4 * c + 1] * pr[4 * c + 1] + w[4 * c + 2] * pr[4 * c + 2] + w[4 * c + 3] * pr[4 * c + 3];
-      store_chunk_mn(Pd, Pd_lo, i, c, pr[4 * c] * m.x, pr[4 * c + 1] * m.y, pr[4 * c + 2] * m.z, pr[4 * c + 3] * m.w);
+      for (int j = 0; j < 16; ++j) {
+        const float e = exp_el(v[j], sl2, mxs, 16 * cc + j < nv);
+        sum += e;
+        dotr += (kb >> j) & 1u ? g[j] * e : 0.f;
+      }
     }
+    const float inv = (i < p.T && nv > 0) ? 1.f / sum : 0.f;
+    const float dot = dotr * ik * inv;
+#pragma unroll 1
+    for (int cc = 0; cc < 4; ++cc) {
+      float v[16], g[16];
+      tmem_ld16(srow + 16 * cc, v);
+      tmem_ld16(drow + 16 * cc, g);
+      const unsigned kb = (unsigned)(bits >> (16 * cc)) & 0xFFFFu;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {      // scale * dS = scale * P * (dP - rowsum(dP * P)): row-wise AND column-wise images
-      const float d0 = pr[4 * c] * (w[4 * c] - dot) * p.scale, d1 = pr[4 * c + 1] * (w[4 * c + 1] - dot) * p.scale;
-      const float d2 = pr[4 * c + 2] * (w[4 * c + 2] - dot) * p.scale, d3 = pr[4 * c + 3] * (w[4 * c + 3] - dot) * p.scale;
-      store_chunk_hi_lo(dSk, i, c, d0, d1, d2, d3);
-      store_chunk_mn(dSm, dSm_lo, i, c, d0, d1, d2, d3);
+      for (int c4 = 0; c4 < 4; ++c4) {
+        float pd[4], ds[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = 4 * c4 + q;
+          const float pr = exp_el(v[j], sl2, mxs, 16 * cc + j < nv) * inv;      // probability
+          const float m = (kb >> j) & 1u ? ik : 0.f;
+          pd[q] = pr * m;                                                        // Pd = P * mask (read column-wise by dV)
+          ds[q] = pr * (g[j] * m - dot) * p.scale;                               // scale * dS = scale * P * (dP - rowsum(dP * P))
+        }
+        const int c = 4 * cc + c4;
+        store_chunk_mn(Pd, Pd_lo, i, c, pd[0], pd[1], pd[2], pd[3]);
+        store_chunk_hi_lo(dSk, i, c, ds[0], ds[1], ds[2], ds[3]);                // row-wise image (dQ = dS K)
+        store_chunk_mn(dSm, dSm_lo, i, c, ds[0], ds[1], ds[2], ds[3]);           // column-wise image (dK = dS^T Q)
+      }
     }
     fence_async_smem();
+    stamp(p, 5);
   }
   mbar_wait(bar_m1, 0);
+  stamp(p, 6);
   lo_pass(R2, TILE, TILE);
   lo_pass(R3, TILE, TILE);
   fence_async_smem();
@@ -430,10 +483,12 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
     // dQ[i, d] = sum_j (scale dS)[i, j] K[j, d]
     mma3<false, true>(tDQ, dSk, PT, R3, TILE, 8, umma_idesc_tf32(128, 96, false, true));
     umma_commit(bar_2);
+    stamp(p, 7);
     mbar_wait(bar_2, 0);                 // the dO image is dead: its region receives Q (MN image)
     mbar_expect_tx(bar_m2, (uint32_t)TILE);
 #pragma unroll
     for (int g = 0; g < NG; ++g) tma_load_5d(&tmQKVm, bar_m2, R2 + g * GRP, 32 * g, h, 0, b, 0);
+    stamp(p, 8);
   }
   __syncwarp();
   auto store_out = [&](uint32_t t0, int which) {     // accumulator rows 0..63 -> d_qkv[t, b, which*D + h*hd + d]
@@ -458,9 +513,11 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
     tc_fence_after();
     store_out(tDQ, 0);
     store_out(tDV, 2);
+    stamp(p, 9);
   }
   // ---- phase 3: dK[j, d] = sum_i (scale dS)[i, j] Q[i, d] ---------------------------------------------
   mbar_wait(bar_m2, 0);
+  stamp(p, 10);
   lo_pass(R2, TILE, TILE);
   fence_async_smem();
   tc_fence_before();
@@ -469,6 +526,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
     tc_fence_after();
     mma3<true, true>(tDK, dSm, dSm_lo - dSm, R2, TILE, 8, umma_idesc_tf32(128, 96, true, true));
     umma_commit(bar_out);
+    stamp(p, 11);
   }
   __syncwarp();
   if (warp < 2) {
@@ -477,6 +535,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
     tc_fence_after();
     store_out(tDK, 1);
   }
+  stamp(p, 12);
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -542,7 +601,7 @@ int attn_tc_bwd(const float* qkv, const float* dctx, const int64_t* lengths, int
   }
   AttnTcP p{};
   p.dqkv = dqkv; p.lengths = lengths; p.B = B; p.H = H; p.T = T; p.hd = hd; p.D = H * hd;
-  p.scale = 1.f / sqrtf((float)hd); p.drop_p = drop_p; p.rng = rng; p.site = site;
+  p.scale = 1.f / sqrtf((float)hd); p.drop_p = drop_p; p.rng = rng; p.site = site; p.dbg = g_attn_dbg;
   CUtensorMap tq, tqm, tg, tgm;
   RD_TRY(encode_qkv(&tq, qkv, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B));
   RD_TRY(encode_qkv(&tqm, qkv, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));

@@ -502,8 +502,9 @@ def test_graph_operator_gradients(golden_dir):
     assert normwise(ob, ol) < 1e-6
     (ol * Gb).sum().backward()
     assert normwise(xb_grad, xb.grad) < 1e-5
-    for a_, p in zip(gb_batched, P):
-        assert normwise(a_, p.grad) < 1e-5
+    scale = max(float(p.grad.abs().max()) for p in P)
+    for a_, p in zip(gb_batched, P):      # lin_key.bias is softmax-invariant: both are rounding noise around zero
+        assert normwise(a_, p.grad) < 1e-5 or float((a_ - p.grad).abs().max()) < 1e-6 * scale
 
 
 def test_legacy_raindrop_v1_against_reference(golden_dir):

@@ -25,6 +25,26 @@ for i, n in enumerate(names):
     print("%-18s median +%.2f us   (p10 %.2f, p90 %.2f)" % (n, col.median() / 1e3, col.quantile(0.1) / 1e3, col.quantile(0.9) / 1e3))
 print("CTA start offsets: median %.2f us, max %.2f us" % (((d[:, 0] - t0).median()) / 1e3, (d[:, 0] - t0).max() / 1e3))
 
+# ---- backward ----------------------------------------------------------------------------------------------
+dctx = torch.randn(T, B, D, device="cuda"); dqkv = torch.empty(T, B, 3 * D, device="cuda")
+def runb():
+    L.check(lib.rd_temporal_attention_bwd(qkv.data_ptr(), dctx.data_ptr(), lengths.data_ptr(), B, H, T, hd, 0.2, rng.data_ptr(), 16, 1, dqkv.data_ptr(), L.stream_ptr()), "bwd")
+for _ in range(3): runb()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); [run() for _ in range(20)]; e1.record(); torch.cuda.synchronize()
+print("\nforward  %.2f us per call (back to back)" % (e0.elapsed_time(e1) / 20 * 1e3))
+e0.record(); [runb() for _ in range(20)]; e1.record(); torch.cuda.synchronize()
+print("backward %.2f us per call (back to back)" % (e0.elapsed_time(e1) / 20 * 1e3))
+dbg = torch.zeros(B * H, 16, dtype=torch.int64, device="cuda")
+lib.rd_debug_attention_timing(dbg.data_ptr()); runb(); torch.cuda.synchronize(); lib.rd_debug_attention_timing(None)
+d = dbg.cpu().double(); t0 = d[:, 0].min()
+names = ["setup done", "Q,K landed", "S issued", "dP issued", "S,dP done", "softmax/dS stored", "dO,K (MN) landed", "dV,dQ issued",
+         "dV,dQ done; Q TMA", "dQ,dV stored", "Q (MN) landed", "dK issued", "dK stored"]
+print("backward kernel span %.2f us; CTA start offsets median %.2f max %.2f us" % ((d[:, 12].max() - t0) / 1e3, (d[:, 0] - t0).median() / 1e3, (d[:, 0] - t0).max() / 1e3))
+for i, n in enumerate(names):
+    col = d[:, i] - d[:, 0]
+    print("%-20s median +%.2f us   (p10 %.2f, p90 %.2f)" % (n, col.median() / 1e3, col.quantile(0.1) / 1e3, col.quantile(0.9) / 1e3))
+
 # ---- projection GEMM (rd_linear_fwd): M = 7680 tokens, K = 152, N = 152 / 456 ---------------------------------
 for (K, N) in ((152, 152), (152, 456), (456, 152), (272, 152)):
     x = torch.randn(7680, K, device="cuda"); W = torch.randn(N, K, device="cuda") * 0.1; b = torch.zeros(N, device="cuda")

@@ -47,5 +47,8 @@ def full(rep, out, json_out=None):
                    "rows": 557056, "C": 240}, open(json_out, "w"), indent=1)
 
 if __name__ == "__main__":
-    launches("gpurun_out/launches.csv", "profiles/r01_step_launches.txt")
-    full("gpurun_out/prof_tc.ncu-rep", "profiles/r01_obprop_tc_full.txt", "profiles/obprop_tc_traffic.json")
+    # usage: ncu_summary.py launches <csv> <out.txt> | full <rep> <out.txt> [traffic.json]
+    if sys.argv[1] == "launches":
+        launches(sys.argv[2], sys.argv[3])
+    else:
+        full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else None)
