@@ -74,26 +74,41 @@ __device__ __forceinline__ void lo_pass(uint32_t hi, uint32_t lo_off, uint32_t b
 // The four base descriptors are built once; a k-step only moves the 14-bit start-address field (units of 16 bytes), so
 // the single issuing thread spends a handful of instructions per MMA (building descriptors inside the loop made the
 // issue of 36 MMAs take 3 us -- one thread's dependent 64-bit arithmetic, not the tensor pipe).
-template <bool A_MN, bool B_MN>
-__device__ __forceinline__ void mma3(uint32_t d_tmem, uint32_t a, uint32_t a_lo, uint32_t b, uint32_t b_lo, int ksteps,
+__device__ __forceinline__ void umma_tf32_split(uint32_t d_tmem, uint32_t a_lo32, uint32_t a_hi32, uint32_t b_lo32, uint32_t b_hi32,
+                                                uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(d_tmem), "r"(a_lo32), "r"(a_hi32), "r"(b_lo32), "r"(b_hi32), "r"(idesc), "r"(acc) : "memory");
+}
+template <bool A_MN, bool B_MN, int MAXK>
+__device__ __forceinline__ void mma3(uint32_t d_tmem, uint32_t a_, uint32_t a_lo, uint32_t b_, uint32_t b_lo, int ksteps_,
                                      uint32_t idesc) {
-  uint64_t ah = A_MN ? umma_desc_mn_sw128(a, GRP) : umma_desc_sw128(a);
-  uint64_t al = A_MN ? umma_desc_mn_sw128(a + a_lo, GRP) : umma_desc_sw128(a + a_lo);
-  uint64_t bh = B_MN ? umma_desc_mn_sw128(b, GRP) : umma_desc_sw128(b);
-  uint64_t bl = B_MN ? umma_desc_mn_sw128(b + b_lo, GRP) : umma_desc_sw128(b + b_lo);
-  constexpr uint64_t A_STEP = A_MN ? 64 : 2, B_STEP = B_MN ? 64 : 2;                 // one k-step, in 16-byte units
-  constexpr uint64_t A_GRP = A_MN ? 256 : (GRP >> 4), B_GRP = B_MN ? 256 : (GRP >> 4);   // four k-steps
-#pragma unroll 1
-  for (int g = 0; g < ksteps; g += 4) {
+  // called by a whole (converged) warp; lane 0 issues.  The broadcasts tell the compiler the operands are warp-uniform,
+  // so the descriptors live in uniform registers instead of going through a per-MMA R2UR waterfall
+  const uint32_t a = __shfl_sync(0xffffffffu, a_, 0), b = __shfl_sync(0xffffffffu, b_, 0);
+  const int ksteps = __shfl_sync(0xffffffffu, ksteps_, 0);
+  const bool leader = (threadIdx.x & 31) == 0;
+  // descriptors as (low word, high word): only the low word (start address, 16-byte units) changes between MMAs
+  const uint64_t a0 = A_MN ? umma_desc_mn_sw128(0, GRP) : umma_desc_sw128(0);
+  const uint64_t b0 = B_MN ? umma_desc_mn_sw128(0, GRP) : umma_desc_sw128(0);
+  const uint32_t a_hi32 = (uint32_t)(a0 >> 32), b_hi32 = (uint32_t)(b0 >> 32);
+  const uint32_t ah = (uint32_t)a0 | ((a >> 4) & 0x3FFFu), al = (uint32_t)a0 | (((a + a_lo) >> 4) & 0x3FFFu);
+  const uint32_t bh = (uint32_t)b0 | ((b >> 4) & 0x3FFFu), bl = (uint32_t)b0 | (((b + b_lo) >> 4) & 0x3FFFu);
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      if (g + j < ksteps) {
-        umma_tf32(d_tmem, al + j * A_STEP, bh + j * B_STEP, idesc, (g | j) ? 1u : 0u);     // small terms first
-        umma_tf32(d_tmem, ah + j * A_STEP, bl + j * B_STEP, idesc, 1u);
-        umma_tf32(d_tmem, ah + j * A_STEP, bh + j * B_STEP, idesc, 1u);
-      }
+  for (int ks = 0; ks < MAXK; ++ks) {
+    if (ks < ksteps && leader) {
+      const uint32_t ao = A_MN ? (uint32_t)ks * 64u : (uint32_t)((ks >> 2) * (GRP >> 4) + (ks & 3) * 2);
+      const uint32_t bo = B_MN ? (uint32_t)ks * 64u : (uint32_t)((ks >> 2) * (GRP >> 4) + (ks & 3) * 2);
+      umma_tf32_split(d_tmem, al + ao, a_hi32, bh + bo, b_hi32, idesc, ks ? 1u : 0u);     // small terms first
+      umma_tf32_split(d_tmem, ah + ao, a_hi32, bl + bo, b_hi32, idesc, 1u);
+      umma_tf32_split(d_tmem, ah + ao, a_hi32, bh + bo, b_hi32, idesc, 1u);
     }
-    ah += A_GRP; al += A_GRP; bh += B_GRP; bl += B_GRP;
   }
 }
 
@@ -214,9 +229,11 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   fence_async_smem();
   __syncthreads();
   stamp(p, 3);
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     tc_fence_after();
-    mma3<false, false>(tS, QV, TILE, KP, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
+    mma3<false, false, 4 * NG>(tS, QV, TILE, KP, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
+  }
+  if (threadIdx.x == 0) {
     umma_commit(bar_s);
     stamp(p, 4);
     mbar_wait(bar_s, 0);                       // Q is dead: its region receives V
@@ -277,9 +294,11 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   tc_fence_before();
   __syncthreads();
   stamp(p, 8);
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     tc_fence_after();
-    mma3<false, true>(tO, KP, PT, QV, TILE, 8, umma_idesc_tf32(128, 96, false, true));
+    mma3<false, true, 8>(tO, KP, PT, QV, TILE, 8, umma_idesc_tf32(128, 96, false, true));
+  }
+  if (threadIdx.x == 0) {
     umma_commit(bar_o);
     stamp(p, 9);
   }
@@ -380,9 +399,11 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   lo_pass(R1, TILE, TILE);
   fence_async_smem();
   __syncthreads();
-  if (threadIdx.x == 0) {     // recompute the scores
+  if (warp == 0) {     // recompute the scores
     tc_fence_after();
-    mma3<false, false>(tS, R0, TILE, R1, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
+    mma3<false, false, 4 * NG>(tS, R0, TILE, R1, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
+  }
+  if (threadIdx.x == 0) {
     umma_commit(bar_s);
     stamp(p, 2);
   }
@@ -392,9 +413,11 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   lo_pass(R3, TILE, TILE);
   fence_async_smem();
   __syncthreads();
-  if (threadIdx.x == 0) {     // dPd[i, j] = sum_d dO[i, d] V[j, d]
+  if (warp == 0) {     // dPd[i, j] = sum_d dO[i, d] V[j, d]
     tc_fence_after();
-    mma3<false, false>(tDP, R3, TILE, R2, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
+    mma3<false, false, 4 * NG>(tDP, R3, TILE, R2, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
+  }
+  if (threadIdx.x == 0) {
     umma_commit(bar_dp);
     stamp(p, 3);
     // every phase-1 image is dead once both accumulators are complete: fetch the MN images of dO and K
@@ -476,12 +499,14 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     tc_fence_after();
     // dV[j, d] = sum_i Pd[i, j] dO[i, d]        A = Pd read column-wise (MN-major), B = dO (MN-major)
-    mma3<true, true>(tDV, Pd, PT, R2, TILE, 8, umma_idesc_tf32(128, 96, true, true));
+    mma3<true, true, 8>(tDV, Pd, PT, R2, TILE, 8, umma_idesc_tf32(128, 96, true, true));
     // dQ[i, d] = sum_j (scale dS)[i, j] K[j, d]
-    mma3<false, true>(tDQ, dSk, PT, R3, TILE, 8, umma_idesc_tf32(128, 96, false, true));
+    mma3<false, true, 8>(tDQ, dSk, PT, R3, TILE, 8, umma_idesc_tf32(128, 96, false, true));
+  }
+  if (threadIdx.x == 0) {
     umma_commit(bar_2);
     stamp(p, 7);
     mbar_wait(bar_2, 0);                 // the dO image is dead: its region receives Q (MN image)
@@ -522,9 +547,11 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   fence_async_smem();
   tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (warp == 0) {
     tc_fence_after();
-    mma3<true, true>(tDK, dSm, dSm_lo - dSm, R2, TILE, 8, umma_idesc_tf32(128, 96, true, true));
+    mma3<true, true, 8>(tDK, dSm, dSm_lo - dSm, R2, TILE, 8, umma_idesc_tf32(128, 96, true, true));
+  }
+  if (threadIdx.x == 0) {
     umma_commit(bar_out);
     stamp(p, 11);
   }

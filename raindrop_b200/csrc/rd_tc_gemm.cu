@@ -100,11 +100,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_t = tile % p.n_tiles, m_t = tile / p.n_tiles;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), (uint32_t)A_TILE + 2u * b_tile);
+          mbar_expect_tx(full_bar(stage), (uint32_t)A_TILE + b_tile);
           tma_load_2d(&tmA, full_bar(stage), base + (uint32_t)stage * stage_bytes, kb * BK, m_t * BM);
           const uint32_t sb = base + (uint32_t)stage * stage_bytes + 2u * A_TILE;
           tma_load_2d(&tmB, full_bar(stage), sb, kb * BK, n_t * p.BN);
-          tma_load_2d(&tmBlo, full_bar(stage), sb + b_tile, kb * BK, n_t * p.BN);
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -235,6 +234,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(full_bar(stage), phase);
         const uint32_t sa = base + (uint32_t)stage * stage_bytes;
         lo_image<8>(sa, sa + A_TILE, A_TILE / 16, (uint32_t)lt, 128u);
+        lo_image<5>(sa + 2u * A_TILE, sa + 2u * A_TILE + b_tile, b_tile / 16, (uint32_t)lt, 128u);     // weight remainder too:
+        // every CTA re-reads the weight tile from L2 (60 row tiles x the whole matrix), so not fetching a second image of
+        // it takes a third off the kernel's L2 traffic
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready_bar(stage));
