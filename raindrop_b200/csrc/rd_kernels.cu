@@ -311,7 +311,10 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 // partial row [2][D] per CTA (summed later in a fixed order).  128-bit accesses (D % 4 == 0).
 constexpr int LNB_ROWS = 32;    // rows per CTA (4 per warp: enough CTAs to fill the SMs at B = 128)
 constexpr int LNB_MAXIT = 5;    // D <= 640
-__global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(
+// ITERS float4 per lane and row (D <= 128 * ITERS); RB rows of a warp are in flight together: their loads are all issued
+// before the first reduction, so a warp pays one memory round trip for RB rows instead of RB dependent ones.
+template <int ITERS, int RB>
+__global__ void __launch_bounds__(256, 2) layernorm_bwd_fused_kernel(
     const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ dy, long long rows, int D, float* __restrict__ dx, float* __restrict__ dx_drop,
     float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial) {
@@ -320,54 +323,73 @@ __global__ void __launch_bounds__(256) layernorm_bwd_fused_kernel(
   extern __shared__ float lsm[];                     // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  float4 ag[LNB_MAXIT], ab[LNB_MAXIT];
+  float4 ag[ITERS], ab[ITERS], g4[ITERS];
 #pragma unroll
-  for (int it = 0; it < LNB_MAXIT; ++it) { ag[it] = make_float4(0.f, 0.f, 0.f, 0.f); ab[it] = ag[it]; }
+  for (int it = 0; it < ITERS; ++it) {
+    ag[it] = make_float4(0.f, 0.f, 0.f, 0.f); ab[it] = ag[it];
+    const int j = 4 * lane + 128 * it;
+    g4[it] = j < D ? __ldg(reinterpret_cast<const float4*>(gamma + j)) : ag[it];
+  }
   const long long r0 = (long long)blockIdx.x * LNB_ROWS;
-  for (int rr = warp; rr < LNB_ROWS; rr += 8) {
-    const long long row = r0 + rr;
-    if (row >= rows) break;
-    const float* xr = x + row * D;
-    const float* dyr = dy + row * D;
-    const float mean = stats[2 * row], rstd = stats[2 * row + 1];
-    float4 d4[LNB_MAXIT], xh[LNB_MAXIT], g4[LNB_MAXIT];
-    float s1 = 0.f, s2 = 0.f;
+  for (int rr = warp; rr < LNB_ROWS; rr += 8 * RB) {
+    float4 d4[RB][ITERS], xh[RB][ITERS];
+    float rstd[RB], s1[RB], s2[RB];
 #pragma unroll
-    for (int it = 0; it < LNB_MAXIT; ++it) {
-      const int j = 4 * lane + 128 * it;
-      if (j < D) {
-        d4[it] = *reinterpret_cast<const float4*>(dyr + j);
-        const float4 x4 = *reinterpret_cast<const float4*>(xr + j);
-        g4[it] = __ldg(reinterpret_cast<const float4*>(gamma + j));
-        xh[it] = make_float4((x4.x - mean) * rstd, (x4.y - mean) * rstd, (x4.z - mean) * rstd, (x4.w - mean) * rstd);
-        s1 += d4[it].x * g4[it].x + d4[it].y * g4[it].y + d4[it].z * g4[it].z + d4[it].w * g4[it].w;
-        s2 += d4[it].x * g4[it].x * xh[it].x + d4[it].y * g4[it].y * xh[it].y + d4[it].z * g4[it].z * xh[it].z +
-              d4[it].w * g4[it].w * xh[it].w;
+    for (int k = 0; k < RB; ++k) {
+      const long long row = r0 + rr + 8 * k;
+      const bool ok = row < rows;
+      const float mean = ok ? stats[2 * row] : 0.f;
+      rstd[k] = ok ? stats[2 * row + 1] : 0.f;
+      s1[k] = 0.f; s2[k] = 0.f;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int j = 4 * lane + 128 * it;
+        d4[k][it] = make_float4(0.f, 0.f, 0.f, 0.f); xh[k][it] = d4[k][it];
+        if (ok && j < D) {
+          d4[k][it] = *reinterpret_cast<const float4*>(dy + row * D + j);
+          const float4 x4 = *reinterpret_cast<const float4*>(x + row * D + j);
+          xh[k][it] = make_float4((x4.x - mean) * rstd[k], (x4.y - mean) * rstd[k], (x4.z - mean) * rstd[k], (x4.w - mean) * rstd[k]);
+        }
       }
     }
-    s1 = warp_sum(s1) / (float)D;
-    s2 = warp_sum(s2) / (float)D;
 #pragma unroll
-    for (int it = 0; it < LNB_MAXIT; ++it) {
-      const int j = 4 * lane + 128 * it;
-      if (j < D) {
-        float4 o;
-        o.x = rstd * (d4[it].x * g4[it].x - s1 - xh[it].x * s2);
-        o.y = rstd * (d4[it].y * g4[it].y - s1 - xh[it].y * s2);
-        o.z = rstd * (d4[it].z * g4[it].z - s1 - xh[it].z * s2);
-        o.w = rstd * (d4[it].w * g4[it].w - s1 - xh[it].w * s2);
-        *reinterpret_cast<float4*>(dx + row * D + j) = o;
-        if (dx_drop) {
-          const float4 m = dropout_scale4(rng, site, (uint64_t)row * D + j, drop_p, ik);
-          *reinterpret_cast<float4*>(dx_drop + row * D + j) = make_float4(o.x * m.x, o.y * m.y, o.z * m.z, o.w * m.w);
+    for (int k = 0; k < RB; ++k) {
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const float4 d = d4[k][it], g = g4[it], h = xh[k][it];
+        s1[k] += d.x * g.x + d.y * g.y + d.z * g.z + d.w * g.w;
+        s2[k] += d.x * g.x * h.x + d.y * g.y * h.y + d.z * g.z * h.z + d.w * g.w * h.w;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < RB; ++k) { s1[k] = warp_sum(s1[k]) / (float)D; s2[k] = warp_sum(s2[k]) / (float)D; }
+#pragma unroll
+    for (int k = 0; k < RB; ++k) {
+      const long long row = r0 + rr + 8 * k;
+      if (row >= rows) continue;
+#pragma unroll
+      for (int it = 0; it < ITERS; ++it) {
+        const int j = 4 * lane + 128 * it;
+        if (j < D) {
+          const float4 d = d4[k][it], g = g4[it], h = xh[k][it];
+          float4 o;
+          o.x = rstd[k] * (d.x * g.x - s1[k] - h.x * s2[k]);
+          o.y = rstd[k] * (d.y * g.y - s1[k] - h.y * s2[k]);
+          o.z = rstd[k] * (d.z * g.z - s1[k] - h.z * s2[k]);
+          o.w = rstd[k] * (d.w * g.w - s1[k] - h.w * s2[k]);
+          *reinterpret_cast<float4*>(dx + row * D + j) = o;
+          if (dx_drop) {
+            const float4 m = dropout_scale4(rng, site, (uint64_t)row * D + j, drop_p, ik);
+            *reinterpret_cast<float4*>(dx_drop + row * D + j) = make_float4(o.x * m.x, o.y * m.y, o.z * m.z, o.w * m.w);
+          }
+          ag[it].x += d.x * h.x; ag[it].y += d.y * h.y; ag[it].z += d.z * h.z; ag[it].w += d.w * h.w;
+          ab[it].x += d.x; ab[it].y += d.y; ab[it].z += d.z; ab[it].w += d.w;
         }
-        ag[it].x += d4[it].x * xh[it].x; ag[it].y += d4[it].y * xh[it].y; ag[it].z += d4[it].z * xh[it].z; ag[it].w += d4[it].w * xh[it].w;
-        ab[it].x += d4[it].x; ab[it].y += d4[it].y; ab[it].z += d4[it].z; ab[it].w += d4[it].w;
       }
     }
   }
 #pragma unroll
-  for (int it = 0; it < LNB_MAXIT; ++it) {
+  for (int it = 0; it < ITERS; ++it) {
     const int j = 4 * lane + 128 * it;
     if (j < D) {
       *reinterpret_cast<float4*>(lsm + (warp * 2) * D + j) = ag[it];
@@ -737,7 +759,8 @@ int layernorm_bwd(const float* x, const float* stats, const float* gamma, const 
   int chunks;
   if ((D & 3) == 0 && D <= 128 * LNB_MAXIT && (bits & 15) == 0) {     // fused single pass
     chunks = (int)ceil_div(rows, LNB_ROWS);
-    launch_pdl(layernorm_bwd_fused_kernel, dim3(chunks), dim3(256), 8 * 2 * D * sizeof(float), st, x, stats, gamma, dy, (long long)rows, D,
+    auto kern = D <= 128 ? layernorm_bwd_fused_kernel<1, 4> : (D <= 256 ? layernorm_bwd_fused_kernel<2, 4> : layernorm_bwd_fused_kernel<LNB_MAXIT, 1>);
+    launch_pdl(kern, dim3(chunks), dim3(256), 8 * 2 * D * sizeof(float), st, x, stats, gamma, dy, (long long)rows, D,
                dx, drop_p > 0.f ? dx_drop : (float*)nullptr, drop_p, rng, site, scratch);
     RD_CHECK_LAUNCH("layernorm_bwd_fused_kernel");
   } else {

@@ -100,10 +100,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int n_t = tile % p.n_tiles, m_t = tile / p.n_tiles;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
           mbar_wait(empty_bar(stage), phase ^ 1u);
-          mbar_expect_tx(full_bar(stage), (uint32_t)A_TILE + b_tile);
+          mbar_expect_tx(full_bar(stage), (uint32_t)A_TILE + 2u * b_tile);
           tma_load_2d(&tmA, full_bar(stage), base + (uint32_t)stage * stage_bytes, kb * BK, m_t * BM);
           const uint32_t sb = base + (uint32_t)stage * stage_bytes + 2u * A_TILE;
           tma_load_2d(&tmB, full_bar(stage), sb, kb * BK, n_t * p.BN);
+          tma_load_2d(&tmBlo, full_bar(stage), sb + b_tile, kb * BK, n_t * p.BN);     // (deriving it on chip like A_lo was slower:
+          // the remainder pass, not L2, paces the k-loop -- 0.73 vs 0.56 us per k-block)
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -234,9 +236,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         mbar_wait(full_bar(stage), phase);
         const uint32_t sa = base + (uint32_t)stage * stage_bytes;
         lo_image<8>(sa, sa + A_TILE, A_TILE / 16, (uint32_t)lt, 128u);
-        lo_image<5>(sa + 2u * A_TILE, sa + 2u * A_TILE + b_tile, b_tile / 16, (uint32_t)lt, 128u);     // weight remainder too:
-        // every CTA re-reads the weight tile from L2 (60 row tiles x the whole matrix), so not fetching a second image of
-        // it takes a third off the kernel's L2 traffic
         fence_async_smem();
         __syncwarp();
         if (lane == 0) mbar_arrive(ready_bar(stage));
@@ -271,14 +270,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // plant the "ones" column that makes the bias gradient fall out of the same MMAs.
 struct WP {
   float* partial;                    // [nsplit][Mpad][Nld]
-  long long rows; int M, N, BN, n_tiles, m_tiles, nsplit, rows_per_split, nstages, Mpad, Nld;
-  int cta0;                          // first CTA of this problem inside the grouped grid
+  long long rows; int M, N, BN, n_tiles, m_tiles, nsplit, rows_per_split, Mpad, Nld;
+  int item0;                         // first work item of this problem inside the grouped list
 };
-struct WGroup { CUtensorMap tmA[WG_MAX]; CUtensorMap tmB[WG_MAX]; WP it[WG_MAX]; int n; };
+struct WGroup { CUtensorMap tmA[WG_MAX]; CUtensorMap tmB[WG_MAX]; WP it[WG_MAX]; int n, total_items, nstages, stage_bytes; };
 
-constexpr int W_THREADS = 192;       // warp 0 TMA, warp 1 MMA, warps 2-5 remainder pass + epilogue
+// PERSISTENT: one CTA per SM walks the work items (problem, m tile, n tile, row split) round-robin.  The accumulator is
+// double-buffered in tensor memory (2 x 256 columns), so the epilogue of item i (TMEM -> partial slab, 80 KB of stores)
+// overlaps the MMAs of item i+1, and the TMA ring runs ahead across item boundaries.  One CTA per item (the previous
+// design) paid prologue + pipeline fill + epilogue serially per item and ran 3.1 waves as 4.
+constexpr int W_THREADS = 320;       // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-9 remainder pass
 constexpr int MN_BOX = 32 * 32 * 4;  // one {32 col, 32 row} fp32 box = 4096 bytes
 
+struct WItem { int pi, n_t, m_t, split, k_blocks; long long r_begin, r_end; };
+__device__ __forceinline__ WItem wgrad_item(const WGroup& g, int w) {
+  WItem it;
+  it.pi = 0;
+#pragma unroll 1
+  for (int k = 1; k < g.n; ++k) if (w >= g.it[k].item0) it.pi = k;
+  const WP& p = g.it[it.pi];
+  const int item = w - p.item0;
+  it.n_t = item % p.n_tiles; it.m_t = (item / p.n_tiles) % p.m_tiles; it.split = item / (p.n_tiles * p.m_tiles);
+  it.r_begin = (long long)it.split * p.rows_per_split;
+  it.r_end = min(p.rows, it.r_begin + p.rows_per_split);
+  it.k_blocks = (int)((it.r_end - it.r_begin + BK - 1) / BK);
+  return it;
+}
 
 __global__ void __launch_bounds__(W_THREADS, 1)
 tc_wgrad_kernel(const __grid_constant__ WGroup g) {
@@ -286,41 +303,31 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
   pdl_launch_dependents();
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  int pi = 0;
-#pragma unroll 1
-  for (int k = 1; k < g.n; ++k) if ((int)blockIdx.x >= g.it[k].cta0) pi = k;
-  const WP& p = g.it[pi];
-  const uint32_t b_tile = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;      // A hi | A lo | B hi | B lo
-  const uint32_t bar_base = base + (uint32_t)p.nstages * stage_bytes;
+  const uint32_t stage_bytes = (uint32_t)g.stage_bytes;        // sized for the widest problem of the group
+  const int nstages = g.nstages;
+  const uint32_t bar_base = base + (uint32_t)nstages * stage_bytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };                    // TMA bytes landed
   auto ready_bar = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };    // remainders written
   auto empty_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };// MMAs have read the stage
-  const uint32_t tfull_bar = bar_base + 8u * (3 * MAX_STAGES);
-  const uint32_t tmem_slot = bar_base + 8u * (3 * MAX_STAGES + 1);
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (3 * MAX_STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (3 * MAX_STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (3 * MAX_STAGES + 4);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
-  // work item of this CTA: (split, m tile, n tile)
-  const int item = (int)blockIdx.x - p.cta0;
-  const int n_t = item % p.n_tiles, m_t = (item / p.n_tiles) % p.m_tiles, split = item / (p.n_tiles * p.m_tiles);
-  const long long r_begin = (long long)split * p.rows_per_split;
-  const long long r_end = min(p.rows, r_begin + p.rows_per_split);
-  const int k_blocks = (int)((r_end - r_begin + BK - 1) / BK);
-  const int nstages = p.nstages;
-  const int b_groups = p.BN >> 5;                       // 32-column groups of the B tile
-
   if (warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmA[pi]) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmB[pi]) : "memory");
+    for (int k = 0; k < g.n; ++k) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmA[k]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&g.tmB[k]) : "memory");
+    }
   }
   if (warp == 1) {
     if (lane == 0) {
       for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 4); mbar_init(empty_bar(s), 1); }
-      mbar_init(tfull_bar, 1);
+      for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(tmem_slot) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(tmem_slot) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   tc_fence_before();
@@ -333,57 +340,105 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
     // ===== TMA producer: raw row-major tiles, up to `nstages` k-blocks in flight ======================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(empty_bar(stage), phase ^ 1u);
-        mbar_expect_tx(full_bar(stage), (uint32_t)(4 + b_groups) * MN_BOX);
-        const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-        const int r0 = (int)(r_begin + (long long)kb * BK);
+      for (int w = blockIdx.x; w < g.total_items; w += gridDim.x) {
+        const WItem it = wgrad_item(g, w);
+        const WP& p = g.it[it.pi];
+        const int b_groups = p.BN >> 5;                       // 32-column groups of the B tile
+        for (int kb = 0; kb < it.k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          mbar_expect_tx(full_bar(stage), (uint32_t)(4 + b_groups) * MN_BOX);
+          const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+          const int r0 = (int)(it.r_begin + (long long)kb * BK);
 #pragma unroll
-        for (int gq = 0; gq < 4; ++gq) tma_load_2d(&g.tmA[pi], full_bar(stage), sa + gq * MN_BOX, m_t * BM + gq * 32, r0);
-        for (int gq = 0; gq < b_groups; ++gq)
-          tma_load_2d(&g.tmB[pi], full_bar(stage), sa + 2u * A_TILE + gq * MN_BOX, n_t * p.BN + gq * 32, r0);
-        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+          for (int gq = 0; gq < 4; ++gq) tma_load_2d(&g.tmA[it.pi], full_bar(stage), sa + gq * MN_BOX, it.m_t * BM + gq * 32, r0);
+          for (int gq = 0; gq < b_groups; ++gq)
+            tma_load_2d(&g.tmB[it.pi], full_bar(stage), sa + 2u * A_TILE + gq * MN_BOX, it.n_t * p.BN + gq * 32, r0);
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
+        }
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer ================================================================================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |     // MN-major A and B
-                             ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int stage = 0; uint32_t phase = 0;
-      for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(ready_bar(stage), phase);
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      for (int w = blockIdx.x; w < g.total_items; w += gridDim.x) {
+        const WItem it = wgrad_item(g, w);
+        const WP& p = g.it[it.pi];
+        const uint32_t b_tile = (uint32_t)p.BN * 128u;
+        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |     // MN-major A and B
+                               ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-        const uint64_t a_hi = umma_desc_mn_sw128(sa, MN_BOX), a_lo = umma_desc_mn_sw128(sa + A_TILE, MN_BOX);
-        const uint64_t b_hi = umma_desc_mn_sw128(sa + 2u * A_TILE, MN_BOX), b_lo = umma_desc_mn_sw128(sa + 2u * A_TILE + b_tile, MN_BOX);
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        for (int kb = 0; kb < it.k_blocks; ++kb) {
+          mbar_wait(ready_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = base + (uint32_t)stage * stage_bytes;
+          const uint64_t a_hi = umma_desc_mn_sw128(sa, MN_BOX), a_lo = umma_desc_mn_sw128(sa + A_TILE, MN_BOX);
+          const uint64_t b_hi = umma_desc_mn_sw128(sa + 2u * A_TILE, MN_BOX), b_lo = umma_desc_mn_sw128(sa + 2u * A_TILE + b_tile, MN_BOX);
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk) {
-          const uint64_t o = (uint64_t)(kk * 64);            // next 8-row K group: +1024 bytes
-          umma_tf32(tmem_base, a_lo + o, b_hi + o, idesc, (kb | kk) ? 1u : 0u);
-          umma_tf32(tmem_base, a_hi + o, b_lo + o, idesc, 1u);
-          umma_tf32(tmem_base, a_hi + o, b_hi + o, idesc, 1u);
+          for (int kk = 0; kk < BK / 8; ++kk) {
+            const uint64_t o = (uint64_t)(kk * 64);            // next 8-row K group: +1024 bytes
+            umma_tf32(d_tmem, a_lo + o, b_hi + o, idesc, (kb | kk) ? 1u : 0u);
+            umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
+            umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1u);
+          }
+          umma_commit(empty_bar(stage));
+          if (++stage == nstages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(empty_bar(stage));
-        if (++stage == nstages) { stage = 0; phase ^= 1u; }
+        umma_commit(tfull_bar(acc));
+        acc ^= 1; if (acc == 0) acc_phase ^= 1u;
       }
-      umma_commit(tfull_bar);
+    }
+  } else if (warp < 6) {
+    // ===== epilogue: accumulator tile -> partial slab (each lane owns one row: 128-byte runs) ===========
+    const int q = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int w = blockIdx.x; w < g.total_items; w += gridDim.x) {
+      const WItem it = wgrad_item(g, w);
+      const WP& p = g.it[it.pi];
+      const int n_chunks = (p.BN + 31) / 32;
+      float* prow = p.partial + ((long long)it.split * p.Mpad + it.m_t * BM + q * 32 + lane) * p.Nld + it.n_t * p.BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        uint32_t v[32];
+        if (it.k_blocks > 0) {
+          tmem_ld32(tmem_base + (uint32_t)acc * 256u + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
+        } else {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = 0u;
+        }
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+          const int c = ch * 32 + 4 * j4;
+          if (c < p.BN)
+            *reinterpret_cast<uint4*>(prow + c) = make_uint4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      acc ^= 1; if (acc == 0) acc_phase ^= 1u;
     }
   } else {
-    // ===== warps 2-5: remainder pass per k-block, then the epilogue ====================================
-    const int lt = threadIdx.x - 64;            // 0..127
-    {
-      int stage = 0; uint32_t phase = 0;
-      const int ones_col = p.N - n_t * p.BN;    // tile-local column of the implicit ones column (bias gradient)
+    // ===== warps 6-9: remainder pass per k-block (+ the implicit ones column of the bias gradient) ========
+    const int lt = threadIdx.x - 192;            // 0..127
+    int stage = 0; uint32_t phase = 0;
+    for (int w = blockIdx.x; w < g.total_items; w += gridDim.x) {
+      const WItem it = wgrad_item(g, w);
+      const WP& p = g.it[it.pi];
+      const uint32_t b_tile = (uint32_t)p.BN * 128u;
+      const int ones_col = p.N - it.n_t * p.BN;    // tile-local column of the implicit ones column (bias gradient)
       const bool has_ones = ones_col >= 0 && ones_col < p.BN;
       const uint32_t a_vec = A_TILE / 16, b_vec = b_tile / 16;
-      for (int kb = 0; kb < k_blocks; ++kb) {
+      for (int kb = 0; kb < it.k_blocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
         const uint32_t sa = base + (uint32_t)stage * stage_bytes;
         if (has_ones && lt < BK) {             // X[r, N] := 1 for the valid rows of this k-block (OOB columns arrived as 0)
-          const long long r = r_begin + (long long)kb * BK + lt;
+          const long long r = it.r_begin + (long long)kb * BK + lt;
           const uint32_t off = (uint32_t)((ones_col >> 5) * MN_BOX) + mn_sw_offset(lt, (ones_col & 31) >> 2) + (uint32_t)(ones_col & 3) * 4u;
-          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 2u * A_TILE + off), "f"(r < r_end ? 1.f : 0.f) : "memory");
+          asm volatile("st.shared.f32 [%0], %1;" ::"r"(sa + 2u * A_TILE + off), "f"(r < it.r_end ? 1.f : 0.f) : "memory");
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");
         lo_image<6>(sa, sa + A_TILE, a_vec, (uint32_t)lt, 128u);                              // dY tile
@@ -394,33 +449,12 @@ tc_wgrad_kernel(const __grid_constant__ WGroup g) {
         if (++stage == nstages) { stage = 0; phase ^= 1u; }
       }
     }
-    // ----- epilogue: accumulator tile -> partial buffer (each lane owns one row: 128-byte runs) -------
-    const int q = warp & 3;
-    const int n_chunks = (p.BN + 31) / 32;
-    float* prow = p.partial + ((long long)split * p.Mpad + m_t * BM + q * 32 + lane) * p.Nld + n_t * p.BN;
-    mbar_wait(tfull_bar, 0);
-    tc_fence_after();
-    for (int ch = 0; ch < n_chunks; ++ch) {
-      uint32_t v[32];
-      if (k_blocks > 0) {
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ch * 32), v);
-      } else {
-#pragma unroll
-        for (int e = 0; e < 32; ++e) v[e] = 0u;
-      }
-#pragma unroll
-      for (int j4 = 0; j4 < 8; ++j4) {
-        const int c = ch * 32 + 4 * j4;
-        if (c < p.BN)
-          *reinterpret_cast<uint4*>(prow + c) = make_uint4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-      }
-    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem_base) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
   }
 }
 
@@ -463,7 +497,9 @@ __global__ void wgrad_reduce_kernel(const __grid_constant__ RGroup g) {
 }
 
 struct WPlan { int BN, n_tiles, m_tiles, nsplit, rows_per_split, Mpad, Nld; };
-WPlan wgrad_plan(int M, int N, long long rows) {
+// `rows_target`: contraction rows per work item.  512 sizes the partial buffers (the CAPACITY in row splits); the grouped
+// launch may raise it so that the item count of the whole group fills whole rounds of the persistent grid.
+WPlan wgrad_plan(int M, int N, long long rows, int rows_target = 512) {
   WPlan w;
   w.m_tiles = (int)ceil_div(M, BM);
   w.Mpad = w.m_tiles * BM;
@@ -471,10 +507,10 @@ WPlan wgrad_plan(int M, int N, long long rows) {
   w.n_tiles = (int)ceil_div(Ncols, MAX_BN);
   w.BN = (int)round_up(ceil_div(Ncols, w.n_tiles), 32);     // whole 32-column TMA boxes
   w.Nld = (int)round_up(w.n_tiles * w.BN, 4);
-  // row splits: ~512 rows (16 k-blocks) per CTA so the pipeline amortises its fill, but never more than
-  // ~2 waves of CTAs per problem (bounds the partial buffer for the big configurations)
+  // row splits: ~512 rows (16 k-blocks) per item so the pipeline amortises its fill, but never more than
+  // ~2 rounds of items per problem (bounds the partial buffer for the big configurations)
   const int mn = w.m_tiles * w.n_tiles;
-  long long ns = ceil_div(rows, 512);
+  long long ns = ceil_div(rows, rows_target);
   const long long cap = (2 * num_sms()) / mn > 1 ? (2 * num_sms()) / mn : 1;
   if (ns > cap) ns = cap;
   if (ns < 1) ns = 1;
@@ -619,7 +655,22 @@ int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs,
   WGroup g;
   RGroup r;
   g.n = n; r.n = n + (ncs > 0 ? ncs : 0);
-  int cta = 0, smem_bytes = 0;
+  // rows per work item: the smallest target >= 512 for which the group's item count fills whole rounds of the grid
+  auto count_items = [&](int target) {
+    long long t = 0;
+    for (int i = 0; i < n; ++i) { const WPlan w = wgrad_plan(items[i].Nout, items[i].Kin, items[i].rows, target); t += (long long)w.nsplit * w.m_tiles * w.n_tiles; }
+    return t;
+  };
+  int target = 512;
+  if (n > 0) {
+    const long long sms = num_sms(), t0 = count_items(512);
+    if (t0 > sms && t0 % sms) {
+      const long long goal = (t0 / sms) * sms;
+      for (int t = 544; t <= 1024; t += 32)
+        if (count_items(t) <= goal) { target = t; break; }
+    }
+  }
+  int item = 0, max_bn = 32;
   long long tot = 0;
   for (int i = 0; i < n; ++i) {
     const WgradItem& a = items[i];
@@ -628,7 +679,7 @@ int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs,
       set_error("tc_wgrad_group: problem %d has an unsupported shape/alignment", i);
       return -2;
     }
-    const WPlan w = wgrad_plan(a.Nout, a.Kin, a.rows);
+    const WPlan w = wgrad_plan(a.Nout, a.Kin, a.rows, target);
     WP& p = g.it[i];
     p.partial = a.partial;
     p.rows = a.rows; p.M = a.Nout; p.N = a.Kin;
@@ -641,22 +692,23 @@ int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs,
     }
     p.BN = w.BN; p.n_tiles = w.n_tiles; p.m_tiles = w.m_tiles; p.nsplit = w.nsplit; p.rows_per_split = w.rows_per_split;
     p.Mpad = w.Mpad; p.Nld = w.Nld;
-    const int stage_bytes = 2 * A_TILE + 2 * p.BN * 128;
-    const int fixed = 1024 + 256;
-    p.nstages = (SMEM_LIMIT - fixed) / stage_bytes;
-    if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
-    if (p.nstages < 2) { set_error("tc_wgrad_group: not enough shared memory"); return -2; }
+    if (p.BN > max_bn) max_bn = p.BN;
     if (a.rows > 0x7fffffffLL) { set_error("tc_wgrad_group: too many rows"); return -2; }
-    const int sb = fixed + p.nstages * stage_bytes;
-    if (sb > smem_bytes) smem_bytes = sb;
-    p.cta0 = cta;
-    cta += w.nsplit * w.m_tiles * w.n_tiles;
+    p.item0 = item;
+    item += w.nsplit * w.m_tiles * w.n_tiles;
     RItem& q = r.it[i];
     q.partial = a.partial; q.dW = a.dW; q.db = a.db; q.nsplit = w.nsplit; q.M = a.Nout; q.N = a.Kin; q.Mpad = w.Mpad; q.Nld = w.Nld;
     q.kind = 0; q.stride = 0;
     q.start = tot;
     tot += (long long)a.Nout * (a.Kin + 1);
   }
+  g.total_items = item;
+  g.stage_bytes = 2 * A_TILE + 2 * max_bn * 128;
+  const int fixed = 1024 + 256;
+  g.nstages = (SMEM_LIMIT - fixed) / g.stage_bytes;
+  if (g.nstages > MAX_STAGES) g.nstages = MAX_STAGES;
+  if (n > 0 && g.nstages < 2) { set_error("tc_wgrad_group: not enough shared memory"); return -2; }
+  const int smem_bytes = fixed + g.nstages * g.stage_bytes;
   for (int i = 0; i < ncs; ++i) {
     RItem& q = r.it[n + i];
     q.partial = cs[i].partial; q.dW = cs[i].out; q.db = nullptr; q.nsplit = cs[i].nsplit; q.M = 1; q.N = cs[i].ncols;
@@ -668,7 +720,8 @@ int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs,
   r.total = tot;
   if (n > 0) {
     RD_TRY(ensure_attr((const void*)tc_wgrad_kernel, 15));
-    launch_pdl(tc_wgrad_kernel, dim3(cta), dim3(W_THREADS), smem_bytes, st, g);
+    const int grid = item < num_sms() ? item : num_sms();
+    launch_pdl(tc_wgrad_kernel, dim3(grid), dim3(W_THREADS), smem_bytes, st, g);
     RD_CHECK_LAUNCH("tc_wgrad_kernel");
   }
   launch_pdl(wgrad_reduce_kernel, dim3((unsigned)ceil_div(tot, 256)), dim3(256), 0, st, r);
