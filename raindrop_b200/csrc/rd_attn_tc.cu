@@ -55,9 +55,8 @@ struct AttnTcP {
 
 __device__ __forceinline__ void stamp(const AttnTcP& p, int slot) {
   if (p.dbg && threadIdx.x == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    p.dbg[(size_t)blockIdx.x * 16 + slot] = t;
+    // SM cycle counter: a %globaltimer read costs 0.25-0.5 us (and ticks every 256 ns), which perturbed what it measured
+    p.dbg[(size_t)blockIdx.x * 16 + slot] = (unsigned long long)clock64();
   }
 }
 
@@ -130,34 +129,38 @@ __device__ __forceinline__ void store_chunk_mn(uint32_t hi, uint32_t lo, int i, 
 }
 
 // keep/scale factors (0 or 1/(1-p)) of the attention-dropout decisions (i, 4c..4c+3): index space [B, H, T, T]
-__device__ __forceinline__ float4 mask4(const AttnTcP& p, uint64_t row_base, int c, float ik) {
+__device__ __forceinline__ float4 mask4(const AttnTcP& p, const RngKey& key, uint64_t row_base, int c, float ik) {
   if (p.drop_p <= 0.f) return make_float4(1.f, 1.f, 1.f, 1.f);
   if (4 * c >= p.T) return make_float4(0.f, 0.f, 0.f, 0.f);
-  if ((p.T & 3) == 0) return dropout_scale4(p.rng, p.site, row_base + 4 * c, p.drop_p, ik);     // row_base % 4 == 0
+  if ((p.T & 3) == 0) return dropout_scale4(key, p.site, row_base + 4 * c, p.drop_p, ik);     // row_base % 4 == 0
   float4 q;
-  q.x = dropout_scale(p.rng, p.site, row_base + 4 * c, p.drop_p, ik);
-  q.y = 4 * c + 1 < p.T ? dropout_scale(p.rng, p.site, row_base + 4 * c + 1, p.drop_p, ik) : 0.f;
-  q.z = 4 * c + 2 < p.T ? dropout_scale(p.rng, p.site, row_base + 4 * c + 2, p.drop_p, ik) : 0.f;
-  q.w = 4 * c + 3 < p.T ? dropout_scale(p.rng, p.site, row_base + 4 * c + 3, p.drop_p, ik) : 0.f;
+  q.x = dropout_scale(key, p.site, row_base + 4 * c, p.drop_p, ik);
+  q.y = 4 * c + 1 < p.T ? dropout_scale(key, p.site, row_base + 4 * c + 1, p.drop_p, ik) : 0.f;
+  q.z = 4 * c + 2 < p.T ? dropout_scale(key, p.site, row_base + 4 * c + 2, p.drop_p, ik) : 0.f;
+  q.w = 4 * c + 3 < p.T ? dropout_scale(key, p.site, row_base + 4 * c + 3, p.drop_p, ik) : 0.f;
   return q;
 }
 
-// Attention-dropout keep bits of row r = threadIdx.x - 64 (warps 2, 3), computed while the tiles are still in flight:
-// the counter-based stream needs nothing but indices, and these warps have no accumulator rows to work on, so the
-// 16 Philox blocks per row leave the critical path of the softmax warps.  bit j of keep[r] = element (r, j) is kept.
-__device__ __forceinline__ void precompute_keep_bits(const AttnTcP& p, int b, int h, unsigned long long* keep) {
-  if (p.drop_p <= 0.f || threadIdx.x < 64) return;
-  const int r = threadIdx.x - 64;
+// Attention-dropout keep bits, computed by all 128 threads while the tiles are still in flight: the counter-based
+// stream needs nothing but indices.  Thread t covers row t & 63, columns 32*(t >> 6) .. +31 (8 Philox blocks, four
+// independent ones in flight: a fully rolled loop is one 10-round dependent chain after another and took 2.8 us, a
+// fully unrolled one is 1600 instructions of straight-line code).  bit j of keep[r] = element (r, j) is kept.
+__device__ __forceinline__ void precompute_keep_bits(const AttnTcP& p, const RngKey& key, int b, int h, unsigned long long* keep) {
+  if (p.drop_p <= 0.f) return;
+  const int r = threadIdx.x & 63, half = threadIdx.x >> 6;
   const uint64_t row_base = ((uint64_t)(b * p.H + h) * p.T + r) * p.T;
-  unsigned long long bits = 0ull;
+  uint32_t bits = 0u;
   if (r < p.T) {
-#pragma unroll 1        // rolled: 16 unrolled Philox blocks are 1600 instructions of straight-line code per CTA
-    for (int c = 0; c < 16; ++c) {
-      const float4 m = mask4(p, row_base, c, 1.f);
-      bits |= (unsigned long long)((m.x > 0.f ? 1u : 0u) | (m.y > 0.f ? 2u : 0u) | (m.z > 0.f ? 4u : 0u) | (m.w > 0.f ? 8u : 0u)) << (4 * c);
+#pragma unroll 1
+    for (int c0 = 0; c0 < 8; c0 += 4) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const float4 m = mask4(p, key, row_base, 8 * half + c0 + u, 1.f);
+        bits |= ((m.x > 0.f ? 1u : 0u) | (m.y > 0.f ? 2u : 0u) | (m.z > 0.f ? 4u : 0u) | (m.w > 0.f ? 8u : 0u)) << (4 * (c0 + u));
+      }
     }
   }
-  keep[r] = bits;
+  reinterpret_cast<uint32_t*>(keep)[2 * r + half] = bits;      // little-endian halves of the 64-bit row mask
 }
 
 // Row softmax in rolled passes over 16-column chunks of the accumulator row (re-read from TMEM each pass): the kernel
@@ -188,6 +191,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  const RngKey key = load_rng_key(p.drop_p > 0.f ? p.rng : nullptr);     // one read; in flight during the set-up
   const uint32_t QV = base, KP = base + 2u * TILE;
   const uint32_t bar = base + 4u * TILE;
   const uint32_t bar_qk = bar, bar_v = bar + 8, bar_s = bar + 16, bar_o = bar + 24, tmem_slot = bar + 32;
@@ -212,6 +216,12 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tO = tmem + 64;
   stamp(p, 0);
+  if (p.dbg_mode == 9 && threadIdx.x == 0) {      // experiment: a throw-away MMA while the tiles are still in flight
+    mbar_init(bar + 40, 1);
+    umma_tf32(tmem + 192, umma_desc_sw128(QV), umma_desc_sw128(KP), umma_idesc_tf32(128, 64, false, false), 0u);
+    umma_commit(bar + 40);
+  }
+  __syncwarp();
 
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_qk, 2u * TILE);
@@ -221,23 +231,28 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
       tma_load_5d(&tmQKV, bar_qk, KP + g * GRP, 32 * g, h, 1, b, 0);
     }
   }
-  precompute_keep_bits(p, b, h, keep);
+  precompute_keep_bits(p, key, b, h, keep);
   stamp(p, 1);
   mbar_wait(bar_qk, 0);
   stamp(p, 2);
-  lo_pass(QV, TILE, TILE);
-  lo_pass(KP, TILE, TILE);
-  fence_async_smem();
+  if (p.dbg_mode != 7) {
+    lo_pass(QV, TILE, TILE);
+    lo_pass(KP, TILE, TILE);
+    fence_async_smem();
+  }
   __syncthreads();
   stamp(p, 3);
   if (warp == 0) {
+    if (p.dbg_mode == 14) stamp(p, 13);
     tc_fence_after();
-    if (p.dbg_mode == 0) {
+    if (p.dbg_mode == 14) stamp(p, 14);
+    if (p.dbg_mode == 0 || p.dbg_mode == 9 || p.dbg_mode == 14) {
       mma3<false, false, 4 * NG>(tS, QV, TILE, KP, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
     } else if (lane == 0) {      // timing experiments on the S = Q K^T issue (results are wrong on purpose)
       const uint32_t id = umma_idesc_tf32(128, p.dbg_mode == 5 ? 128 : 64, false, false);
       const uint64_t ah = umma_desc_sw128(QV), al = umma_desc_sw128(QV + TILE), bh = umma_desc_sw128(KP), bl = umma_desc_sw128(KP + TILE);
       const int reps = p.dbg_mode == 3 ? 2 : 1;
+      if (p.dbg_mode == 13) stamp(p, 13);
       for (int r = 0; r < reps; ++r)
 #pragma unroll
         for (int ks = 0; ks < 10; ++ks) {
@@ -245,10 +260,14 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
           const uint32_t d = p.dbg_mode == 2 ? tS + 160u * (ks & 1) : (p.dbg_mode == 4 ? tS + 64u * (ks % 3) : tS);
           if (p.dbg_mode != 1) {
             umma_tf32(d, al + o, bh + o, id, ks ? 1u : 0u);
+            if (p.dbg_mode == 13 && ks == 0) stamp(p, 14);
             umma_tf32(d, ah + o, bl + o, id, 1u);
           }
           umma_tf32(d, ah + o, bh + o, id, 1u);
+          if (p.dbg_mode == 13 && ks == 0) stamp(p, 15);
+          if (p.dbg_mode >= 6 && (ks == 0 || ks == 4)) stamp(p, ks == 0 ? 13 : 14);
         }
+      if (p.dbg_mode >= 6) stamp(p, 15);
     }
   }
   if (threadIdx.x == 0) {
@@ -363,6 +382,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
+  const RngKey key = load_rng_key(p.drop_p > 0.f ? p.rng : nullptr);     // one read; in flight during the set-up
   constexpr uint32_t REG = 2u * TILE;                              // 48 KB: hi + lo image of one head slice
   const uint32_t R0 = base, R1 = base + REG, R2 = base + 2u * REG, R3 = base + 3u * REG;
   const uint32_t Pd = R0, Pd_lo = R0 + PT;                         // MN image
@@ -410,7 +430,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
       tma_load_4d(&tmDO, bar_gv, R3 + g * GRP, 32 * g, h, b, 0);
     }
   }
-  precompute_keep_bits(p, b, h, keep);
+  precompute_keep_bits(p, key, b, h, keep);
   mbar_wait(bar_qk, 0);
   stamp(p, 1);
   lo_pass(R0, TILE, TILE);

@@ -102,6 +102,34 @@ __device__ __forceinline__ float4 dropout_scale4(const uint64_t* __restrict__ rn
                      keep_scale(b.w, p, inv_keep));
 }
 
+// The same stream with the key held in registers: kernels that draw many blocks read (seed, step) from global memory
+// ONCE per thread -- a load inside every call is an L2 round trip on the critical path whenever the compiler cannot
+// hoist it (any "memory" clobber in between), which cost the attention kernels 2 us per CTA.
+struct RngKey { uint32_t k0, k1, c3; };
+__device__ __forceinline__ RngKey load_rng_key(const uint64_t* __restrict__ rng) {
+  RngKey k{0u, 0u, 0u};
+  if (rng) {
+    const uint64_t seed = rng[0], step = rng[1];
+    k.k0 = (uint32_t)seed; k.k1 = (uint32_t)(seed >> 32) ^ (uint32_t)(step >> 32); k.c3 = (uint32_t)step;
+  }
+  return k;
+}
+__device__ __forceinline__ uint4 dropout_block(const RngKey& k, uint32_t site, uint64_t idx) {
+  const uint64_t blk = idx >> 2;
+  return philox4(k.k0, k.k1, (uint32_t)blk, (uint32_t)(blk >> 32), site, k.c3);
+}
+__device__ __forceinline__ float dropout_scale(const RngKey& k, uint32_t site, uint64_t idx, float p, float inv_keep) {
+  const uint4 b = dropout_block(k, site, idx);
+  const uint32_t sel = (uint32_t)idx & 3u;
+  const uint32_t w = sel == 0 ? b.x : (sel == 1 ? b.y : (sel == 2 ? b.z : b.w));
+  return keep_scale(w, p, inv_keep);
+}
+__device__ __forceinline__ float4 dropout_scale4(const RngKey& k, uint32_t site, uint64_t idx, float p, float inv_keep) {
+  const uint4 b = dropout_block(k, site, idx);
+  return make_float4(keep_scale(b.x, p, inv_keep), keep_scale(b.y, p, inv_keep), keep_scale(b.z, p, inv_keep),
+                     keep_scale(b.w, p, inv_keep));
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

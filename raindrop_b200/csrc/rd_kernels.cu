@@ -323,6 +323,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_fused_kernel(
   extern __shared__ float lsm[];                     // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
+  const RngKey key = load_rng_key(dx_drop ? rng : nullptr);
   float4 ag[ITERS], ab[ITERS], g4[ITERS];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
@@ -379,7 +380,7 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_fused_kernel(
           o.w = rstd[k] * (d.w * g.w - s1[k] - h.w * s2[k]);
           *reinterpret_cast<float4*>(dx + row * D + j) = o;
           if (dx_drop) {
-            const float4 m = dropout_scale4(rng, site, (uint64_t)row * D + j, drop_p, ik);
+            const float4 m = dropout_scale4(key, site, (uint64_t)row * D + j, drop_p, ik);
             *reinterpret_cast<float4*>(dx_drop + row * D + j) = make_float4(o.x * m.x, o.y * m.y, o.z * m.z, o.w * m.w);
           }
           ag[it].x += d.x * h.x; ag[it].y += d.y * h.y; ag[it].z += d.z * h.z; ag[it].w += d.w * h.w;

@@ -149,6 +149,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0; uint32_t acc_phase = 0; int buf = 0;
     const int n_chunks = (p.BN + 31) / 32;
     const float ik = p.drop_p > 0.f ? 1.f / (1.f - p.drop_p) : 1.f;
+    const RngKey key = load_rng_key(DROP ? p.rng : nullptr);
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_t = tile / p.n_tiles, n_t = tile - m_t * p.n_tiles;
       const int col0 = n_t * p.BN;
@@ -201,7 +202,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             o[2] = g.z > 0.f ? o[2] * p.gate_scale : 0.f; o[3] = g.w > 0.f ? o[3] * p.gate_scale : 0.f;
           }
           if (DROP && ok) {   // row*N + c is a multiple of 4: one Philox block for the four columns
-            const float4 m = dropout_scale4(p.rng, p.drop_site, (uint64_t)row * (uint64_t)p.N + (uint64_t)c, p.drop_p, ik);
+            const float4 m = dropout_scale4(key, p.drop_site, (uint64_t)row * (uint64_t)p.N + (uint64_t)c, p.drop_p, ik);
             o[0] *= m.x; o[1] *= m.y; o[2] *= m.z; o[3] *= m.w;
           }
           if (RESID && ok) {

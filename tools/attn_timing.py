@@ -16,14 +16,13 @@ dbg = torch.zeros(B * H, 16, dtype=torch.int64, device="cuda")
 lib.rd_debug_attention_timing(dbg.data_ptr())
 run(); torch.cuda.synchronize()
 lib.rd_debug_attention_timing(None)
-d = dbg.cpu().double()
+d = dbg.cpu().double() / 1.965      # SM cycle counter (per-SM, not comparable across CTAs) -> ns at 1965 MHz
 t0 = d[:, 0].min()
 names = ["setup done", "keep bits", "Q,K landed", "lo(Q,K)+sync", "S issued", "S done", "softmax+P stored", "V landed", "lo(V)+sync", "O issued", "O done", "ctx stored", "exit"]
-print("kernel span %.2f us (first setup -> last exit)" % ((d[:, 12].max() - t0) / 1e3))
+print("per-CTA setup -> exit: median %.2f us, max %.2f us" % ((d[:, 12] - d[:, 0]).median() / 1e3, (d[:, 12] - d[:, 0]).max() / 1e3))
 for i, n in enumerate(names):
     col = d[:, i] - d[:, 0]
     print("%-18s median +%.2f us   (p10 %.2f, p90 %.2f)" % (n, col.median() / 1e3, col.quantile(0.1) / 1e3, col.quantile(0.9) / 1e3))
-print("CTA start offsets: median %.2f us, max %.2f us" % (((d[:, 0] - t0).median()) / 1e3, (d[:, 0] - t0).max() / 1e3))
 
 # ---- backward ----------------------------------------------------------------------------------------------
 dctx = torch.randn(T, B, D, device="cuda"); dqkv = torch.empty(T, B, 3 * D, device="cuda")
@@ -37,10 +36,10 @@ e0.record(); [runb() for _ in range(20)]; e1.record(); torch.cuda.synchronize()
 print("backward %.2f us per call (back to back)" % (e0.elapsed_time(e1) / 20 * 1e3))
 dbg = torch.zeros(B * H, 16, dtype=torch.int64, device="cuda")
 lib.rd_debug_attention_timing(dbg.data_ptr()); runb(); torch.cuda.synchronize(); lib.rd_debug_attention_timing(None)
-d = dbg.cpu().double(); t0 = d[:, 0].min()
+d = dbg.cpu().double() / 1.965; t0 = d[:, 0].min()
 names = ["setup done", "Q,K landed", "S issued", "dP issued", "S,dP done", "softmax/dS stored", "dO,K (MN) landed", "dV,dQ issued",
          "dV,dQ done; Q TMA", "dQ,dV stored", "Q (MN) landed", "dK issued", "dK stored"]
-print("backward kernel span %.2f us; CTA start offsets median %.2f max %.2f us" % ((d[:, 12].max() - t0) / 1e3, (d[:, 0] - t0).median() / 1e3, (d[:, 0] - t0).max() / 1e3))
+print("backward per-CTA setup -> dK stored: median %.2f us, max %.2f us" % ((d[:, 12] - d[:, 0]).median() / 1e3, (d[:, 12] - d[:, 0]).max() / 1e3))
 for i, n in enumerate(names):
     col = d[:, i] - d[:, 0]
     print("%-20s median +%.2f us   (p10 %.2f, p90 %.2f)" % (n, col.median() / 1e3, col.quantile(0.1) / 1e3, col.quantile(0.9) / 1e3))
