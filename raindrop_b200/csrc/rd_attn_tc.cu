@@ -60,6 +60,9 @@ __device__ __forceinline__ void stamp(const AttnTcP& p, int slot) {
   }
 }
 
+__device__ __forceinline__ void stamp_by(const AttnTcP& p, int slot, int tid) {
+  if (p.dbg && (int)threadIdx.x == tid) p.dbg[(size_t)blockIdx.x * 16 + slot] = (unsigned long long)clock64();
+}
 __device__ __forceinline__ float lo_of(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 
 // lo image (at +lo_off) of `bytes` bytes of hi image; same addresses, so the swizzle never has to be undone
@@ -323,11 +326,12 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
     }
     fence_async_smem();
     stamp(p, 6);
+  } else {      // warps 2, 3 meanwhile: remainder image of V (it lands during the softmax)
+    mbar_wait(bar_v, 0);
+    stamp_by(p, 7, 64);
+    lo_image<6>(QV, QV + TILE, TILE / 16u, threadIdx.x - 64u, 64u);
+    fence_async_smem();
   }
-  mbar_wait(bar_v, 0);
-  stamp(p, 7);
-  lo_pass(QV, TILE, TILE);
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   stamp(p, 8);
@@ -529,12 +533,13 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
     }
     fence_async_smem();
     stamp(p, 5);
+  } else {      // warps 2, 3 have no accumulator rows: they derive the remainder images of the MN tiles meanwhile
+    mbar_wait(bar_m1, 0);
+    stamp_by(p, 6, 64);
+    lo_image<6>(R2, R2 + TILE, TILE / 16u, threadIdx.x - 64u, 64u);
+    lo_image<6>(R3, R3 + TILE, TILE / 16u, threadIdx.x - 64u, 64u);
+    fence_async_smem();
   }
-  mbar_wait(bar_m1, 0);
-  stamp(p, 6);
-  lo_pass(R2, TILE, TILE);
-  lo_pass(R3, TILE, TILE);
-  fence_async_smem();
   tc_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -570,30 +575,28 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
       }
     }
   };
-  if (warp < 2) {                        // dQ and dV leave while Q is on its way
+  if (warp < 2) {                        // dQ and dV leave while warps 2, 3 prepare and issue the last product
     mbar_wait(bar_2, 0);
     __syncwarp();
     tc_fence_after();
     store_out(tDQ, 0);
     store_out(tDV, 2);
     stamp(p, 9);
+  } else {
+    // ---- phase 3: dK[j, d] = sum_i (scale dS)[i, j] Q[i, d] -------------------------------------------
+    mbar_wait(bar_m2, 0);
+    stamp_by(p, 10, 64);
+    lo_image<6>(R2, R2 + TILE, TILE / 16u, threadIdx.x - 64u, 64u);
+    fence_async_smem();
+    asm volatile("bar.sync 1, 64;" ::: "memory");      // warps 2 and 3
+    if (warp == 2) {
+      tc_fence_after();
+      mma3<true, true, 8>(tDK, dSm, dSm_lo - dSm, R2, TILE, 8, umma_idesc_tf32(128, 96, true, true));
+      if (lane == 0) umma_commit(bar_out);
+      stamp_by(p, 11, 64);
+      __syncwarp();
+    }
   }
-  // ---- phase 3: dK[j, d] = sum_i (scale dS)[i, j] Q[i, d] ---------------------------------------------
-  mbar_wait(bar_m2, 0);
-  stamp(p, 10);
-  lo_pass(R2, TILE, TILE);
-  fence_async_smem();
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tc_fence_after();
-    mma3<true, true, 8>(tDK, dSm, dSm_lo - dSm, R2, TILE, 8, umma_idesc_tf32(128, 96, true, true));
-  }
-  if (threadIdx.x == 0) {
-    umma_commit(bar_out);
-    stamp(p, 11);
-  }
-  __syncwarp();
   if (warp < 2) {
     mbar_wait(bar_out, 0);
     __syncwarp();
