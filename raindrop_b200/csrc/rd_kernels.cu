@@ -606,8 +606,19 @@ __global__ void cross_entropy_kernel(const float* __restrict__ logits, const int
 
 // One launch: every CTA reads the step count t (before anyone changes it), updates its slice with bias
 // corrections for t + 1, and the LAST CTA to finish stores t + 1 (ticket in step[1], self-resetting).
+__device__ __forceinline__ void adam_el(float& p, float g, float& m, float& v, float b1, float b2, float eps, float gscale,
+                                        float bc1, float bc2s, float lr) {
+  const float gi = g * gscale;
+  m = b1 * m + (1.f - b1) * gi;
+  v = b2 * v + (1.f - b2) * gi * gi;
+  const float denom = sqrtf(v) / bc2s + eps;
+  p -= (lr / bc1) * (m / denom);
+}
+// A few CTAs per SM stride over the flat buffers in 128-bit pieces (`vec`: all four pointers 16-byte aligned): the bias
+// corrections (two double-precision pow) and the ticket atomic are per CTA, and with one element per thread there were
+// ~2000 CTAs each paying them for 256 elements of work.
 __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                            float* __restrict__ v, long long n, float lr, const float* __restrict__ lr_dev, float b1,
+                            float* __restrict__ v, long long n, int vec, float lr, const float* __restrict__ lr_dev, float b1,
                             float b2, float eps, float gscale, int64_t* __restrict__ step) {
   pdl_launch_dependents();
   pdl_wait();
@@ -619,16 +630,19 @@ __global__ void adam_kernel(float* __restrict__ p, const float* __restrict__ g, 
     bc[2] = lr_dev ? *lr_dev : lr;
   }
   __syncthreads();
-  long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) {
-    float gi = g[i] * gscale;
-    float mi = b1 * m[i] + (1.f - b1) * gi;
-    float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
-    float denom = sqrtf(vi) / bc[1] + eps;
-    p[i] -= (bc[2] / bc[0]) * (mi / denom);
+  const float bc1 = bc[0], bc2s = bc[1], lrv = bc[2];
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, stride = (long long)gridDim.x * blockDim.x;
+  const long long n4 = vec ? n >> 2 : 0;
+  for (long long i = tid; i < n4; i += stride) {
+    float4 pp = reinterpret_cast<float4*>(p)[i], mm = reinterpret_cast<float4*>(m)[i], vv = reinterpret_cast<float4*>(v)[i];
+    const float4 gg = reinterpret_cast<const float4*>(g)[i];
+    adam_el(pp.x, gg.x, mm.x, vv.x, b1, b2, eps, gscale, bc1, bc2s, lrv);
+    adam_el(pp.y, gg.y, mm.y, vv.y, b1, b2, eps, gscale, bc1, bc2s, lrv);
+    adam_el(pp.z, gg.z, mm.z, vv.z, b1, b2, eps, gscale, bc1, bc2s, lrv);
+    adam_el(pp.w, gg.w, mm.w, vv.w, b1, b2, eps, gscale, bc1, bc2s, lrv);
+    reinterpret_cast<float4*>(p)[i] = pp; reinterpret_cast<float4*>(m)[i] = mm; reinterpret_cast<float4*>(v)[i] = vv;
   }
+  for (long long i = 4 * n4 + tid; i < n; i += stride) adam_el(p[i], g[i], m[i], v[i], b1, b2, eps, gscale, bc1, bc2s, lrv);
   __syncthreads();
   if (threadIdx.x == 0) {
     unsigned long long* ticket = reinterpret_cast<unsigned long long*>(step + 1);
@@ -826,7 +840,14 @@ int cross_entropy(const float* logits, const int64_t* y, int B, int ncls, float*
 
 int adam(float* p, const float* g, float* m, float* v, int64_t n, float lr, const float* lr_dev, float b1, float b2,
          float eps, float gscale, int64_t* step, cudaStream_t st) {
-  launch_pdl(adam_kernel, dim3(blocks_for(n)), dim3(TPB), 0, st, p, g, m, v, (long long)n, lr, lr_dev, b1, b2, eps, gscale, step);
+  const int vec = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) == 0;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  long long blocks = ceil_div(n, (int64_t)TPB * 4);
+  if (blocks > 4LL * sms) blocks = 4LL * sms;
+  if (blocks < 1) blocks = 1;
+  launch_pdl(adam_kernel, dim3((unsigned)blocks), dim3(TPB), 0, st, p, g, m, v, (long long)n, vec, lr, lr_dev, b1, b2, eps, gscale, step);
   RD_CHECK_LAUNCH("adam_kernel");
   return 0;
 }

@@ -487,14 +487,33 @@ __global__ void wgrad_reduce_kernel(const __grid_constant__ RGroup g) {
     if (lane == 0) r.dW[col] = s;
     return;
   }
-  const int m = (int)(e / (r.N + 1)), n = (int)(e - (long long)m * (r.N + 1));
+  // kind 0: one thread per four consecutive columns of a row (N % 4 == 0, slabs 16-byte aligned), plus one per row for
+  // the bias column N
+  const int q_per_row = (r.N >> 2) + 1;
+  const int m = (int)(e / q_per_row), q = (int)(e - (long long)m * q_per_row);
   if (m >= r.M) return;       // padding between this item and the next (warp-aligned) one
-  const float* src = r.partial + (long long)m * r.Nld + n;
   const long long stride = (long long)r.Mpad * r.Nld;
-  float s = 0.f;
+  if (q == (r.N >> 2)) {
+    const float* src = r.partial + (long long)m * r.Nld + r.N;
+    float s = 0.f;
 #pragma unroll 4
-  for (int sp = 0; sp < r.nsplit; ++sp) s += __ldg(src + sp * stride);
-  if (n < r.N) r.dW[(long long)m * r.N + n] = s; else if (r.db) r.db[m] = s;
+    for (int sp = 0; sp < r.nsplit; ++sp) s += __ldg(src + sp * stride);
+    if (r.db) r.db[m] = s;
+    return;
+  }
+  const float* src = r.partial + (long long)m * r.Nld + 4 * q;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int sp = 0; sp < r.nsplit; ++sp) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src + sp * stride));
+    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+  }
+  float* dst = r.dW + (long long)m * r.N + 4 * q;
+  if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
+    *reinterpret_cast<float4*>(dst) = s;
+  } else {
+    dst[0] = s.x; dst[1] = s.y; dst[2] = s.z; dst[3] = s.w;
+  }
 }
 
 struct WPlan { int BN, n_tiles, m_tiles, nsplit, rows_per_split, Mpad, Nld; };
@@ -701,7 +720,7 @@ int tc_wgrad_group(const WgradItem* items, int n, const ColsumItem* cs, int ncs,
     q.partial = a.partial; q.dW = a.dW; q.db = a.db; q.nsplit = w.nsplit; q.M = a.Nout; q.N = a.Kin; q.Mpad = w.Mpad; q.Nld = w.Nld;
     q.kind = 0; q.stride = 0;
     q.start = tot;
-    tot += (long long)a.Nout * (a.Kin + 1);
+    tot += (long long)a.Nout * (a.Kin / 4 + 1);
   }
   g.total_items = item;
   g.stage_bytes = 2 * A_TILE + 2 * max_bn * 128;
