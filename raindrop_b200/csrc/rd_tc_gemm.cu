@@ -9,9 +9,11 @@
 //               double buffered so the epilogue of tile i overlaps the MMAs of tile i+1
 //   warps 2-5   epilogue: tcgen05.ld -> bias / relu / gate / dropout / residual -> swizzled smem ->
 //               TMA store (coalesced 128-byte lines)
-//   warps 6-9   remainder pass: the activation tile arrives by TMA like the weight tile (128B-swizzled K-major image,
-//               up to 4 k-blocks in flight -- register-staged loads were L2-latency bound: 0.63 us per k-block at
-//               K = 456 against a 0.3 us MMA floor); these warps only derive A_lo = A - trunc19(A) in shared memory
+//   warps 6-9   stagers: the activation tile arrives by TMA like the weight tile; these warps move it from shared memory
+//               into TENSOR memory (tcgen05.st, thread = row), split into hi (raw) and lo = x - trunc19(x).  The MMAs then
+//               take A from tensor memory: with both operands in shared memory the three error-compensation passes read
+//               the 128-row A slice three times per k-step and the kernel was shared-memory-bandwidth bound (156 KB of
+//               shared-memory traffic per k-block at BN = 96, 0.56 us; the tensor pipe idle 97 % of the time)
 #include <stdlib.h>
 
 #include "rd_tc_common.cuh"
@@ -25,6 +27,9 @@ constexpr int BM = 128, BK = 32, MAX_STAGES = 4, NTHREADS = 320;
 constexpr int A_TILE = BM * BK * 4;        // 16 KB (hi) + 16 KB (lo)
 constexpr int STG_BYTES = 4096;
 constexpr int MAX_BN = 160;
+// tensor memory: two accumulators of ACC_COLS columns, then A_SLOTS activation slots of 64 columns (hi | lo, 32 each)
+constexpr uint32_t ACC_COLS = 160, A_COL0 = 2 * ACC_COLS;
+constexpr int A_SLOTS = 3;
 
 struct P {
   const float* A; long long lda;
@@ -55,7 +60,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t b_tile = (uint32_t)p.BN * 128u;
-  const uint32_t stage_bytes = 2u * A_TILE + 2u * b_tile;
+  const uint32_t stage_bytes = (uint32_t)A_TILE + 2u * b_tile;      // A (raw) | B hi | B lo
   const uint32_t stg_base = base + (uint32_t)p.nstages * stage_bytes;
   const uint32_t bias_base = stg_base + 8 * STG_BYTES;
   const uint32_t bar_base = bias_base + 2 * 256 * 4;
@@ -64,7 +69,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 2 + a); };
   const uint32_t tmem_slot = bar_base + 8u * (2 * MAX_STAGES + 4);
-  auto ready_bar = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + 5 + s); };     // A_lo written
+  auto aready_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 5 + a); };    // A slot staged in tensor memory
+  auto aempty_bar = [&](int a) { return bar_base + 8u * (2 * MAX_STAGES + 5 + A_SLOTS + a); };   // MMAs have read it
   float* bias_s = reinterpret_cast<float*>(smem_raw + (bias_base - smem_u32(smem_raw)));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -76,7 +82,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
   if (warp == 1) {
     if (lane == 0) {
-      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); mbar_init(ready_bar(s), 4); }
+      for (int s = 0; s < MAX_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+      for (int a = 0; a < A_SLOTS; ++a) { mbar_init(aready_bar(a), 4); mbar_init(aempty_bar(a), 1); }
       for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -102,7 +109,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           mbar_wait(empty_bar(stage), phase ^ 1u);
           mbar_expect_tx(full_bar(stage), (uint32_t)A_TILE + 2u * b_tile);
           tma_load_2d(&tmA, full_bar(stage), base + (uint32_t)stage * stage_bytes, kb * BK, m_t * BM);
-          const uint32_t sb = base + (uint32_t)stage * stage_bytes + 2u * A_TILE;
+          const uint32_t sb = base + (uint32_t)stage * stage_bytes + (uint32_t)A_TILE;
           tma_load_2d(&tmB, full_bar(stage), sb, kb * BK, n_t * p.BN);
           tma_load_2d(&tmBlo, full_bar(stage), sb + b_tile, kb * BK, n_t * p.BN);     // (deriving it on chip like A_lo was slower:
           // the remainder pass, not L2, paces the k-loop -- 0.73 vs 0.56 us per k-block)
@@ -114,27 +121,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // ===== MMA issuer ================================================================================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0;
+      int stage = 0; uint32_t phase = 0; int acc = 0; uint32_t acc_phase = 0; int slot = 0; uint32_t slot_phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)acc * 256u;
+        const uint32_t d_tmem = tmem_base + (uint32_t)acc * ACC_COLS;
         for (int kb = 0; kb < p.k_blocks; ++kb) {
-          mbar_wait(ready_bar(stage), phase);
+          mbar_wait(full_bar(stage), phase);           // weight tiles (the stagers waited for the same barrier)
+          mbar_wait(aready_bar(slot), slot_phase);     // activation tile staged in tensor memory
           if (kb == 0) gstamp(p, 2);
           tc_fence_after();
-          const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + A_TILE);
-          const uint64_t b_hi = umma_desc_sw128(sa + 2u * A_TILE), b_lo = umma_desc_sw128(sa + 2u * A_TILE + b_tile);
+          const uint32_t sb = base + (uint32_t)stage * stage_bytes + (uint32_t)A_TILE;
+          const uint64_t b_hi = umma_desc_sw128(sb), b_lo = umma_desc_sw128(sb + b_tile);
+          const uint32_t a_hi = tmem_base + A_COL0 + (uint32_t)slot * 64u, a_lo = a_hi + 32u;
 #pragma unroll
           for (int kk = 0; kk < BK / 8; ++kk) {
             const uint64_t o = (uint64_t)(kk * 2);
-            umma_tf32(d_tmem, a_lo + o, b_hi + o, idesc, (kb | kk) ? 1u : 0u);   // small terms first
-            umma_tf32(d_tmem, a_hi + o, b_lo + o, idesc, 1u);
-            umma_tf32(d_tmem, a_hi + o, b_hi + o, idesc, 1u);
+            const uint32_t ao = (uint32_t)(kk * 8);                                  // 8 columns = 8 tf32 of K
+            umma_tf32_ts(d_tmem, a_lo + ao, b_hi + o, idesc, (kb | kk) ? 1u : 0u);   // small terms first
+            umma_tf32_ts(d_tmem, a_hi + ao, b_lo + o, idesc, 1u);
+            umma_tf32_ts(d_tmem, a_hi + ao, b_hi + o, idesc, 1u);
           }
           umma_commit(empty_bar(stage));
+          umma_commit(aempty_bar(slot));
           if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+          if (++slot == A_SLOTS) { slot = 0; slot_phase ^= 1u; }
         }
         umma_commit(tfull_bar(acc));
         gstamp(p, 3);
@@ -176,7 +187,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_after();
       for (int ch = 0; ch < n_chunks; ++ch) {
         uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * 256 + ch * 32), v);
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * ACC_COLS + (uint32_t)(ch * 32), v);
         float4 cg[8], cr[8];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) { if (GATE) cg[j4] = pg[j4]; if (RESID) cr[j4] = pr[j4]; }
@@ -229,18 +240,33 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (lane == 0) bulk_wait_read<0>();
     if (threadIdx.x == 64) gstamp(p, 6);
   } else {
-    // ===== remainder pass: A_lo = A - trunc19(A), same swizzled addresses =============================================
-    const int lt = threadIdx.x - 192;           // 0..127
-    int stage = 0; uint32_t phase = 0;
+    // ===== stagers: activation tile shared memory -> tensor memory, split into hi (raw) and lo = x - trunc19(x) ==========
+    // thread = tile row (its TMEM lane); the row's 32 values of the k-block are 8 swizzled 16-byte pieces
+    const int q = warp & 3, row = q * 32 + lane;
+    const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+    int stage = 0; uint32_t phase = 0; int slot = 0; uint32_t slot_phase = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       for (int kb = 0; kb < p.k_blocks; ++kb) {
         mbar_wait(full_bar(stage), phase);
-        const uint32_t sa = base + (uint32_t)stage * stage_bytes;
-        lo_image<8>(sa, sa + A_TILE, A_TILE / 16, (uint32_t)lt, 128u);
-        fence_async_smem();
+        const uint32_t sa = base + (uint32_t)stage * stage_bytes + (uint32_t)row * 128u;
+        uint32_t x[32], l[32];
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(x[4 * c]), "=r"(x[4 * c + 1]), "=r"(x[4 * c + 2]), "=r"(x[4 * c + 3])
+                       : "r"(sa + (uint32_t)(((c ^ (row & 7)) << 4))));
+#pragma unroll
+        for (int e = 0; e < 32; ++e) l[e] = __float_as_uint(__uint_as_float(x[e]) - __uint_as_float(x[e] & 0xFFFFE000u));
+        mbar_wait(aempty_bar(slot), slot_phase ^ 1u);      // the MMAs of three k-blocks ago have read this slot
+        tc_fence_after();
+        const uint32_t ta = tmem_base + lane_addr + A_COL0 + (uint32_t)slot * 64u;
+        tmem_st32(ta, x);
+        tmem_st32(ta + 32u, l);
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(ready_bar(stage));
+        if (lane == 0) mbar_arrive(aready_bar(slot));
         if (++stage == p.nstages) { stage = 0; phase ^= 1u; }
+        if (++slot == A_SLOTS) { slot = 0; slot_phase ^= 1u; }
       }
     }
   }
@@ -606,7 +632,7 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
   plan(a.M, a.N, &p.BN, &p.n_tiles);
   p.m_tiles = (int)ceil_div(a.M, BM);
   p.k_blocks = (int)ceil_div(a.K, BK);
-  const int stage_bytes = 2 * A_TILE + 2 * p.BN * 128;
+  const int stage_bytes = A_TILE + 2 * p.BN * 128;
   const int fixed = 1024 + 8 * STG_BYTES + 2 * 256 * 4 + 256;
   p.nstages = (SMEM_LIMIT - fixed) / stage_bytes;
   if (p.nstages > MAX_STAGES) p.nstages = MAX_STAGES;
