@@ -49,7 +49,6 @@ struct AttnTcP {
   int B, H, T, hd, D;
   float scale, drop_p;
   const uint64_t* rng; uint32_t site;
-  int dbg_mode;                 // RD_ATTN_DBG experiments (timing only)
   unsigned long long* dbg;      // optional phase timestamps (rd_debug_attention_timing): [CTA][16] of %globaltimer
 };
 
@@ -219,12 +218,6 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tO = tmem + 64;
   stamp(p, 0);
-  if (p.dbg_mode == 9 && threadIdx.x == 0) {      // experiment: a throw-away MMA while the tiles are still in flight
-    mbar_init(bar + 40, 1);
-    umma_tf32(tmem + 192, umma_desc_sw128(QV), umma_desc_sw128(KP), umma_idesc_tf32(128, 64, false, false), 0u);
-    umma_commit(bar + 40);
-  }
-  __syncwarp();
 
   if (threadIdx.x == 0) {
     mbar_expect_tx(bar_qk, 2u * TILE);
@@ -238,40 +231,14 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   stamp(p, 1);
   mbar_wait(bar_qk, 0);
   stamp(p, 2);
-  if (p.dbg_mode != 7) {
-    lo_pass(QV, TILE, TILE);
-    lo_pass(KP, TILE, TILE);
-    fence_async_smem();
-  }
+  lo_pass(QV, TILE, TILE);
+  lo_pass(KP, TILE, TILE);
+  fence_async_smem();
   __syncthreads();
   stamp(p, 3);
   if (warp == 0) {
-    if (p.dbg_mode == 14) stamp(p, 13);
     tc_fence_after();
-    if (p.dbg_mode == 14) stamp(p, 14);
-    if (p.dbg_mode == 0 || p.dbg_mode == 9 || p.dbg_mode == 14) {
-      mma3<false, false, 4 * NG>(tS, QV, TILE, KP, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
-    } else if (lane == 0) {      // timing experiments on the S = Q K^T issue (results are wrong on purpose)
-      const uint32_t id = umma_idesc_tf32(128, p.dbg_mode == 5 ? 128 : 64, false, false);
-      const uint64_t ah = umma_desc_sw128(QV), al = umma_desc_sw128(QV + TILE), bh = umma_desc_sw128(KP), bl = umma_desc_sw128(KP + TILE);
-      const int reps = p.dbg_mode == 3 ? 2 : 1;
-      if (p.dbg_mode == 13) stamp(p, 13);
-      for (int r = 0; r < reps; ++r)
-#pragma unroll
-        for (int ks = 0; ks < 10; ++ks) {
-          const uint64_t o = (uint64_t)((ks >> 2) * (GRP >> 4) + (ks & 3) * 2);
-          const uint32_t d = p.dbg_mode == 2 ? tS + 160u * (ks & 1) : (p.dbg_mode == 4 ? tS + 64u * (ks % 3) : tS);
-          if (p.dbg_mode != 1) {
-            umma_tf32(d, al + o, bh + o, id, ks ? 1u : 0u);
-            if (p.dbg_mode == 13 && ks == 0) stamp(p, 14);
-            umma_tf32(d, ah + o, bl + o, id, 1u);
-          }
-          umma_tf32(d, ah + o, bh + o, id, 1u);
-          if (p.dbg_mode == 13 && ks == 0) stamp(p, 15);
-          if (p.dbg_mode >= 6 && (ks == 0 || ks == 4)) stamp(p, ks == 0 ? 13 : 14);
-        }
-      if (p.dbg_mode >= 6) stamp(p, 15);
-    }
+    mma3<false, false, 4 * NG>(tS, QV, TILE, KP, TILE, (p.hd + 7) >> 3, umma_idesc_tf32(128, 64, false, false));
   }
   if (threadIdx.x == 0) {
     umma_commit(bar_s);
@@ -651,7 +618,6 @@ int attn_tc_fwd(const float* qkv, const int64_t* lengths, int B, int H, int T, i
   AttnTcP p{};
   p.ctx = ctx; p.lengths = lengths; p.B = B; p.H = H; p.T = T; p.hd = hd; p.D = H * hd;
   p.scale = 1.f / sqrtf((float)hd); p.drop_p = drop_p; p.rng = rng; p.site = site; p.dbg = g_attn_dbg;
-  { const char* e = getenv("RD_ATTN_DBG"); p.dbg_mode = e ? atoi(e) : 0; }
   CUtensorMap tm, tmm;
   RD_TRY(encode_qkv(&tm, qkv, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B));
   RD_TRY(encode_qkv(&tmm, qkv, B, H, T, hd, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B));
