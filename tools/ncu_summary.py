@@ -30,13 +30,16 @@ def full(rep, out, json_out=None):
             "sm__mem_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__inst_executed_pipe_uniform.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
             "launch__registers_per_thread", "launch__shared_mem_per_block_dynamic", "launch__grid_size", "launch__block_size", "lts__t_sector_hit_rate.pct",
             "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "sm__cycles_elapsed.max", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
-            "smsp__inst_executed.sum", "sm__inst_executed_pipe_tmem.sum"]
+            "smsp__inst_executed.sum", "sm__inst_executed_pipe_tmem.sum",
+            "TPC.TriageCompute.sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
+            "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed", "l1tex__data_pipe_tc_wavefronts_mem_shared.sum.pct_of_peak_sustained_elapsed",
+            "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", "l1tex__data_bank_reads.avg.pct_of_peak_sustained_elapsed", "l1tex__data_bank_writes.avg.pct_of_peak_sustained_elapsed"]
     with open(out, "w") as f:
         f.write("# ncu --set full --clock-control none --import-source on, %s\n" % rep)
         for r in rows[2:]:
             f.write("\nkernel: %s  (launch id %s)\n" % (r[hdr.index("Kernel Name")][:70], r[hdr.index("ID")]))
             for k in hdr:
-                if k in keys or ("tensor" in k and "pct" in k and "avg" in k) or "tmem" in k.lower() and "sum" in k:
+                if k in keys:
                     f.write("  %-78s %s %s\n" % (k, r[hdr.index(k)], units[hdr.index(k)]))
     if json_out:
         def val(r, k):
