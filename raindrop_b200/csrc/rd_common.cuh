@@ -162,6 +162,7 @@ struct GemmP {
   const float* rowscale = nullptr; int rowscale_mod = 1;  // * rowscale[i % mod]
   const float* gate = nullptr; long long gate_ld = 0; float gate_scale = 1.f;  // * (gate[i,j] > 0 ? gate_scale : 0)
   float drop_p = 0.f; const uint64_t* rng = nullptr; uint32_t drop_site = 0;   // dropout, index i*N + j
+  uint32_t* drop_mask = nullptr; int drop_mask_ld = 0;   // optional keep bits out: word [i*ld + j/32], bit j%32 (tensor-core path only)
   const float* resid = nullptr; long long resid_ld = 0;  // + resid[i*ld + j]
   // permuted store of the ob-prop output into the encoder input (code/models_rd.py:338-341):
   // row i = b*N + n, col j = t*d_ob + k  ->  C[((t*B + b)*D) + n*d_ob + k]

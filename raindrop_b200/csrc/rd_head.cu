@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadP p, const float* __re
     const int tg = tid >> 6, dq0 = tid & 63, nq = p.D >> 2;
     for (int dq = dq0; dq < nq; dq += 64) {
       float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
+#pragma unroll 8
       for (int t = tg; t < nv; t += 8) {
         const float4 v = __ldg(reinterpret_cast<const float4*>(x + ((long long)t * p.B + b) * p.D) + dq);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -68,26 +68,30 @@ __global__ void __launch_bounds__(HT) head_fwd_kernel(HeadP p, const float* __re
     }
   }
   __syncthreads();
-  // a warp owns 4 hidden units at a time; all weight loads of a 256-wide k pass are issued before the FMAs
-  for (int j0 = warp * 4; j0 < p.Df; j0 += (HT / 32) * 4) {
-    float a[4] = {0.f, 0.f, 0.f, 0.f};
+  // a warp owns HU hidden units at a time; all weight loads of a 256-wide k pass are issued before the FMAs
+  // (HU = 6: the 186 units of the P19 head take two L2 round trips per warp instead of three)
+  constexpr int HU = 6;
+  for (int j0 = warp * HU; j0 < p.Df; j0 += (HT / 32) * HU) {
+    float a[HU];
+#pragma unroll
+    for (int u = 0; u < HU; ++u) a[u] = 0.f;
     for (int kb = 0; kb < p.Df; kb += 256) {
-      float w[4][8], f[8];
+      float w[HU][8], f[8];
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int k = kb + lane + 32 * e;
         const bool ok = k < p.Df;
         f[e] = ok ? fs[k] : 0.f;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) w[u][e] = (ok && j0 + u < p.Df) ? __ldg(p.w0 + (long long)(j0 + u) * p.Df + k) : 0.f;
+        for (int u = 0; u < HU; ++u) w[u][e] = (ok && j0 + u < p.Df) ? __ldg(p.w0 + (long long)(j0 + u) * p.Df + k) : 0.f;
       }
 #pragma unroll
       for (int e = 0; e < 8; ++e)
 #pragma unroll
-        for (int u = 0; u < 4; ++u) a[u] = fmaf(f[e], w[u][e], a[u]);
+        for (int u = 0; u < HU; ++u) a[u] = fmaf(f[e], w[u][e], a[u]);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
+    for (int u = 0; u < HU; ++u) {
       const float v = warp_sum(a[u]);
       if (lane == 0 && j0 + u < p.Df) {
         const float h = fmaxf(v + __ldg(p.b0 + j0 + u), 0.f);

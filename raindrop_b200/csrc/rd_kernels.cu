@@ -305,6 +305,67 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
   if (lane == 0) { stats[2 * row] = mean; stats[2 * row + 1] = rstd; }
 }
 
+// The same with the row held in registers (ITERS float4 per lane, D % 4 == 0, D <= 128 * ITERS): one global read instead of
+// three, 128-bit accesses, two rows per warp in flight.
+template <int ITERS>
+__global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, long long rows, int D, float eps,
+                                                                float* __restrict__ y, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
+  constexpr int RB = 2;
+  const int lane = threadIdx.x & 31;
+  const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RB;
+  float4 v[RB][ITERS];
+  float s[RB], q[RB];
+#pragma unroll
+  for (int k = 0; k < RB; ++k) {
+    s[k] = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      const int j = 4 * lane + 128 * it;
+      v[k][it] = (row0 + k < rows && j < D) ? *reinterpret_cast<const float4*>(x + (row0 + k) * D + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s[k] += (v[k][it].x + v[k][it].y) + (v[k][it].z + v[k][it].w);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < RB; ++k) s[k] = warp_sum(s[k]) / (float)D;
+#pragma unroll
+  for (int k = 0; k < RB; ++k) {
+    q[k] = 0.f;
+#pragma unroll
+    for (int it = 0; it < ITERS; ++it) {
+      if (4 * lane + 128 * it < D) {
+        const float a = v[k][it].x - s[k], b = v[k][it].y - s[k], c = v[k][it].z - s[k], d = v[k][it].w - s[k];
+        q[k] += (a * a + b * b) + (c * c + d * d);
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < RB; ++k) q[k] = 1.f / sqrtf(warp_sum(q[k]) / (float)D + eps);
+#pragma unroll
+  for (int it = 0; it < ITERS; ++it) {
+    const int j = 4 * lane + 128 * it;
+    if (j < D) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + j)), bt = __ldg(reinterpret_cast<const float4*>(beta + j));
+#pragma unroll
+      for (int k = 0; k < RB; ++k) {
+        if (row0 + k < rows) {
+          float4 o;
+          o.x = (v[k][it].x - s[k]) * q[k] * g.x + bt.x; o.y = (v[k][it].y - s[k]) * q[k] * g.y + bt.y;
+          o.z = (v[k][it].z - s[k]) * q[k] * g.z + bt.z; o.w = (v[k][it].w - s[k]) * q[k] * g.w + bt.w;
+          *reinterpret_cast<float4*>(y + (row0 + k) * D + j) = o;
+        }
+      }
+    }
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < RB; ++k)
+      if (row0 + k < rows) { stats[2 * (row0 + k)] = s[k]; stats[2 * (row0 + k) + 1] = q[k]; }
+  }
+}
+
 // LayerNorm backward, one pass over (x, dy): every warp walks LNB_ROWS/8 rows, writes dx (and the
 // dropout-masked copy the sub-layer's weight gradient needs) and keeps per-lane column sums of
 // dy*xhat / dy in registers; the 8 warps of a CTA combine them through shared memory into one
@@ -317,13 +378,14 @@ template <int ITERS, int RB>
 __global__ void __launch_bounds__(256, 2) layernorm_bwd_fused_kernel(
     const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ dy, long long rows, int D, float* __restrict__ dx, float* __restrict__ dx_drop,
-    float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial) {
+    float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial,
+    const uint32_t* __restrict__ keep_bits, int keep_ld) {
   pdl_launch_dependents();
   pdl_wait();
   extern __shared__ float lsm[];                     // [8 warps][2][D]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float ik = drop_p > 0.f ? 1.f / (1.f - drop_p) : 1.f;
-  const RngKey key = load_rng_key(dx_drop ? rng : nullptr);
+  const RngKey key = load_rng_key(dx_drop && !keep_bits ? rng : nullptr);
   float4 ag[ITERS], ab[ITERS], g4[ITERS];
 #pragma unroll
   for (int it = 0; it < ITERS; ++it) {
@@ -380,7 +442,13 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_fused_kernel(
           o.w = rstd[k] * (d.w * g.w - s1[k] - h.w * s2[k]);
           *reinterpret_cast<float4*>(dx + row * D + j) = o;
           if (dx_drop) {
-            const float4 m = dropout_scale4(key, site, (uint64_t)row * D + j, drop_p, ik);
+            float4 m;
+            if (keep_bits) {      // decisions stored by the forward GEMM epilogue: word [row, j / 32], bit j % 32
+              const uint32_t b4 = (__ldg(keep_bits + row * keep_ld + (j >> 5)) >> (j & 31)) & 15u;
+              m = make_float4(b4 & 1u ? ik : 0.f, b4 & 2u ? ik : 0.f, b4 & 4u ? ik : 0.f, b4 & 8u ? ik : 0.f);
+            } else {
+              m = dropout_scale4(key, site, (uint64_t)row * D + j, drop_p, ik);
+            }
             *reinterpret_cast<float4*>(dx_drop + row * D + j) = make_float4(o.x * m.x, o.y * m.y, o.z * m.z, o.w * m.w);
           }
           ag[it].x += d.x * h.x; ag[it].y += d.y * h.y; ag[it].z += d.z * h.z; ag[it].w += d.w * h.w;
@@ -556,6 +624,25 @@ __global__ void obprop_out_grad_kernel(const float* __restrict__ dZ, const float
   long long zi = ((long long)t * B + b) * D + n * d_ob + k;
   float v = (Z[zi] > 0.f) ? dZ[zi] * __ldg(s + n) : 0.f;
   dZ2[o] = round ? to_tf32(v) : v;
+}
+
+// d_ob == 4: one thread per (row, timestamp), the four channels as one 128-bit access (Z0 rows are 16-byte aligned: D % 4 == 0)
+__global__ void obprop_out_grad_vec4_kernel(const float* __restrict__ dZ, const float* __restrict__ Z,
+                                            const float* __restrict__ s, int B, int T, int N, int D, int round,
+                                            float* __restrict__ dZ2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (long long)B * N * T) return;
+  const long long row = o / T;
+  const int t = (int)(o - row * T);
+  const int b = (int)(row / N), n = (int)(row - (long long)b * N);
+  const long long zi = ((long long)t * B + b) * D + n * 4;
+  const float4 z = *reinterpret_cast<const float4*>(Z + zi), g = *reinterpret_cast<const float4*>(dZ + zi);
+  const float sc = __ldg(s + n);
+  float4 v = make_float4(z.x > 0.f ? g.x * sc : 0.f, z.y > 0.f ? g.y * sc : 0.f, z.z > 0.f ? g.z * sc : 0.f, z.w > 0.f ? g.w * sc : 0.f);
+  if (round) v = make_float4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+  *reinterpret_cast<float4*>(dZ2 + o * 4) = v;
 }
 
 __global__ void apply_dropout_kernel(const float* __restrict__ x, long long n, float p,
@@ -756,6 +843,15 @@ int node_scale(const int64_t* edge_tgt, const float* edge_w, int E, int N, float
 
 int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t rows, int D, float eps, float* y,
                   float* stats, cudaStream_t st) {
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta);
+  if ((D & 3) == 0 && D <= 640 && (bits & 15) == 0) {
+    const unsigned blocks = (unsigned)ceil_div(rows, (int64_t)(TPB / 32) * 2);      // 8 warps x 2 rows per CTA
+    if (D <= 128) launch_pdl(layernorm_fwd_vec_kernel<1>, dim3(blocks), dim3(TPB), 0, st, x, gamma, beta, (long long)rows, D, eps, y, stats);
+    else if (D <= 256) launch_pdl(layernorm_fwd_vec_kernel<2>, dim3(blocks), dim3(TPB), 0, st, x, gamma, beta, (long long)rows, D, eps, y, stats);
+    else launch_pdl(layernorm_fwd_vec_kernel<5>, dim3(blocks), dim3(TPB), 0, st, x, gamma, beta, (long long)rows, D, eps, y, stats);
+    RD_CHECK_LAUNCH("layernorm_fwd_vec_kernel");
+    return 0;
+  }
   launch_pdl(layernorm_fwd_kernel, dim3(blocks_for(rows * 32)), dim3(TPB), 0, st, x, gamma, beta, (long long)rows, D, eps, y, stats);
   RD_CHECK_LAUNCH("layernorm_fwd_kernel");
   return 0;
@@ -768,7 +864,8 @@ int64_t ln_bwd_scratch_floats(int64_t rows, int D) {
 
 int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows, int D,
                   float* dx, float* dgamma, float* dbeta, float* scratch, float* dx_drop, float drop_p,
-                  const uint64_t* rng, uint32_t site, int* deferred_chunks, cudaStream_t st) {
+                  const uint64_t* rng, uint32_t site, int* deferred_chunks, cudaStream_t st, const uint32_t* keep_bits,
+                  int keep_ld) {
   const uintptr_t bits = reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dy) |
                          reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_drop);
   int chunks;
@@ -776,7 +873,7 @@ int layernorm_bwd(const float* x, const float* stats, const float* gamma, const 
     chunks = (int)ceil_div(rows, LNB_ROWS);
     auto kern = D <= 128 ? layernorm_bwd_fused_kernel<1, 4> : (D <= 256 ? layernorm_bwd_fused_kernel<2, 4> : layernorm_bwd_fused_kernel<LNB_MAXIT, 1>);
     launch_pdl(kern, dim3(chunks), dim3(256), 8 * 2 * D * sizeof(float), st, x, stats, gamma, dy, (long long)rows, D,
-               dx, drop_p > 0.f ? dx_drop : (float*)nullptr, drop_p, rng, site, scratch);
+               dx, drop_p > 0.f ? dx_drop : (float*)nullptr, drop_p, rng, site, scratch, keep_bits, keep_ld);
     RD_CHECK_LAUNCH("layernorm_bwd_fused_kernel");
   } else {
     layernorm_bwd_dx_kernel<<<blocks_for(rows * 32), TPB, 0, st>>>(x, stats, gamma, dy, rows, D, dx,
@@ -812,6 +909,12 @@ int attn_softmax_bwd(const float* P, float* dP, int B, int H, int T, float drop_
 int obprop_out_grad(const float* dZ, const float* Z, const float* s, int B, int T, int N, int d_ob, int D,
                     int round, float* dZ2, cudaStream_t st) {
   int64_t total = (int64_t)B * N * T * d_ob;
+  const uintptr_t bits = reinterpret_cast<uintptr_t>(dZ) | reinterpret_cast<uintptr_t>(Z) | reinterpret_cast<uintptr_t>(dZ2);
+  if (d_ob == 4 && (D & 3) == 0 && (bits & 15) == 0) {
+    launch_pdl(obprop_out_grad_vec4_kernel, dim3(blocks_for(total / 4)), dim3(TPB), 0, st, dZ, Z, s, B, T, N, D, round, dZ2);
+    RD_CHECK_LAUNCH("obprop_out_grad_vec4_kernel");
+    return 0;
+  }
   launch_pdl(obprop_out_grad_kernel, dim3(blocks_for(total)), dim3(TPB), 0, st, dZ, Z, s, B, T, N, d_ob, D, round, dZ2);
   RD_CHECK_LAUNCH("obprop_out_grad_kernel");
   return 0;

@@ -47,7 +47,8 @@ int64_t ln_bwd_scratch_floats(int64_t rows, int D);
 // (*deferred_chunks = chunks), who folds it into a later grouped reduction launch (tc_wgrad_group)
 int layernorm_bwd(const float* x, const float* stats, const float* gamma, const float* dy, int64_t rows,
                   int D, float* dx, float* dgamma, float* dbeta, float* scratch, float* dx_drop, float drop_p,
-                  const uint64_t* rng, uint32_t site, int* deferred_chunks, cudaStream_t st);
+                  const uint64_t* rng, uint32_t site, int* deferred_chunks, cudaStream_t st,
+                  const uint32_t* keep_bits = nullptr, int keep_ld = 0);   // keep_bits: decisions stored by the forward (else Philox)
 
 // in-place masked softmax over rows of S [B,H,T,T]; key j masked when j >= lengths[b].
 // If Pd != nullptr also writes the dropped probabilities (training).

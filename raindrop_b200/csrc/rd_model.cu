@@ -57,7 +57,7 @@ struct Arena {
 
 struct WsLayout {
   int64_t rng, cnt, loss_ps, X0, H1, W1r, W2r, W2t, W1lo, W2lo, W2tlo, Z[RD_MAX_LAYERS + 1], feat, hpre, total;
-  struct { int64_t qkv, P, Pd, ctx, r1, st1, x1, f, r2, st2; } l[RD_MAX_LAYERS];
+  struct { int64_t qkv, P, Pd, ctx, r1, st1, x1, f, r2, st2, m1, m2; } l[RD_MAX_LAYERS];   // m1, m2: dropout keep bits of r1, r2
   // error-compensation remainders and transposes of the encoder weights (rd_tc_gemm.cuh)
   struct { int64_t in_lo, in_t, in_tlo, out_lo, out_t, out_tlo, l1_lo, l1_t, l1_tlo, l2_lo, l2_t, l2_tlo; } wsp[RD_MAX_LAYERS];
 };
@@ -90,6 +90,8 @@ WsLayout ws_layout(const Shape& s) {
     w.l[i].f = a.take(s.M2 * s.nhid);
     w.l[i].r2 = a.take(s.M2 * s.D);
     w.l[i].st2 = a.take(s.M2 * 2);
+    const int64_t mw = s.p > 0.f ? s.M2 * ((s.D + 31) / 32) : 0;     // one 32-bit word per 32 columns
+    w.l[i].m1 = a.take(mw); w.l[i].m2 = a.take(mw);
     const int64_t nin = 3LL * s.D * s.D, nout = (int64_t)s.D * s.D, nff = (int64_t)s.nhid * s.D;
     w.wsp[i].in_lo = a.take(nin); w.wsp[i].in_t = a.take(nin); w.wsp[i].in_tlo = a.take(nin);
     w.wsp[i].out_lo = a.take(nout); w.wsp[i].out_t = a.take(nout); w.wsp[i].out_tlo = a.take(nout);
@@ -221,10 +223,21 @@ static int linear_nt(const GemmP& g, const float* W_lo, cudaStream_t st) {
   a.A = g.A; a.lda = g.sAi; a.B = g.B; a.B_lo = W_lo; a.M = g.M; a.N = g.N; a.K = g.K; a.C = g.C;
   a.bias = g.bias; a.relu = g.relu; a.gate = g.gate; a.gate_ld = g.gate_ld; a.gate_scale = g.gate_scale;
   a.drop_p = g.drop_p; a.rng = g.rng; a.drop_site = g.drop_site; a.resid = g.resid; a.resid_ld = g.resid_ld;
+  a.drop_mask = g.drop_mask; a.drop_mask_ld = g.drop_mask_ld;
   const bool plain = g.ta == 0 && g.tb == 1 && g.sBj == g.K && g.sCi == g.N && g.sCj == 1 && g.nz == 1 && g.nsplit == 1 &&
                      g.alpha == 1.f && !g.rowscale && !g.perm && !g.asum;
   if (plain && W_lo && tc_gemm_supported(a)) return tc_gemm(a, st);
   return gemm(g, st);
+}
+
+// The predicate of linear_nt for a plain y = x W^T GEMM: the backward calls it with the forward's operands to know
+// whether the forward's epilogue stored the dropout keep bits (only the tensor-core kernel does).
+static bool linear_nt_is_tc(const GemmP& g, const float* W_lo) {
+  TcGemmArgs a;
+  a.A = g.A; a.lda = g.sAi; a.B = g.B; a.B_lo = W_lo; a.M = g.M; a.N = g.N; a.K = g.K; a.C = g.C;
+  a.bias = g.bias; a.relu = g.relu; a.gate = g.gate; a.gate_ld = g.gate_ld; a.gate_scale = g.gate_scale;
+  a.drop_p = g.drop_p; a.rng = g.rng; a.drop_site = g.drop_site; a.resid = g.resid; a.resid_ld = g.resid_ld;
+  return W_lo && tc_gemm_supported(a);
 }
 
 // ---- observation propagation layer (operator level) ---------------------------------------------
@@ -344,6 +357,7 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
       GemmP g = nt(ctx, s.D, E.out_proj_weight, s.D, r1, s.D, s.M2, s.D, s.D);
       g.bias = E.out_proj_bias; g.drop_p = s.p; g.rng = rng; g.drop_site = SITE_RESID1 + l;
       g.resid = x; g.resid_ld = s.D;
+      if (s.p > 0.f) { g.drop_mask = reinterpret_cast<uint32_t*>(ws + w.l[l].m1); g.drop_mask_ld = (s.D + 31) / 32; }
       RD_TRY(linear_nt(g, ws + w.wsp[l].out_lo, st));
     }
     RD_TRY(layernorm_fwd(r1, E.norm1_weight, E.norm1_bias, s.M2, s.D, dims->ln_eps, x1, ws + w.l[l].st1, st));
@@ -357,6 +371,7 @@ static int raindrop_fwd(const rd_dims* dims, const rd_params* P, const float* sr
       GemmP g = nt(f, s.nhid, E.linear2_weight, s.nhid, r2, s.D, s.M2, s.D, s.nhid);
       g.bias = E.linear2_bias; g.drop_p = s.p; g.rng = rng; g.drop_site = SITE_RESID2 + l;
       g.resid = x1; g.resid_ld = s.D;
+      if (s.p > 0.f) { g.drop_mask = reinterpret_cast<uint32_t*>(ws + w.l[l].m2); g.drop_mask_ld = (s.D + 31) / 32; }
       RD_TRY(linear_nt(g, ws + w.wsp[l].l2_lo, st));
     }
     RD_TRY(layernorm_fwd(r2, E.norm2_weight, E.norm2_bias, s.M2, s.D, dims->ln_eps, ws + w.Z[l + 1], ws + w.l[l].st2, st));
@@ -405,8 +420,19 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     // gradient, kept until the grouped launch; res = the undropped residual-path gradient
     float* res = s.p > 0.f ? gB : K2;
     int chunks = 0;
+    // did the forward GEMMs of this layer store their dropout keep bits (tensor-core epilogue)?  Same predicate, same operands.
+    const uint32_t* m2 = nullptr; const uint32_t* m1 = nullptr;
+    const int mld = (s.D + 31) / 32;
+    if (s.p > 0.f) {
+      GemmP g2 = nt(f, s.nhid, E.linear2_weight, s.nhid, const_cast<float*>(r2), s.D, s.M2, s.D, s.nhid);
+      g2.bias = E.linear2_bias; g2.drop_p = s.p; g2.rng = rng; g2.resid = x1; g2.resid_ld = s.D;
+      if (linear_nt_is_tc(g2, ws + w.wsp[l].l2_lo)) m2 = reinterpret_cast<const uint32_t*>(ws + w.l[l].m2);
+      GemmP g1 = nt(ctx, s.D, E.out_proj_weight, s.D, const_cast<float*>(r1), s.D, s.M2, s.D, s.D);
+      g1.bias = E.out_proj_bias; g1.drop_p = s.p; g1.rng = rng; g1.resid = x; g1.resid_ld = s.D;
+      if (linear_nt_is_tc(g1, ws + w.wsp[l].out_lo)) m1 = reinterpret_cast<const uint32_t*>(ws + w.l[l].m1);
+    }
     RD_TRY(layernorm_bwd(r2, ws + w.l[l].st2, E.norm2_weight, gA, s.M2, s.D, res, GE.norm2_weight, GE.norm2_bias,
-                         sc + b.l[l].ln[0], K2, s.p, rng, SITE_RESID2 + l, &chunks, st));
+                         sc + b.l[l].ln[0], K2, s.p, rng, SITE_RESID2 + l, &chunks, st, m2, mld));
     RD_TRY(wq.colsum(sc + b.l[l].ln[0], 2 * s.D, chunks, s.D, GE.norm2_weight, st));
     RD_TRY(wq.colsum(sc + b.l[l].ln[0] + s.D, 2 * s.D, chunks, s.D, GE.norm2_bias, st));
     RD_TRY(tn(&wq, K2, s.D, f, s.nhid, GE.linear2_weight, GE.linear2_bias, s.D, s.nhid, s.M2, sc + b.l[l].wp[0], partial, st));
@@ -424,7 +450,7 @@ static int raindrop_bwd(const rd_dims* dims, const rd_params* P, const float* st
     // norm1 + self-attention block
     res = s.p > 0.f ? gB : K1;
     RD_TRY(layernorm_bwd(r1, ws + w.l[l].st1, E.norm1_weight, gA, s.M2, s.D, res, GE.norm1_weight, GE.norm1_bias,
-                         sc + b.l[l].ln[1], K1, s.p, rng, SITE_RESID1 + l, &chunks, st));
+                         sc + b.l[l].ln[1], K1, s.p, rng, SITE_RESID1 + l, &chunks, st, m1, mld));
     RD_TRY(wq.colsum(sc + b.l[l].ln[1], 2 * s.D, chunks, s.D, GE.norm1_weight, st));
     RD_TRY(wq.colsum(sc + b.l[l].ln[1] + s.D, 2 * s.D, chunks, s.D, GE.norm1_bias, st));
     RD_TRY(tn(&wq, K1, s.D, ctx, s.D, GE.out_proj_weight, GE.out_proj_bias, s.D, s.D, s.M2, sc + b.l[l].wp[2], partial, st));

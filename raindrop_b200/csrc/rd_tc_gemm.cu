@@ -37,6 +37,7 @@ struct P {
   const float* bias; int relu;
   const float* gate; long long gate_ld; float gate_scale;
   float drop_p; const uint64_t* rng; uint32_t drop_site;
+  uint32_t* drop_mask; int drop_mask_ld;
   const float* resid; long long resid_ld;
   unsigned long long* dbg;     // optional %globaltimer phase stamps [CTA][8] (rd_debug_gemm_timing)
 };
@@ -197,6 +198,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) bulk_wait_read<1>();
         __syncwarp();
         const uint32_t stg = my_stg + (uint32_t)buf * STG_BYTES;
+        uint32_t keep_word = 0u;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
           float o[4];
@@ -215,6 +217,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           if (DROP && ok) {   // row*N + c is a multiple of 4: one Philox block for the four columns
             const float4 m = dropout_scale4(key, p.drop_site, (uint64_t)row * (uint64_t)p.N + (uint64_t)c, p.drop_p, ik);
             o[0] *= m.x; o[1] *= m.y; o[2] *= m.z; o[3] *= m.w;
+            keep_word |= ((m.x > 0.f ? 1u : 0u) | (m.y > 0.f ? 2u : 0u) | (m.z > 0.f ? 4u : 0u) | (m.w > 0.f ? 8u : 0u)) << (4 * j4);
           }
           if (RESID && ok) {
             const float4 r = cr[j4];
@@ -223,6 +226,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const uint32_t off = (uint32_t)(lane * 128 + ((j4 ^ (lane & 7)) << 4));
           asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(stg + off), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
         }
+        // the backward of the consumer (LayerNorm) reads these bits instead of regenerating the Philox stream
+        if (DROP && p.drop_mask && row_ok && c0 < p.N) p.drop_mask[row * p.drop_mask_ld + (c0 >> 5)] = keep_word;
         fence_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -640,6 +645,7 @@ int tc_gemm(const TcGemmArgs& a, cudaStream_t st) {
   const int smem_bytes = fixed + p.nstages * stage_bytes;
   p.bias = a.bias; p.relu = a.relu; p.gate = a.gate; p.gate_ld = a.gate_ld; p.gate_scale = a.gate_scale;
   p.drop_p = a.drop_p; p.rng = a.rng; p.drop_site = a.drop_site; p.resid = a.resid; p.resid_ld = a.resid_ld;
+  p.drop_mask = a.drop_mask; p.drop_mask_ld = a.drop_mask_ld;
   p.dbg = g_gemm_dbg;
 
   CUtensorMap tmA, tmB, tmBlo, tmC;

@@ -17,6 +17,7 @@ struct TcGemmArgs {
   const float* bias = nullptr; int relu = 0;
   const float* gate = nullptr; long long gate_ld = 0; float gate_scale = 1.f;
   float drop_p = 0.f; const uint64_t* rng = nullptr; uint32_t drop_site = 0;
+  uint32_t* drop_mask = nullptr; int drop_mask_ld = 0;      // optional: keep bits of the dropout decisions, word [row*ld + col/32]
   const float* resid = nullptr; long long resid_ld = 0;
 };
 bool tc_gemm_supported(const TcGemmArgs& a);
