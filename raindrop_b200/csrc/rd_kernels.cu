@@ -370,12 +370,14 @@ __global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const float* __r
 // dropout-masked copy the sub-layer's weight gradient needs) and keeps per-lane column sums of
 // dy*xhat / dy in registers; the 8 warps of a CTA combine them through shared memory into one
 // partial row [2][D] per CTA (summed later in a fixed order).  128-bit accesses (D % 4 == 0).
-constexpr int LNB_ROWS = 32;    // rows per CTA (4 per warp: enough CTAs to fill the SMs at B = 128)
+constexpr int LNB_ROWS = 32;    // rows per CTA of the wide (D > 256) variant: 4 sequential rows per warp
+constexpr int LNB_ROWS_NARROW = 8;   // D <= 256: one row per warp -- 7680 rows = 52 warps per SM in flight; with 4 rows per warp
+                                     // there were 13, and the kernel sat at 9 cycles per issued instruction (latency bound)
 constexpr int LNB_MAXIT = 5;    // D <= 640
 // ITERS float4 per lane and row (D <= 128 * ITERS); RB rows of a warp are in flight together: their loads are all issued
 // before the first reduction, so a warp pays one memory round trip for RB rows instead of RB dependent ones.
-template <int ITERS, int RB>
-__global__ void __launch_bounds__(256, 2) layernorm_bwd_fused_kernel(
+template <int ITERS, int RB, int ROWS>
+__global__ void __launch_bounds__(256, (ITERS <= 2 && RB == 1) ? 4 : 2) layernorm_bwd_fused_kernel(
     const float* __restrict__ x, const float* __restrict__ stats, const float* __restrict__ gamma,
     const float* __restrict__ dy, long long rows, int D, float* __restrict__ dx, float* __restrict__ dx_drop,
     float drop_p, const uint64_t* __restrict__ rng, uint32_t site, float* __restrict__ partial,
@@ -393,8 +395,8 @@ __global__ void __launch_bounds__(256, 2) layernorm_bwd_fused_kernel(
     const int j = 4 * lane + 128 * it;
     g4[it] = j < D ? __ldg(reinterpret_cast<const float4*>(gamma + j)) : ag[it];
   }
-  const long long r0 = (long long)blockIdx.x * LNB_ROWS;
-  for (int rr = warp; rr < LNB_ROWS; rr += 8 * RB) {
+  const long long r0 = (long long)blockIdx.x * ROWS;
+  for (int rr = warp; rr < ROWS; rr += 8 * RB) {
     float4 d4[RB][ITERS], xh[RB][ITERS];
     float rstd[RB], s1[RB], s2[RB];
 #pragma unroll
@@ -858,7 +860,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t
 }
 
 int64_t ln_bwd_scratch_floats(int64_t rows, int D) {
-  int64_t a = ceil_div(rows, LN_ROWS), b = ceil_div(rows, LNB_ROWS);
+  int64_t a = ceil_div(rows, LN_ROWS), b = ceil_div(rows, D <= 256 ? LNB_ROWS_NARROW : LNB_ROWS);
   return (a > b ? a : b) * 2 * D;
 }
 
@@ -870,8 +872,9 @@ int layernorm_bwd(const float* x, const float* stats, const float* gamma, const 
                          reinterpret_cast<uintptr_t>(dx) | reinterpret_cast<uintptr_t>(dx_drop);
   int chunks;
   if ((D & 3) == 0 && D <= 128 * LNB_MAXIT && (bits & 15) == 0) {     // fused single pass
-    chunks = (int)ceil_div(rows, LNB_ROWS);
-    auto kern = D <= 128 ? layernorm_bwd_fused_kernel<1, 4> : (D <= 256 ? layernorm_bwd_fused_kernel<2, 4> : layernorm_bwd_fused_kernel<LNB_MAXIT, 1>);
+    chunks = (int)ceil_div(rows, D <= 256 ? LNB_ROWS_NARROW : LNB_ROWS);
+    auto kern = D <= 128 ? layernorm_bwd_fused_kernel<1, 1, LNB_ROWS_NARROW>
+                         : (D <= 256 ? layernorm_bwd_fused_kernel<2, 1, LNB_ROWS_NARROW> : layernorm_bwd_fused_kernel<LNB_MAXIT, 1, LNB_ROWS>);
     launch_pdl(kern, dim3(chunks), dim3(256), 8 * 2 * D * sizeof(float), st, x, stats, gamma, dy, (long long)rows, D,
                dx, drop_p > 0.f ? dx_drop : (float*)nullptr, drop_p, rng, site, scratch, keep_bits, keep_ld);
     RD_CHECK_LAUNCH("layernorm_bwd_fused_kernel");

@@ -29,6 +29,18 @@ class _Shim(torch.nn.Module):
         return [sd[k] for k in self.keys]
 
 
+def _get(q, procs, timeout=900.0):
+    """q.get() that cannot hang: gives up when a worker died or the deadline passed (slow first `import torch` under load)"""
+    import time
+    t0 = time.time()
+    while q.empty():
+        dead = [p.exitcode for p in procs if p.exitcode not in (None, 0)]
+        assert not dead, "worker exited with %s" % dead
+        assert time.time() - t0 < timeout, "workers produced nothing within %.0f s" % timeout
+        time.sleep(0.05)
+    return q.get()
+
+
 def _worker(rank, world, port, alias, out_q):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -57,7 +69,9 @@ def _worker(rank, world, port, alias, out_q):
         shim._flat_grad = flat
     allreduce_gradients(shim)
     if rank == 0:
-        out_q.put({k: p.grad.clone() for k, p in zip(keys, params)})
+        # numpy, not torch tensors: tensors travel as shared-memory handles served by THIS process, which may have exited
+        # before the parent unpickles them (FileNotFoundError on the handle listener)
+        out_q.put({k: p.grad.detach().numpy().copy() for k, p in zip(keys, params)})
     dist.barrier()
     dist.destroy_process_group()
 
@@ -72,9 +86,9 @@ def test_two_rank_gradients_equal_full_batch(alias):
     procs = [ctx.Process(target=_worker, args=(r, 2, port, alias, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get()
+    got = _get(q, procs)
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=900)
         assert p.exitcode == 0
     cfg = model_config("TINY", dropout=0.0)
     full = make_batch(cfg, 8, seed=3)
@@ -84,7 +98,7 @@ def test_two_rank_gradients_equal_full_batch(alias):
     F.cross_entropy(logits, full["y"]).backward()
     ref = dict(oracle.named_parameters())
     for k in used_param_keys(cfg):
-        assert torch.allclose(got[k], ref[k].grad, rtol=1e-4, atol=1e-7), k
+        assert torch.allclose(torch.from_numpy(got[k]), ref[k].grad, rtol=1e-4, atol=1e-7), k
 
 
 def _eval_worker(rank, world, port, out_q):
@@ -105,7 +119,7 @@ def _eval_worker(rank, world, port, out_q):
     P, Pt = torch.randn(5, 11, 4, generator=g), torch.rand(5, 11, generator=g)
     out = evaluate_sharded(Stub(), P, None, Pt)
     if rank == 0:
-        out_q.put(out)
+        out_q.put(out.detach().numpy().copy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -118,11 +132,12 @@ def test_sharded_evaluation_gathers_the_whole_set_in_order():
     procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, q)) for r in range(2)]
     for p in procs:
         p.start()
-    got = q.get()
+    got = _get(q, procs)
     for p in procs:
-        p.join(timeout=120)
+        p.join(timeout=900)
         assert p.exitcode == 0
     g = torch.Generator().manual_seed(0)
     P, Pt = torch.randn(5, 11, 4, generator=g), torch.rand(5, 11, generator=g)
     feat = torch.stack([P.sum((0, 2)), Pt.sum(0), (Pt > 0).sum(0).float()], 1)
+    got = torch.from_numpy(got)
     assert got.shape == (11, 2) and torch.allclose(got, feat @ torch.arange(6.0).view(3, 2), atol=1e-5)
