@@ -193,7 +193,6 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
-  const RngKey key = load_rng_key(p.drop_p > 0.f ? p.rng : nullptr);     // one read; in flight during the set-up
   const uint32_t QV = base, KP = base + 2u * TILE;
   const uint32_t bar = base + 4u * TILE;
   const uint32_t bar_qk = bar, bar_v = bar + 8, bar_s = bar + 16, bar_o = bar + 24, tmem_slot = bar + 32;
@@ -215,6 +214,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_fwd_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   pdl_wait();
+  const RngKey key = load_rng_key(p.drop_p > 0.f ? p.rng : nullptr);     // one read per thread (after the dependency wait: nothing global is touched before it)
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tO = tmem + 64;
   stamp(p, 0);
@@ -353,7 +353,6 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x / p.H, h = blockIdx.x - b * p.H;
-  const RngKey key = load_rng_key(p.drop_p > 0.f ? p.rng : nullptr);     // one read; in flight during the set-up
   constexpr uint32_t REG = 2u * TILE;                              // 48 KB: hi + lo image of one head slice
   const uint32_t R0 = base, R1 = base + REG, R2 = base + 2u * REG, R3 = base + 3u * REG;
   const uint32_t Pd = R0, Pd_lo = R0 + PT;                         // MN image
@@ -382,6 +381,7 @@ __global__ void __launch_bounds__(NTHR) attn_tc_bwd_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   pdl_wait();
+  const RngKey key = load_rng_key(p.drop_p > 0.f ? p.rng : nullptr);
   const uint32_t tmem = *tmem_slot_ptr;
   const uint32_t tS = tmem, tDP = tmem + 64, tDV = tmem + 128, tDQ = tmem + 224, tDK = tmem + 320;
   stamp(p, 0);

@@ -23,7 +23,10 @@ static unsigned long long g_launches = 0;
 unsigned long long launch_count() { return g_launches; }
 bool pdl_enabled() {
   static int v = -1;
-  if (v < 0) { const char* e = getenv("RD_PDL"); v = (e && e[0] == '1') ? 1 : 0; }   // measured: no gain inside a CUDA graph -> opt-in
+  // programmatic dependent launch: a kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) overlaps the tail
+  // of its predecessor; every kernel waits (griddepcontrol.wait) before it touches global memory.  0.539 -> 0.518 ms per
+  // P19 step inside the graph (it measured at no gain before the kernels were shortened).  RD_PDL=0 turns it off.
+  if (v < 0) { const char* e = getenv("RD_PDL"); v = (e && e[0] == '0') ? 0 : 1; }
   return v == 1;
 }
 int check_launch(const char* what) {
@@ -306,14 +309,14 @@ __global__ void layernorm_fwd_kernel(const float* __restrict__ x, const float* _
 }
 
 // The same with the row held in registers (ITERS float4 per lane, D % 4 == 0, D <= 128 * ITERS): one global read instead of
-// three, 128-bit accesses, two rows per warp in flight.
+// three, 128-bit accesses.
 template <int ITERS>
 __global__ void __launch_bounds__(256) layernorm_fwd_vec_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, long long rows, int D, float eps,
                                                                 float* __restrict__ y, float* __restrict__ stats) {
   pdl_launch_dependents();
   pdl_wait();
-  constexpr int RB = 2;
+  constexpr int RB = 1;      // one row per warp: more warps in flight beats fewer, fatter ones at these sizes
   const int lane = threadIdx.x & 31;
   const long long row0 = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * RB;
   float4 v[RB][ITERS];
@@ -847,7 +850,7 @@ int layernorm_fwd(const float* x, const float* gamma, const float* beta, int64_t
                   float* stats, cudaStream_t st) {
   const uintptr_t bits = reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(beta);
   if ((D & 3) == 0 && D <= 640 && (bits & 15) == 0) {
-    const unsigned blocks = (unsigned)ceil_div(rows, (int64_t)(TPB / 32) * 2);      // 8 warps x 2 rows per CTA
+    const unsigned blocks = (unsigned)ceil_div(rows, (int64_t)(TPB / 32));          // 8 warps, one row each
     if (D <= 128) launch_pdl(layernorm_fwd_vec_kernel<1>, dim3(blocks), dim3(TPB), 0, st, x, gamma, beta, (long long)rows, D, eps, y, stats);
     else if (D <= 256) launch_pdl(layernorm_fwd_vec_kernel<2>, dim3(blocks), dim3(TPB), 0, st, x, gamma, beta, (long long)rows, D, eps, y, stats);
     else launch_pdl(layernorm_fwd_vec_kernel<5>, dim3(blocks), dim3(TPB), 0, st, x, gamma, beta, (long long)rows, D, eps, y, stats);

@@ -534,10 +534,13 @@ __global__ void wgrad_reduce_kernel(const __grid_constant__ RGroup g) {
   }
   const float* src = r.partial + (long long)m * r.Nld + 4 * q;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int sp = 0; sp < r.nsplit; ++sp) {
-    const float4 t = __ldg(reinterpret_cast<const float4*>(src + sp * stride));
-    s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+  for (int sp0 = 0; sp0 < r.nsplit; sp0 += 8) {      // eight slabs in flight per round trip, summed in slab order
+    float4 t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      t[u] = sp0 + u < r.nsplit ? __ldg(reinterpret_cast<const float4*>(src + (sp0 + u) * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int u = 0; u < 8; ++u) { s.x += t[u].x; s.y += t[u].y; s.z += t[u].z; s.w += t[u].w; }
   }
   float* dst = r.dW + (long long)m * r.N + 4 * q;
   if ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
